@@ -1,0 +1,57 @@
+"""Synthetic problem data for benchmarks and tests.
+
+The reference's warm start comes from a crocoddyl whole-body DDP run that is not shipped
+(``wholeBody_to_centroidal_traj.npz``; src/centroidal_model.py:87,174).  The stand-in is a
+constant-velocity CoM reference with per-instance perturbations drawn from
+``numpy.random.default_rng(1000 + b)``.
+"""
+import importlib
+import types
+
+import numpy as np
+
+from .config import _robots
+
+_COM_HEIGHT = {"solo12_trot": _robots.SOLO12_COM_HEIGHT, "solo12_pace": _robots.SOLO12_COM_HEIGHT,
+               "solo12_bound": _robots.SOLO12_COM_HEIGHT, "bolt": _robots.BOLT_COM_HEIGHT,
+               "talos": _robots.TALOS_COM_HEIGHT}
+
+
+def load_conf(name, N=None):
+    """Copy of ``config/conf_<name>`` as a namespace, optionally windowed to the first N knots
+    (the contact plan is simply read for k < N; src/centroidal_model.py:132)."""
+    mod = importlib.import_module(".config.conf_" + name, package=__package__)
+    conf = types.SimpleNamespace(**{k: v for k, v in vars(mod).items() if not k.startswith("__")})
+    conf.name = name
+    if N is not None:
+        if N > conf.N:
+            raise ValueError("window N=%d exceeds the gait's horizon %d" % (N, conf.N))
+        conf.N = int(N)
+    return conf
+
+
+def reference_trajectory(conf, b=0, mode="B", v=0.1):
+    """(N+1, 9) warm-start / tracking trajectory for instance ``b``.
+
+    mode 'B' (independent instances): CoM offset N(0,(1 cm)^2) per axis constant in k and
+    angular-momentum noise N(0,(1e-3)^2) i.i.d. per knot.
+    mode 'A' (perturbed initial state only): the shared nominal trajectory; the caller
+    perturbs x_init (see ``perturbed_x_init``)."""
+    N, m, dt = conf.N, conf.robot_mass, conf.dt
+    k = np.arange(N + 1)
+    X = np.zeros((N + 1, 9))
+    X[:, 0] = v * dt * k
+    X[:, 2] = _COM_HEIGHT.get(conf.name, 0.23)
+    X[:, 3] = m * v
+    if mode == "B":
+        rng = np.random.default_rng(1000 + b)
+        X[:, 0:3] += rng.normal(0.0, 0.01, size=3)[None, :]
+        X[:, 6:9] += rng.normal(0.0, 1e-3, size=(N + 1, 3))
+    return X
+
+
+def perturbed_x_init(conf, b):
+    """mode 'A' initial-state perturbation: N(0, diag(1 cm, 0.05 kg m/s, 0.01 kg m^2/s)^2)."""
+    rng = np.random.default_rng(1000 + b)
+    sig = np.array([0.01] * 3 + [0.05] * 3 + [0.01] * 3)
+    return reference_trajectory(conf, 0, mode="A")[0] + rng.normal(0.0, 1.0, size=9) * sig
