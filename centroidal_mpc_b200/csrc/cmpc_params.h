@@ -1,0 +1,59 @@
+// cmpc_params.h — host-side translation of the C-ABI structs (include/cmpc.h) into the
+// solver's Params.  Shared by the CUDA library and by the test-only host build (tests/emu).
+#pragma once
+#include "../../include/cmpc.h"
+#include "cmpc_core.cuh"
+
+namespace cmpc {
+
+inline void default_qp_settings(cmpc_qp_settings* s) {
+  s->eps_abs = 1e-7;            // scp_solver.py:63
+  s->eps_rel = 1e-7;
+  s->sigma = 1e-6;              // OSQP default
+  s->alpha = 1.6;               // OSQP default
+  s->rho = 3.0;                 // initial penalty in equilibrated units
+  s->delta = 1e-6;              // OSQP polish regularisation
+  s->adaptive_rho_tolerance = 5.0;
+  s->max_iter = 4000;           // OSQP default
+  s->check_termination = 25;    // OSQP default
+  s->polish = 1;                // scp_solver.py:63
+  s->polish_refine_iter = 3;    // OSQP default
+  s->adaptive_rho = 1;
+}
+
+inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const cmpc_scp_params* scp,
+                       const cmpc_qp_settings* qp, int identity_R) {
+  if (d->N < 1 || d->nc < 1 || d->nc > MAXC || d->batch < 0) return -1;
+  cmpc_qp_settings dq;
+  if (!qp) { default_qp_settings(&dq); qp = &dq; }
+  p->N = d->N; p->nc = d->nc; p->nu = 3 * d->nc; p->identity_R = identity_R;
+  p->m = m->robot_mass; p->g = m->gravity_constant; p->dt = m->dt; p->mu = m->mu;
+  for (int i = 0; i < NX; ++i) p->Wx[i] = m->state_cost_weights[i];
+  for (int i = 0; i < MAXU; ++i) p->Wu[i] = i < p->nu ? m->control_cost_weights[i] : 1.0;
+  for (int i = 0; i < NX; ++i) if (!(p->Wx[i] > 0.0)) return -2;
+  for (int i = 0; i < p->nu; ++i) if (!(p->Wu[i] > 0.0)) return -2;
+  p->sigma = qp->sigma; p->alpha = qp->alpha; p->rho0 = qp->rho; p->eps_abs = qp->eps_abs;
+  p->eps_rel = qp->eps_rel; p->delta = qp->delta; p->adapt_tol = qp->adaptive_rho_tolerance;
+  p->rho_e_rel = 100.0; p->rho_k_rel = 1.0;
+  p->max_iter = qp->max_iter; p->check_every = qp->check_termination > 0 ? qp->check_termination : 25;
+  p->polish = qp->polish; p->refine = qp->polish_refine_iter; p->adaptive_rho = qp->adaptive_rho;
+  if (scp) {
+    p->radius0 = scp->trust_region_radius0; p->omega0 = scp->omega0; p->omega_max = scp->omega_max;
+    p->acc_rho0 = scp->rho0; p->acc_rho1 = scp->rho1; p->beta_succ = scp->beta_succ;
+    p->beta_fail = scp->beta_fail; p->gamma_fail = scp->gamma_fail;
+    p->conv_thresh = scp->convergence_threshold; p->max_scp = scp->max_iterations;
+  }
+  return 0;
+}
+
+// workspace sizes in doubles / ints for a batch
+struct WsSizes { long stg, sta, sta2, fac, dvec, pol, pmask, info; };
+inline WsSizes ws_sizes(int B, int N) {
+  WsSizes w;
+  w.stg = (long)B * (N + 1) * STG; w.sta = (long)B * (N + 1) * STA; w.sta2 = w.sta;
+  w.fac = (long)B * N * FAC; w.dvec = (long)B * N * DVC; w.pol = (long)B * (N + 1) * POL;
+  w.pmask = (long)B * (N + 1); w.info = (long)B * 8;
+  return w;
+}
+
+}  // namespace cmpc

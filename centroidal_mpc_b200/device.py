@@ -1,0 +1,173 @@
+"""Device side of the host package: torch tensors as the batch container, raw device pointers
+into libcmpc_b200.so (include/cmpc.h).  No arithmetic of the hot path happens in Python/torch;
+without the CUDA library or without a GPU every entry point raises."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .batch import ProblemBatch
+
+
+def _torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise L.CmpcError("no CUDA device: the SCP hot path runs only on the GPU (there is no CPU fallback)")
+    return torch
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchSolver:
+    """Owns a cmpc handle (solver workspace) for a fixed (B, N, nc) and the device copies of one
+    ProblemBatch.  ``solve`` runs solve_scp for all instances on the current stream."""
+
+    def __init__(self, batch, device=None):
+        torch = _torch_cuda()
+        self.lib = L.load()
+        self.batch = batch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dims = L.cmpc_dims(batch.B, batch.N, batch.nc, 1 if batch.shared_plan else 0)
+        self.model = L.make_model_struct(batch.proto)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.cmpc_create(C.byref(self.dims), C.byref(self.handle)), self.lib)
+        B, N, nu = batch.B, batch.N, batch.nu
+        f64 = torch.float64
+        self.X = torch.empty((B, N + 1, 9), dtype=f64, device=self.device)
+        self.U = torch.empty((B, N, nu), dtype=f64, device=self.device)
+        self.ints = torch.zeros((5, B), dtype=torch.int32, device=self.device)
+        self.info = torch.zeros((B, 8), dtype=f64, device=self.device)
+        self.d = {}
+        self.upload(batch)
+
+    def upload(self, batch):
+        """Host -> device copy of the problem data and (re)binding of the pointers."""
+        torch = _torch_cuda()
+        for name in ("x_init", "x_final", "X_ref", "U_init", "contact_pos", "contact_R", "contact_active"):
+            a = getattr(batch, name)
+            self.d[name] = None if a is None else torch.from_numpy(a).to(self.device, non_blocking=True)
+        d = self.d
+        L.check(self.lib.cmpc_set_problem(self.handle, C.byref(self.model), _ptr(d["x_init"]), _ptr(d["x_final"]),
+                                          _ptr(d["X_ref"]), _ptr(d["U_init"]), _ptr(d["contact_pos"]),
+                                          _ptr(d["contact_R"]), _ptr(d["contact_active"])), self.lib)
+
+    def solve(self, scp_params, qp_overrides=None, stream=None):
+        torch = _torch_cuda()
+        scp = L.make_scp_struct(scp_params)
+        qp = L.make_qp_struct(qp_overrides, self.lib)
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        with torch.cuda.device(self.device):
+            L.check(self.lib.cmpc_solve_scp(self.handle, C.byref(scp), C.byref(qp), _ptr(self.X), _ptr(self.U),
+                                            _ptr(self.ints[0]), _ptr(self.ints[1]), _ptr(self.ints[2]),
+                                            C.c_void_p(st)), self.lib)
+        return self
+
+    def stats(self):
+        L.check(self.lib.cmpc_get_stats(self.handle, _ptr(self.ints[3]), _ptr(self.ints[4]), _ptr(self.info)),
+                self.lib)
+        return dict(qp_iters=self.ints[3].cpu().numpy(), n_factor=self.ints[4].cpu().numpy(),
+                    info=self.info.cpu().numpy())
+
+    def results(self):
+        """Device -> host: dict of numpy arrays."""
+        ints = self.ints.cpu().numpy()
+        return dict(X=self.X.cpu().numpy(), U=self.U.cpu().numpy(), scp_iters=ints[0], status=ints[1],
+                    n_accepted=ints[2])
+
+    def solve_host(self, scp_params, qp_overrides=None, out=None):
+        """End-to-end call with HOST buffers (cmpc_solve_scp_host): H2D, solve, D2H, sync."""
+        b = self.batch
+        B, N, nu = b.B, b.N, b.nu
+        if out is None:
+            out = dict(X=np.empty((B, N + 1, 9)), U=np.empty((B, N, nu)), scp_iters=np.empty(B, np.int32),
+                       status=np.empty(B, np.int32), n_accepted=np.empty(B, np.int32))
+        scp = L.make_scp_struct(scp_params)
+        qp = L.make_qp_struct(qp_overrides, self.lib)
+
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+        torch = _torch_cuda()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.cmpc_solve_scp_host(self.handle, C.byref(self.model), C.byref(scp), C.byref(qp),
+                                                 p(b.x_init), p(b.x_final), p(b.X_ref), p(b.U_init),
+                                                 p(b.contact_pos), p(b.contact_R), p(b.contact_active),
+                                                 p(out["X"]), p(out["U"]), p(out["scp_iters"]), p(out["status"]),
+                                                 p(out["n_accepted"])), self.lib)
+        return out
+
+    def close(self):
+        if self.handle:
+            self.lib.cmpc_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# Centroidal_model method wrappers (src/centroidal_model.py:189-291 of the reference)
+# ---------------------------------------------------------------------------------------------
+def _lin_call(model, X, U, want_jac):
+    torch = _torch_cuda()
+    lib = L.load()
+    prob = model.problem_arrays()
+    N, nc = prob["N"], prob["contact_active"].shape[1]
+    nu = 3 * nc
+    if prob["robot"] == "TALOS":
+        raise NotImplementedError("TALOS contact model: SURVEY.md section 8 row f4 (next)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Xd = torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float64).T[None])).to(dev)
+    Ud = torch.from_numpy(np.ascontiguousarray(np.asarray(U, dtype=np.float64).T[None])).to(dev)
+    cp = torch.from_numpy(np.ascontiguousarray(prob["contact_pos"][None])).to(dev)
+    ca = torch.from_numpy(np.ascontiguousarray(prob["contact_active"][None].astype(np.int32))).to(dev)
+    dims = L.cmpc_dims(1, N, nc, 1)
+    mdl = L.make_model_struct(prob)
+    f = torch.empty((1, N, 9), dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if want_jac:
+        fx = torch.empty((1, N, 9, 9), dtype=torch.float64, device=dev)
+        fu = torch.empty((1, N, 9, nu), dtype=torch.float64, device=dev)
+        L.check(lib.cmpc_linearize(C.byref(dims), C.byref(mdl), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca), _ptr(f),
+                                   _ptr(fx), _ptr(fu), st), lib)
+        return f[0].cpu().numpy(), fx[0].cpu().numpy(), fu[0].cpu().numpy()
+    L.check(lib.cmpc_rollout(C.byref(dims), C.byref(mdl), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca), _ptr(f), st), lib)
+    return f[0].cpu().numpy()
+
+
+def compute_trajectory_data(model, traj_tuple):
+    """dict(dynamics (9,N), gradients{f_x (N,9,9), f_u (N,9,nu)}) like the reference's
+    compute_trajectory_data; LQR gains / covariances are SURVEY.md section 8 row f1 (next)."""
+    f, fx, fu = _lin_call(model, traj_tuple["state"], traj_tuple["control"], True)
+    return dict(dynamics=f.T.copy(), gradients={"f_x": fx, "f_u": fu}, LQR_gains=None, Covs=None)
+
+
+def integrate_dynamics_trajectory(model, traj_tuple):
+    """(9, N+1) array of one-step predictions; the last column (never read by the reference,
+    scp_solver.py:82-86) repeats column N-1."""
+    f = _lin_call(model, traj_tuple["state"], traj_tuple["control"], False).T
+    return np.concatenate([f, f[:, -1:]], axis=1)
+
+
+def integrate_one_step(model, x, u, contacts_position_all, contacts_logic_all, contacts_orientation_all):
+    torch = _torch_cuda()
+    lib = L.load()
+    prob = model.problem_arrays()
+    nc = prob["contact_active"].shape[1]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    X = np.zeros((1, 2, 9)); X[0, 0] = np.asarray(x, dtype=np.float64)
+    Xd = torch.from_numpy(X).to(dev)
+    Ud = torch.from_numpy(np.asarray(u, dtype=np.float64).reshape(1, 1, -1).copy()).to(dev)
+    cp = torch.from_numpy(np.asarray(contacts_position_all, dtype=np.float64).reshape(1, 1, nc, 3).copy()).to(dev)
+    ca = torch.from_numpy(np.asarray(contacts_logic_all).astype(np.int32).reshape(1, 1, nc).copy()).to(dev)
+    dims = L.cmpc_dims(1, 1, nc, 1)
+    mdl = L.make_model_struct(prob)
+    f = torch.empty((1, 1, 9), dtype=torch.float64, device=dev)
+    L.check(lib.cmpc_rollout(C.byref(dims), C.byref(mdl), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca), _ptr(f),
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), lib)
+    return f[0, 0].cpu().numpy()

@@ -1,0 +1,74 @@
+"""``solve_scp`` — the reference's entry point (/root/reference/src/scp_solver.py:118-179) on
+top of the CUDA library, plus the batched entry ``solve_scp_batched``.
+
+The whole loop — linearisation (compute_trajectory_data), QP assembly (sum_up_all_costs,
+stack_up_all_constraints), the QP solve (solve_subproblem), get_QP_solution, the spectral-norm
+trust test, compute_model_accuracy and the radius/weight updates — runs inside one kernel per
+batch (csrc/cmpc_api.cu: cmpc_scp_kernel); Python only packs inputs and unpacks outputs.
+"""
+from warnings import warn
+
+import numpy as np
+
+from ..batch import ProblemBatch
+
+
+def solve_scp_batched(batch_or_models, scp_params, qp_settings=None, solver=None, return_stats=False):
+    """Solve B independent SCP problems.  Returns dict(X [B,N+1,9], U [B,N,nu], scp_iters [B],
+    status [B], n_accepted [B]) as numpy arrays (plus solver statistics when asked).
+    ``status != 0`` marks instances for which the reference would return False (QP failure);
+    ``n_accepted == 0`` marks instances for which it would return empty lists."""
+    from ..device import BatchSolver
+    batch = batch_or_models if isinstance(batch_or_models, ProblemBatch) else ProblemBatch(list(batch_or_models))
+    own = solver is None
+    if own:
+        solver = BatchSolver(batch)
+    try:
+        solver.solve(scp_params, qp_settings)
+        out = solver.results()
+        if return_stats:
+            out.update(solver.stats())
+    finally:
+        if own:
+            solver.close()
+    return out
+
+
+def solve_scp(model, scp_params):
+    """Drop-in for the reference's solve_scp(model, scp_params): returns
+    dict(state=[X (9,N+1)], control=[U (n_u,N)], gains=[...], covs=[...]) with one entry per
+    accepted SCP iteration, empty lists if nothing was accepted, or False when a QP subproblem
+    failed (scp_solver.py:146-148)."""
+    out = solve_scp_batched([model], scp_params)
+    if int(out["status"][0]) != 0:
+        warn("[solve_OSQP]: Problem unfeasible.")
+        return False
+    all_solution = dict(state=[], control=[], gains=[], covs=[])
+    # the linearisation point never moves (scp_solver.py:129-130), so every accepted iterate
+    # solves the same QP; the last accepted one is what the kernel returns
+    for _ in range(int(out["n_accepted"][0])):
+        all_solution["state"].append(out["X"][0].T.copy())
+        all_solution["control"].append(out["U"][0].T.copy())
+        all_solution["gains"].append(None)     # LQR gains / covariances: SURVEY.md section 8 f1 (next)
+        all_solution["covs"].append(None)
+    return all_solution
+
+
+def get_QP_solution(model, z):
+    """Column-major unpack of a reference-ordered decision vector (scp_solver.py:89-93)."""
+    n_x, n_u, N = model._n_x, model._n_u, model._N
+    X_sol = np.reshape(z[:n_x * (N + 1)], (n_x, N + 1), order="F")
+    U_sol = np.reshape(z[n_x * (N + 1):n_x * (N + 1) + n_u * N], (n_u, N), order="F")
+    return dict(state=X_sol, control=U_sol)
+
+
+def interpolate_SCP_solution(solution):
+    """Linear x10 up-sampling of the last accepted (X, U) (scp_solver.py:95-111), vectorised."""
+    N_inner = 10
+    X, U = solution["state"][-1], solution["control"][-1]
+    frac = np.arange(N_inner) / float(N_inner)
+
+    def up(M):
+        seg = M[:, :-1, None] + (M[:, 1:, None] - M[:, :-1, None]) * frac[None, None, :]
+        return seg.reshape(M.shape[0], -1)
+    return dict(X=up(X), U=up(U))

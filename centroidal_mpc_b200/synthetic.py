@@ -55,3 +55,21 @@ def perturbed_x_init(conf, b):
     rng = np.random.default_rng(1000 + b)
     sig = np.array([0.01] * 3 + [0.05] * 3 + [0.01] * 3)
     return reference_trajectory(conf, 0, mode="A")[0] + rng.normal(0.0, 1.0, size=9) * sig
+
+
+def make_batch(conf, B, mode="B", first=0):
+    """ProblemBatch of B synthetic instances sharing the contact plan of ``conf``.
+
+    mode 'B': independent reference trajectories (every instance has its own linearisation);
+    mode 'A': one shared reference, only x_init perturbed (BASELINE.json config 2)."""
+    from .batch import ProblemBatch
+    from .src.centroidal_model import Centroidal_model
+    proto_model = Centroidal_model(conf, centroidal_traj=reference_trajectory(conf, first, mode=mode))
+    proto = proto_model.problem_arrays()
+    X_ref = np.stack([reference_trajectory(conf, first + b, mode=mode) for b in range(B)])   # [B,N+1,9]
+    U_init = np.broadcast_to(proto["U_init"].T[None], (B,) + proto["U_init"].T.shape).copy()
+    x_init = X_ref[:, 0].copy()
+    x_final = X_ref[:, -1].copy()
+    if mode == "A":
+        x_init = np.stack([perturbed_x_init(conf, first + b) for b in range(B)])
+    return ProblemBatch.from_arrays(proto, x_init, x_final, X_ref, U_init)

@@ -1,0 +1,124 @@
+/* cmpc.h — C ABI of libcmpc_b200.so, the B200 (sm_100a) SCP hot path of ahmadgazar/centroidal-MPC.
+ *
+ * The reference has no FFI: its hot path is Python calling JAX (XLA) and OSQP (C).  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference
+ * repository root).  Plain C types only; every array is a raw pointer + the sizes in cmpc_dims.
+ * Unless a function says "host", pointers are DEVICE pointers owned by the caller (e.g.
+ * torch.Tensor.data_ptr()); the library allocates only its workspace, inside cmpc_create.
+ *
+ * Array layouts (row-major, instance-major; B = batch, N = horizon, nc = contacts, nu = 3*nc):
+ *   x_init, x_final   [B][9]        (src/centroidal_model.py:87-89)
+ *   X_ref             [B][N+1][9]   model._init_trajectories['state'] transposed (:174,:185)
+ *   U_init            [B][N][nu]    model._init_trajectories['control'] transposed (:176-186)
+ *   contact_pos       [Bp][N][nc][3]   model._contact_data['contacts_position'] (:127-156)
+ *   contact_R         [Bp][N][nc][3][3] model._contact_data['contacts_orient']; NULL = identity
+ *   contact_active    [Bp][N][nc]   int32, model._contact_data['contacts_logic']
+ *       Bp = 1 when dims.shared_plan != 0 (one contact plan for the whole batch), else B
+ *   X_out             [B][N+1][9]   last accepted state trajectory  (all_solution['state'][-1].T)
+ *   U_out             [B][N][nu]    last accepted control trajectory (all_solution['control'][-1].T)
+ *
+ * Return value: 0 on success, negative on a usage / CUDA error (message via cmpc_last_error()).
+ * Per-instance solver outcomes are reported in status[] and never through the return value.
+ */
+#ifndef CMPC_H
+#define CMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmpc_handle_s* cmpc_handle;
+
+typedef struct {
+  int32_t batch;        /* B  */
+  int32_t N;            /* horizon (knots of control) */
+  int32_t nc;           /* contacts: 4 (solo12) or 2 (bolt); point-contact model, n_u = 3*nc */
+  int32_t shared_plan;  /* 1: contact arrays have leading dimension 1 */
+} cmpc_dims;
+
+/* conf attributes copied by Centroidal_model.__init__ (src/centroidal_model.py:27-32) */
+typedef struct {
+  double robot_mass, gravity_constant, dt, mu;
+  double state_cost_weights[9];     /* diagonal of conf.state_cost_weights   */
+  double control_cost_weights[12];  /* diagonal of conf.control_cost_weights */
+} cmpc_model;
+
+/* conf.scp_params, keys read at src/scp_solver.py:120-128 */
+typedef struct {
+  double trust_region_radius0, omega0, omega_max, rho0, rho1;
+  double beta_succ, beta_fail, gamma_fail, convergence_threshold;
+  int32_t max_iterations;
+} cmpc_scp_params;
+
+/* QP settings; the defaults reproduce the reference's OSQP call (src/scp_solver.py:61-63:
+ * eps_abs = eps_rel = 1e-7, polish on) with OSQP's own defaults for the rest. */
+typedef struct {
+  double eps_abs, eps_rel, sigma, alpha, rho, delta, adaptive_rho_tolerance;
+  int32_t max_iter, check_termination, polish, polish_refine_iter, adaptive_rho;
+} cmpc_qp_settings;
+
+/* status[] values */
+enum { CMPC_OK = 0, CMPC_QP_MAX_ITER = 1, CMPC_QP_NUMERIC = 2 };
+
+void cmpc_default_qp_settings(cmpc_qp_settings* s);
+
+/* Allocates the per-batch solver workspace on the current CUDA device. */
+int cmpc_create(const cmpc_dims* dims, cmpc_handle* out);
+int cmpc_destroy(cmpc_handle h);
+int64_t cmpc_workspace_bytes(cmpc_handle h);
+
+/* Binds problem data (device pointers are kept, not copied).
+ * Replaces Centroidal_model construction as seen by the solver: src/centroidal_model.py:15-47. */
+int cmpc_set_problem(cmpc_handle h, const cmpc_model* model, const double* x_init, const double* x_final,
+                     const double* X_ref, const double* U_init, const double* contact_pos,
+                     const double* contact_R, const int32_t* contact_active);
+
+/* solve_scp(model, scp_params) for the whole batch: src/scp_solver.py:118-179, including
+ * compute_trajectory_data (src/centroidal_model.py:257-291), the QP assembly
+ * (src/cost.py:9-39, src/constraints.py:12-50,104-109,153-185,260-293), the OSQP solve
+ * (src/scp_solver.py:59-68) and the trust-region logic.  Asynchronous on `stream`
+ * (a cudaStream_t, may be NULL); no host synchronisation inside.
+ * scp_iters[b]: SCP iterations executed; status[b]: CMPC_OK, or the QP failure that makes the
+ * reference return False (:146-148).  n_accepted (nullable): accepted solutions (0 => the
+ * reference returns empty lists, :119,:179). */
+int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
+                   double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, void* stream);
+
+/* Same with HOST buffers: copies inputs to the device, solves, copies the results back and
+ * synchronises.  This is the end-to-end call a host-side caller of solve_scp would make. */
+int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_params* scp,
+                        const cmpc_qp_settings* qp, const double* x_init, const double* x_final,
+                        const double* X_ref, const double* U_init, const double* contact_pos,
+                        const double* contact_R, const int32_t* contact_active, double* X_out,
+                        double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted);
+
+/* Per-instance statistics of the last solve (device pointers, each nullable):
+ * qp_iters[B] total ADMM iterations, n_factor[B] Riccati factorisations, info[B][8] =
+ * {sigma_max(X-Xbar), accuracy ratio, primal res, dual res, rho, radius, weight, polished}. */
+int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info);
+
+/* compute_trajectory_data (src/centroidal_model.py:257-291): f, A=df/dx, B=df/du along (X,U).
+ * X [B][N+1][9], U [B][N][nu] -> f [B][N][9], fx [B][N][9][9], fu [B][N][9][nu]. */
+int cmpc_linearize(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,
+                   const double* contact_pos, const int32_t* contact_active, double* f, double* fx,
+                   double* fu, void* stream);
+
+/* integrate_dynamics_trajectory (src/centroidal_model.py:243-255): f(x_k,u_k), k < N -> f [B][N][9]. */
+int cmpc_rollout(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,
+                 const double* contact_pos, const int32_t* contact_active, double* f, void* stream);
+
+/* DFMA micro-benchmark on the current device: achieved FP64 TFLOP/s and the SM clock (MHz) seen. */
+int cmpc_fp64_peak(double* tflops, double* ms);
+
+/* Counts kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t cmpc_launch_count(void);
+
+const char* cmpc_last_error(void);
+const char* cmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMPC_H */

@@ -1,0 +1,56 @@
+"""ctypes access to the TEST-ONLY host build of the device solver (tests/emu/cmpc_emu.cpp).
+Used by the CPU test-suite to exercise the kernel logic without a GPU; never imported by the
+product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from centroidal_mpc_b200 import _lib as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "emu", "cmpc_emu.cpp")
+_SO = os.path.join(_HERE, "emu", "libcmpc_emu.so")
+_DEPS = [os.path.join(_HERE, "..", "centroidal_mpc_b200", "csrc", f)
+         for f in ("cmpc_core.cuh", "cmpc_solver.cuh", "cmpc_params.h")] + [_SRC]
+_lib = None
+
+
+def build(force=False):
+    newest = max(os.path.getmtime(f) for f in _DEPS)
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", _SO, _SRC])
+    return _SO
+
+
+def load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def solve_scp(batch, scp_params, qp_overrides=None):
+    """Run the host build of the device solver on a ProblemBatch; returns a dict of arrays."""
+    lib = load()
+    B, N, nu = batch.B, batch.N, batch.nu
+    dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0)
+    model = L.make_model_struct(batch.proto)
+    scp = L.make_scp_struct(scp_params)
+    qp = L.make_qp_struct(qp_overrides)
+    out = dict(X=np.zeros((B, N + 1, 9)), U=np.zeros((B, N, nu)), scp_iters=np.zeros(B, np.int32),
+               status=np.zeros(B, np.int32), n_accepted=np.zeros(B, np.int32),
+               qp_iters=np.zeros(B, np.int32), n_factor=np.zeros(B, np.int32), info=np.zeros((B, 8)))
+    rc = lib.cmpc_emu_solve_scp(C.byref(dims), C.byref(model), C.byref(scp), C.byref(qp), _p(batch.x_init),
+                                _p(batch.x_final), _p(batch.X_ref), _p(batch.U_init), _p(batch.contact_pos),
+                                _p(batch.contact_R), _p(batch.contact_active), _p(out["X"]), _p(out["U"]),
+                                _p(out["scp_iters"]), _p(out["status"]), _p(out["n_accepted"]),
+                                _p(out["qp_iters"]), _p(out["n_factor"]), _p(out["info"]))
+    if rc != 0:
+        raise RuntimeError("cmpc_emu_solve_scp returned %d" % rc)
+    return out
