@@ -56,8 +56,8 @@ struct Params {
   double m, g, dt, mu;
   double Wx[NX], Wu[MAXU];
   // QP solver settings (OSQP's where they have the same meaning; scp_solver.py:61-63)
-  double sigma, alpha, rho0, eps_abs, eps_rel, delta, adapt_tol, rho_e_rel, rho_k_rel;
-  int max_iter, check_every, polish, refine, adaptive_rho;
+  double sigma, alpha, rho0, eps_abs, eps_rel, delta, adapt_tol, rho_e_rel, rho_k_rel, rho_e_pol_rel;
+  int max_iter, check_every, polish, refine, adaptive_rho, adapt_start, polish_rounds;
   // SCP parameters (scp_solver.py:120-128)
   double radius0, omega0, omega_max, acc_rho0, acc_rho1, beta_succ, beta_fail, gamma_fail, conv_thresh;
   int max_scp;
@@ -118,7 +118,7 @@ struct WarpMem {
 
 // scalars in WarpMem::sc
 enum { SC_RHO = 0, SC_RADIUS, SC_WEIGHT, SC_PRI, SC_DUA, SC_NPRI, SC_NDUA, SC_NUM, SC_DEN, SC_SNORM,
-       SC_RHOE, SC_RHOK, SC_SIG };
+       SC_RHOE, SC_RHOK, SC_RHOEP };
 
 struct Ctx {
   const Params* prm;
@@ -184,12 +184,9 @@ CMPC_HD void linearize_knot(const Params& P, const double* xbar, const double* u
                             const int* cact, int k, double* rec) {
   // q = -Wx xbar  (cost.py:21-29; the tracking reference IS the linearisation point)
   for (int i = 0; i < NX; ++i) rec[O_Q + i] = -P.Wx[i] * xbar[i];
-  for (int i = 0; i < 3; ++i) rec[O_KB + i] = xbar[6 + i];
   for (int i = O_C; i < STG; ++i) rec[i] = 0.0;
-  if (k == P.N) {   // terminal knot: no dynamics, no controls
-    for (int i = 0; i < 3; ++i) rec[O_KB + i] = xbar[6 + i];
-    return;
-  }
+  for (int i = 0; i < 3; ++i) rec[O_KB + i] = xbar[6 + i];
+  if (k == P.N) return;   // terminal knot: no dynamics, no controls
   double S[3] = {0.0, 0.0, 0.0};
   int mask = 0;
   for (int c = 0; c < P.nc; ++c) {

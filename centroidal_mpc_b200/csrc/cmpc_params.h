@@ -11,7 +11,7 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
   s->eps_rel = 1e-7;
   s->sigma = 1e-6;              // OSQP default
   s->alpha = 1.6;               // OSQP default
-  s->rho = 3.0;                 // initial penalty in equilibrated units
+  s->rho = 2.0;                 // initial penalty in equilibrated units
   s->delta = 1e-6;              // OSQP polish regularisation
   s->adaptive_rho_tolerance = 5.0;
   s->max_iter = 4000;           // OSQP default
@@ -19,6 +19,8 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
   s->polish = 1;                // scp_solver.py:63
   s->polish_refine_iter = 3;    // OSQP default
   s->adaptive_rho = 1;
+  s->polish_active_set_rounds = 2;   // extra polish rounds with a corrected active set
+  s->adaptive_rho_start = 200;  // early residuals are transient: adapting on them hurts
 }
 
 inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const cmpc_scp_params* scp,
@@ -35,8 +37,11 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   p->sigma = qp->sigma; p->alpha = qp->alpha; p->rho0 = qp->rho; p->eps_abs = qp->eps_abs;
   p->eps_rel = qp->eps_rel; p->delta = qp->delta; p->adapt_tol = qp->adaptive_rho_tolerance;
   p->rho_e_rel = 100.0; p->rho_k_rel = 1.0;
+  p->rho_e_pol_rel = 1e4;   // terminal-equality penalty while polishing (x max W_x), DESIGN.md
   p->max_iter = qp->max_iter; p->check_every = qp->check_termination > 0 ? qp->check_termination : 25;
   p->polish = qp->polish; p->refine = qp->polish_refine_iter; p->adaptive_rho = qp->adaptive_rho;
+  p->adapt_start = qp->adaptive_rho_start;
+  p->polish_rounds = qp->polish_active_set_rounds;
   if (scp) {
     p->radius0 = scp->trust_region_radius0; p->omega0 = scp->omega0; p->omega_max = scp->omega_max;
     p->acc_rho0 = scp->rho0; p->acc_rho1 = scp->rho1; p->beta_succ = scp->beta_succ;

@@ -83,6 +83,22 @@ CMPC_HD void fill_G_phase(Ctx& c, int k) {
   }
 }
 
+
+// value of friction row (ct,row) at knot k for control vector u (full layout): G_row . f_ct
+CMPC_HD double friction_row_value(const Ctx& c, int k, int ct, int row, const double* u) {
+  const Params& P = *c.prm;
+  const double kf = P.mu * 0.70710678118654752440;
+  const double pr[3] = {row == 0 ? 1.0 : (row == 1 ? -1.0 : 0.0), row == 2 ? 1.0 : (row == 3 ? -1.0 : 0.0), -kf};
+  double cf = 0.0;
+  if (P.identity_R) {
+    for (int a = 0; a < 3; ++a) cf += pr[a] * u[3 * ct + a];
+  } else {
+    const double* R = c.cR + ((long)k * P.nc + ct) * 9;
+    for (int a = 0; a < 3; ++a) cf += (pr[0] * R[a * 3] + pr[1] * R[a * 3 + 1] + pr[2] * R[a * 3 + 2]) * u[3 * ct + a];
+  }
+  return cf;
+}
+
 // ---------------------------------------------------------------- per-knot penalty/linear terms
 // Fills rrow/lrow (friction rows) and kM/kl (kappa block) for knot k from the loaded records
 // s.stg / s.sta (ADMM) or the polish records.  One phase; caller syncs.
@@ -155,7 +171,7 @@ CMPC_HD int factor(Ctx& c, int mode) {
   WarpMem& s = *c.s;
   const int N = P.N;
   const double sg = (mode == MODE_ADMM) ? P.sigma : P.delta;
-  const double rho_e = (mode == MODE_ADMM) ? s.sc[SC_RHOE] : 1.0 / P.delta;
+  const double rho_e = (mode == MODE_ADMM) ? s.sc[SC_RHOE] : s.sc[SC_RHOEP];
   // terminal knot: P = Q_N + rho_e I
   CMPC_COPY(s.stg, c.stg + (long)N * STG, STG);
   CMPC_COPY(s.sta, c.sta + (long)N * STA, STA);
@@ -286,7 +302,7 @@ CMPC_HD void backward_sweep(Ctx& c, int mode) {
   WarpMem& s = *c.s;
   const int N = P.N;
   const double sg = (mode == MODE_ADMM) ? P.sigma : P.delta;
-  const double rho_e = (mode == MODE_ADMM) ? s.sc[SC_RHOE] : 1.0 / P.delta;
+  const double rho_e = (mode == MODE_ADMM) ? s.sc[SC_RHOE] : s.sc[SC_RHOEP];
   const double* xf = c.bt.x_final + (long)c.b * 9;
   CMPC_COPY(s.stg, c.stg + (long)N * STG, STG);
   CMPC_COPY(s.sta, c.sta + (long)N * STA, STA);
@@ -405,7 +421,7 @@ CMPC_HD void forward_sweep(Ctx& c, int mode) {
         }
       } else if (l == 26 && k == N) {
         // terminal equality: w_e = x_final;  y_e += rho_e (al x~ + (1-al) x_f - x_f)
-        const double re = (mode == MODE_ADMM) ? s.sc[SC_RHOE] : inv;
+        const double re = (mode == MODE_ADMM) ? s.sc[SC_RHOE] : s.sc[SC_RHOEP];
         for (int i = 0; i < 9; ++i) s.ye[i] += re * al * (xa[i] - xf[i]);
       }
     }
@@ -591,6 +607,7 @@ CMPC_HD void set_rho(Ctx& c, double rho) {
       s.sc[SC_RHO] = rho;
       s.sc[SC_RHOK] = rho * P.rho_k_rel * wk;
       s.sc[SC_RHOE] = P.rho_e_rel * wm;
+      s.sc[SC_RHOEP] = P.rho_e_pol_rel * wm;
     }
   }
   CMPC_SYNC();
@@ -612,7 +629,7 @@ CMPC_HD int admm_solve(Ctx& c, int* iters_out, int* nfact_out) {
       const double pri = s.sc[SC_PRI], dua = s.sc[SC_DUA], npri = s.sc[SC_NPRI], ndua = s.sc[SC_NDUA];
       if (pri <= P.eps_abs + P.eps_rel * npri && dua <= P.eps_abs + P.eps_rel * ndua) { solved = 1; break; }
       if (!(pri == pri) || !(dua == dua)) break;   // NaN
-      if (P.adaptive_rho) {
+      if (P.adaptive_rho && it >= P.adapt_start) {
         const double rho = s.sc[SC_RHO];
         double est = rho * sqrt((pri / (npri + 1e-10)) / (dua / (ndua + 1e-10) + 1e-10));
         est = fmin(fmax(est, 1e-6), 1e6);
@@ -686,14 +703,43 @@ CMPC_HD int polish(Ctx& c) {
     }
   }
   CMPC_SYNC();
-  int bad = factor(c, MODE_POLISH);
-  if (!bad) {
+  // Rounds of (factor, PMM sweeps); after each round the friction active set is corrected:
+  // rows that came out violated are added, rows whose multiplier came out negative are dropped.
+  // OSQP polishes once; the correction only matters when the ADMM iterate at eps = 1e-7 did not
+  // identify the active set exactly (DESIGN.md "polish").
+  int bad = 0;
+  for (int round = 0; round < 1 + P.polish_rounds && !bad; ++round) {
+    bad = factor(c, MODE_POLISH);
+    if (bad) break;
     for (int r = 0; r < 1 + P.refine; ++r) {
       backward_sweep(c, MODE_POLISH);
       forward_sweep(c, MODE_POLISH);
     }
-    residuals(c, MODE_POLISH);
+    if (round == P.polish_rounds) break;
+    CMPC_LANES(l) {
+      double changes = 0.0;
+      for (int k = l; k < N; k += 32) {
+        const double* sk = c.sta + (long)k * STA;
+        double* pk = c.pol + (long)k * POL;
+        const int mask = (int)c.stg[(long)k * STG + O_ACT];
+        int pm = c.pmask[k];
+        for (int r = 0; r < 16; ++r) {
+          int ct = r >> 2;
+          if (ct >= P.nc || !((mask >> ct) & 1)) continue;
+          if ((pm >> r) & 1) {
+            if (pk[r] < 0.0) { pm &= ~(1 << r); pk[r] = 0.0; changes += 1.0; }
+          } else if (friction_row_value(c, k, ct, r & 3, &sk[O_U]) > 0.0) {
+            pm |= 1 << r; pk[r] = 0.0; changes += 1.0;
+          }
+        }
+        c.pmask[k] = pm;
+      }
+      s.PB[l] = changes;
+    }
+    CMPC_REDUCE_SUM(c, 0, SC_NUM);
+    if (s.sc[SC_NUM] == 0.0) break;
   }
+  if (!bad) residuals(c, MODE_POLISH);
   const double pri = s.sc[SC_PRI], dua = s.sc[SC_DUA];
   const int ok = !bad && ((pri < pri0 && dua < dua0) || (pri < pri0 && dua0 < 1e-10) || (dua < dua0 && pri0 < 1e-10));
   if (!ok) {
@@ -857,6 +903,18 @@ CMPC_HD void setup_instance(Ctx& c) {
   CMPC_SYNC();
 }
 
+CMPC_HD void write_solution(Ctx& c) {
+  const Params& P = *c.prm;
+  const int N = P.N;
+  CMPC_LANES(l) {
+    for (int e = l; e < (N + 1) * 9; e += 32)
+      c.bt.X_out[(long)c.b * (N + 1) * 9 + e] = c.sta[(long)(e / 9) * STA + O_X + e % 9];
+    for (int e = l; e < N * P.nu; e += 32)
+      c.bt.U_out[(long)c.b * N * P.nu + e] = c.sta[(long)(e / P.nu) * STA + O_U + e % P.nu];
+  }
+  CMPC_SYNC();
+}
+
 // ---------------------------------------------------------------- the SCP loop of one instance
 // scp_solver.py:118-179.  The linearisation point never moves (:129-130), so the stage records
 // are built once; each SCP iteration re-solves the QP for the current (radius, weight).
@@ -889,13 +947,7 @@ CMPC_HD void solve_instance(Ctx& c) {
       if (acc > P.acc_rho1) {
         radius *= P.beta_fail;
       } else {
-        CMPC_LANES(l) {
-          for (int e = l; e < (N + 1) * 9; e += 32)
-            c.bt.X_out[(long)c.b * (N + 1) * 9 + e] = c.sta[(long)(e / 9) * STA + O_X + e % 9];
-          for (int e = l; e < N * P.nu; e += 32)
-            c.bt.U_out[(long)c.b * N * P.nu + e] = c.sta[(long)(e / P.nu) * STA + O_U + e % P.nu];
-        }
-        CMPC_SYNC();
+        write_solution(c);
         success = 1;
         ++n_acc;
         if (acc < P.acc_rho0) radius = fmin(P.beta_succ * radius, P.radius0);
@@ -905,6 +957,9 @@ CMPC_HD void solve_instance(Ctx& c) {
     }
     ++it;
   }
+  // nothing accepted: hand back the last QP solution (n_accepted == 0 tells the caller; the
+  // reference returns empty lists in that case)
+  if (n_acc == 0) write_solution(c);
   CMPC_LANES(l) {
     if (l == 0) {
       c.bt.scp_iters[c.b] = it;

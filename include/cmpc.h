@@ -57,6 +57,8 @@ typedef struct {
 typedef struct {
   double eps_abs, eps_rel, sigma, alpha, rho, delta, adaptive_rho_tolerance;
   int32_t max_iter, check_termination, polish, polish_refine_iter, adaptive_rho;
+  int32_t adaptive_rho_start;   /* first ADMM iteration at which rho may be adapted */
+  int32_t polish_active_set_rounds; /* extra polish rounds with a corrected active set (0 = OSQP) */
 } cmpc_qp_settings;
 
 /* status[] values */

@@ -14,8 +14,10 @@ from . import dynamics
 SIGMA = 1e-6
 ALPHA = 1.6
 PER_ROW_FRICTION = True
-RHO0 = 1.0
+RHO0 = 2.0
+ADAPT_START = 200    # early residuals are transient; adapting on them hurts
 RHO_K_REL = 1.0       # kappa-copy penalty = rho * RHO_K_REL * min(W_kappa)
+RHO_E_POL_REL = 1e4   # terminal-equality penalty while polishing
 RHO_E_REL = 100.0     # terminal-equality penalty = RHO_E_REL * max(W_x), independent of rho
 
 
@@ -99,11 +101,14 @@ class RiccatiADMM:
         self.radius, self.weight = radius, weight
         self.sigma, self.alpha = sigma, alpha
         N, nu, nc = st.N, st.nu, st.nc
-        self.x = np.zeros((N + 1, 9)); self.x[0] = st.x_init
-        self.u = np.zeros((N, nu))
-        self.wf = np.zeros((N, nc, 4)); self.yf = np.zeros((N, nc, 4))
-        self.wk = np.zeros((N + 1, 3)); self.yk = np.zeros((N + 1, 3))
-        self.we = np.zeros(9); self.ye = np.zeros(9)
+        # start at the linearisation point (the device does the same; the answer of a convex
+        # QP does not depend on it, the reference cold-starts OSQP at zero)
+        self.x = st.Xbar.T.copy(); self.x[0] = st.x_init
+        self.u = st.Ubar.T.copy() * np.repeat(st.act, 3, axis=1)
+        cf0 = np.einsum("kiab,kib->kia", st.G, self.u.reshape(N, nc, 3))
+        self.wf = np.minimum(cf0, 0.0); self.yf = np.zeros((N, nc, 4))
+        self.wk = st.Xbar[6:9, :].T.copy(); self.yk = np.zeros((N + 1, 3))
+        self.we = st.x_final.copy(); self.ye = np.zeros(9)
         self.kbar = st.Xbar[6:9, :].T.copy()
         self.branch = np.zeros(N + 1, dtype=int)
         self.n_fact = 0
@@ -273,7 +278,7 @@ class RiccatiADMM:
                 if pri <= eps_abs + eps_rel * npri and dua <= eps_abs + eps_rel * ndua:
                     status = "solved"
                     break
-                if adapt:
+                if adapt and it >= ADAPT_START:
                     est = self.rho * np.sqrt((pri / (npri + 1e-10)) / (dua / (ndua + 1e-10) + 1e-10))
                     est = float(np.clip(est, 1e-6, 1e6))
                     if est > self.rho * adapt_tol or est < self.rho / adapt_tol:
@@ -304,7 +309,7 @@ class RiccatiADMM:
         self.rf = af * inv
         self.yf = self.yf * af
         self.wf = np.zeros_like(self.wf)
-        self.re = inv
+        self.re = RHO_E_POL_REL * float(np.max(st.Wx))
         self.we = st.x_final.copy()
         # kappa rows: up to three pins e_i and one sign row per knot -> 3x3 block Mk, target wk
         self.Mk = np.zeros((N + 1, 3, 3))
