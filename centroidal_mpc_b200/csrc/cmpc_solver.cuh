@@ -657,6 +657,7 @@ CMPC_HD int polish(Ctx& c) {
   WarpMem& s = *c.s;
   const int N = P.N;
   const double pri0 = s.sc[SC_PRI], dua0 = s.sc[SC_DUA];
+  const double m0 = fmax(pri0 / (P.eps_abs + P.eps_rel * s.sc[SC_NPRI]), dua0 / (P.eps_abs + P.eps_rel * s.sc[SC_NDUA]));
   // keep the ADMM iterate; build the polish records
   CMPC_LANES(l) {
     for (long e = l; e < (long)(N + 1) * STA; e += 32) c.sta2[e] = c.sta[e];
@@ -740,8 +741,12 @@ CMPC_HD int polish(Ctx& c) {
     if (s.sc[SC_NUM] == 0.0) break;
   }
   if (!bad) residuals(c, MODE_POLISH);
+  // Acceptance: OSQP keeps the polished point when both residuals improve.  Here the polished
+  // dual residual carries the round-off of the 1e9 terminal penalty (~1e-6, three orders below
+  // eps_dual), so "improve" is judged on the residuals normalised by their tolerances.
   const double pri = s.sc[SC_PRI], dua = s.sc[SC_DUA];
-  const int ok = !bad && ((pri < pri0 && dua < dua0) || (pri < pri0 && dua0 < 1e-10) || (dua < dua0 && pri0 < 1e-10));
+  const double m1 = fmax(pri / (P.eps_abs + P.eps_rel * s.sc[SC_NPRI]), dua / (P.eps_abs + P.eps_rel * s.sc[SC_NDUA]));
+  const int ok = !bad && (m1 < m0) && (pri == pri) && (dua == dua);
   if (!ok) {
     CMPC_LANES(l) {
       for (long e = l; e < (long)(N + 1) * STA; e += 32) c.sta[e] = c.sta2[e];

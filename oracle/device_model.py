@@ -291,7 +291,7 @@ class RiccatiADMM:
         return status, it
 
     # ---------------------------------------------------------------- polish
-    def polish(self, pri0, dua0, delta=1e-6, refine=3):
+    def polish(self, pri0, dua0, delta=1e-6, refine=3, eps_abs=1e-7, eps_rel=1e-7):
         """OSQP-style polish (guess the active set, solve the equality-constrained QP) done
         as a proximal method of multipliers with penalty 1/delta — algebraically OSQP's
         regularised KKT solve + iterative refinement — reusing factor / x_update.
@@ -302,6 +302,7 @@ class RiccatiADMM:
           components, zero components pinned to kappa_bar;  2 surface -> the equality
           sign'(kappa-kappa_bar) = radius, zero components pinned."""
         st, N = self.st, self.st.N
+        _, _, npri0, ndua0 = self.residuals()
         names = ("x", "u", "wf", "yf", "wk", "yk", "we", "ye", "rf", "rk", "re", "lin_k")
         keep = {n: np.copy(getattr(self, n)) for n in names}
         inv = 1.0 / delta
@@ -359,8 +360,11 @@ class RiccatiADMM:
         for k in range(N + 1):
             for (a, b), y in zip(rows_k[k], ymul[k]):
                 self.yk_pol[k] += a * y
-        pri, dua, _, _ = self.residuals(polished=True)
-        ok = (pri < pri0 and dua < dua0) or (pri < pri0 and dua0 < 1e-10) or (dua < dua0 and pri0 < 1e-10)
+        pri, dua, npri, ndua = self.residuals(polished=True)
+        # judged on residuals normalised by their tolerances (see csrc/cmpc_solver.cuh polish())
+        m0 = max(pri0 / (eps_abs + eps_rel * npri0), dua0 / (eps_abs + eps_rel * ndua0))
+        m1 = max(pri / (eps_abs + eps_rel * npri), dua / (eps_abs + eps_rel * ndua))
+        ok = m1 < m0
         self.pol_res = (pri, dua)
         self.Mk = None
         if ok:

@@ -64,7 +64,8 @@ def test_oracle_parity(gpu, cases, name):
 
 @pytest.mark.parametrize("name,B", [("solo12_trot", 64), ("solo12_pace", 33), ("bolt", 7)])
 def test_gpu_equals_host_build_of_the_same_source(gpu, name, B):
-    """Same arithmetic in the same order: results agree to round-off, iteration counts exactly."""
+    """Same arithmetic in the same order (up to FMA contraction, which nvcc and g++ choose
+    differently): results agree to amplified round-off, iteration counts exactly."""
     import emu_binding as E
     from centroidal_mpc_b200 import synthetic
     from centroidal_mpc_b200.src.scp_solver import solve_scp_batched
@@ -76,7 +77,7 @@ def test_gpu_equals_host_build_of_the_same_source(gpu, name, B):
     np.testing.assert_array_equal(out["status"], emu["status"])
     np.testing.assert_array_equal(out["qp_iters"], emu["qp_iters"])
     for b in range(B):
-        assert relerr(out["X"][b], emu["X"][b]) < 1e-9 and relerr(out["U"][b], emu["U"][b]) < 1e-9
+        assert relerr(out["X"][b], emu["X"][b]) < 1e-7 and relerr(out["U"][b], emu["U"][b]) < 1e-7
 
 
 def test_full_size_properties(gpu):
