@@ -149,19 +149,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(batch, qp_iters, n_factor):
-    """HBM bytes the streamed-factor algorithm must move for one launch (DESIGN.md "roofline"):
-    compulsory I/O + per ADMM iteration the per-knot records of both sweeps + factor writes."""
+def algorithmic_work(batch, stats):
+    """HBM bytes and FP64 flops the algorithm must move / execute for one launch (DESIGN.md
+    "roofline"): per sweep pair the per-knot records both sweeps read and write, per
+    factorisation the stage record read and the factor record written, plus compulsory I/O.
+    Counts come from the solver's own statistics (ADMM iterations, multiplier-method sweeps,
+    factorisations per instance)."""
     import numpy as np
-    act = batch.contact_active[0].sum(axis=1)            # active contacts per knot (shared plan)
-    na = 3 * act
+    ns = batch.contact_active[0].sum(axis=1).astype(float)   # active contacts per knot (shared plan)
+    na = 3 * ns
     N = batch.N
-    bwd = 9 + 3 + na + 1 + 3 + 9 + na + 4 * act + 3 + 9 * na + na * na + 9 + na      # reads + d write
-    fwd = 3 + na + 4 + 1 + 3 + 9 + na + 4 * act + 3 + 9 * na + na + 9 + na + 4 * act + 3
-    per_iter = 8.0 * (bwd.sum() + fwd.sum() + 2 * (9 + 3 + 9 + 3))                  # + terminal knot
-    per_factor = 8.0 * (9 * na + na * na + 9 + 40).sum()
+    # backward: Pc 9, xbar 9, S 3, d na, v/y rows 4ns, kappa copy 3, Hinv na^2, K 9na; writes d na
+    bwd = 9 + 9 + 3 + na + 4 * ns + 3 + na * na + 9 * na + na
+    # forward: d na, Kt 9na, stage (xbar 9, S 3, ck 3, d na), rows 4ns read + written, kappa copy 3 + 3
+    fwd = na + 9 * na + 9 + 3 + 3 + na + 8 * ns + 6
+    sweep_bytes = 8.0 * float(bwd.sum() + fwd.sum() + 2 * (9 + 9 + 3))                # + terminal knot
+    pmm_extra = 8.0 * float((9 + na).sum())                                           # solution record
+    factor_bytes = 8.0 * float((28 + na * na + 18 * na + 9).sum())
+    sweep_flops = 2.0 * float((na * na + 9 * na + 9 * na + 14 * ns + 60).sum())
+    factor_flops = 2.0 * float((na ** 3 + 9 * na * na + 81 * na + 6 * (na + 9) * na / 3 + 400).sum())
+    admm = float(stats["qp_iters"].sum())
+    pmm = float(stats["info"][:, 8].sum())
+    nfac = float(stats["n_factor"].sum())
     io = batch.input_bytes() / batch.B + ((N + 1) * 9 + N * batch.nu) * 8 + 12
-    return float(per_iter * qp_iters.sum() + per_factor * n_factor.sum() + io * batch.B), float(per_iter)
+    total_bytes = sweep_bytes * (admm + pmm) + pmm_extra * pmm + factor_bytes * nfac + io * batch.B
+    total_flops = sweep_flops * (admm + pmm) + factor_flops * nfac
+    return float(total_bytes), float(total_flops), sweep_bytes
 
 
 def run_gpu_arm(args):
@@ -258,7 +271,7 @@ def run_gpu_arm(args):
     value = B * world * args.steps / (total_ms * 1e-3)
     e2e = B * world * args.steps / (e2e_ms * 1e-3)
     kernel_ms = float(np.mean(step_ms))            # the step is one launch of cmpc_scp_kernel (+ gather)
-    alg_bytes, per_iter_bytes = algorithmic_bytes(batch, stats["qp_iters"], stats["n_factor"])
+    alg_bytes, flops, per_iter_bytes = algorithmic_work(batch, stats)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -268,11 +281,6 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     tf, ms = __import__("ctypes").c_double(), __import__("ctypes").c_double()
     lib.cmpc_fp64_peak(__import__("ctypes").byref(tf), __import__("ctypes").byref(ms))
-    flops = 0.0
-    act = batch.contact_active[0].sum(axis=1)
-    na = 3 * act
-    flops_iter = 2.0 * float((na * na + 2 * 9 * na + 2 * 9 * na + 150).sum())
-    flops = flops_iter * float(stats["qp_iters"].sum())
 
     cores = host_cores()
     workers = max(1, min(cores, 64))
@@ -286,7 +294,7 @@ def run_gpu_arm(args):
         "config": {"workload": "%s N=%d" % (WORKLOAD, HORIZON), "batch_per_gpu": B, "global_batch": B * world,
                    "mode": "B (independent reference trajectories, rng(1000+b))",
                    "parallelism": "instances sharded across %d GPU(s), no collective on the solve path, one gather" % world,
-                   "l2": "solver workspace %.2f GB per GPU streams through HBM every ADMM iteration (>> 126 MB L2); no flush needed"
+                   "l2": "solver workspace %.2f GB per GPU (>> 126 MB L2) is streamed by every sweep; no flush needed"
                          % (lib.cmpc_workspace_bytes(solver.handle) / 1e9)},
         "latency_ms_p50": srt[len(srt) // 2],
         "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": batch.input_bytes(),
@@ -297,11 +305,14 @@ def run_gpu_arm(args):
                      "frac": achieved / peak_gbs, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "kernel": "cmpc_scp_kernel", "kernel_ms": kernel_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_admm_iteration_per_solve": per_iter_bytes,
+                     "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_sweep_pair_per_solve": per_iter_bytes,
+                     "note": "latency/issue-bound recursion at 28 warps per SM: neither HBM nor the FP64 pipe binds (DESIGN.md)",
                      "fp64": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "measured_peak_tflops": tf.value,
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / max(tf.value, 1e-9)}},
         "solver_stats": {"admm_iters_mean": float(stats["qp_iters"].mean()), "admm_iters_max": int(stats["qp_iters"].max()),
                          "factorisations_mean": float(stats["n_factor"].mean()),
+                         "multiplier_sweeps_mean": float(stats["info"][:, 8].mean()),
+                         "polish_attempts_mean": float(stats["info"][:, 9].mean()),
                          "scp_iters_mean": float(res["scp_iters"].mean()), "failed": int((res["status"] != 0).sum()),
                          "accepted": int((res["n_accepted"] > 0).sum()), "polished_frac": float(stats["info"][:, 7].mean())},
         "cpu_baseline": None if cpu_v is None else {

@@ -30,7 +30,9 @@ class cmpc_qp_settings(C.Structure):
                 ("adaptive_rho_tolerance", C.c_double), ("max_iter", C.c_int32),
                 ("check_termination", C.c_int32), ("polish", C.c_int32),
                 ("polish_refine_iter", C.c_int32), ("adaptive_rho", C.c_int32),
-                ("adaptive_rho_start", C.c_int32), ("polish_active_set_rounds", C.c_int32)]
+                ("adaptive_rho_start", C.c_int32), ("polish_active_set_rounds", C.c_int32),
+                ("active_set_start", C.c_int32), ("active_set_step", C.c_int32),
+                ("active_set_tol", C.c_double)]
 
 
 EXPORTS = ["cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
@@ -82,9 +84,10 @@ def make_qp_struct(overrides=None, lib=None):
     else:   # same numbers as csrc/cmpc_params.h default_qp_settings (checked by the tests)
         q.eps_abs = q.eps_rel = 1e-7
         q.sigma, q.alpha, q.rho, q.delta, q.adaptive_rho_tolerance = 1e-6, 1.6, 2.0, 1e-6, 5.0
-        q.max_iter, q.check_termination, q.polish, q.polish_refine_iter, q.adaptive_rho = 4000, 25, 1, 3, 1
+        q.max_iter, q.check_termination, q.polish, q.polish_refine_iter, q.adaptive_rho = 4000, 5, 1, 3, 1
         q.adaptive_rho_start = 200
-        q.polish_active_set_rounds = 2
+        q.polish_active_set_rounds = 9
+        q.active_set_start, q.active_set_step, q.active_set_tol = 20, 20, 1e-9
     for k, v in (overrides or {}).items():
         if not hasattr(q, k):
             raise CmpcError("unknown QP setting %r" % k)

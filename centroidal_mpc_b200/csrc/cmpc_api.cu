@@ -34,7 +34,7 @@ constexpr int BLOCKS_PER_SM = 7;   // 28 instances in flight per SM
 // ------------------------------------------------------------------------------------------
 // The SCP kernel: one warp per MPC instance, persistent over a work queue.  Warps never
 // synchronise with each other, so instances that need more ADMM iterations do not hold up the
-// block.  __launch_bounds__(128, 7): 28 warps/SM * 7.6 KB shared = 214 KB, <= 72 registers.
+// block.  __launch_bounds__(128, 7): 28 warps/SM (4.7 KB shared each), <= 72 registers.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue) {
@@ -71,18 +71,20 @@ __global__ void cmpc_linearize_kernel(const __grid_constant__ Params prm, int B,
   step_knot(prm, x, u, p, a, xn);
   for (int i = 0; i < 9; ++i) f[t * 9 + i] = xn[i];
   if (!fx) return;
-  double rec[STG];
-  linearize_knot(prm, x, u, p, a, k, rec);
-  double e[9];
-  for (int j = 0; j < 9; ++j) {   // column j of A = A e_j
-    for (int i = 0; i < 9; ++i) e[i] = (i == j) ? 1.0 : 0.0;
-    for (int i = 0; i < 9; ++i) fx[t * 81 + i * 9 + j] = Av_elem(prm, &rec[O_S], e, i);
-  }
-  const int mask = (int)rec[O_ACT];
-  for (int j = 0; j < nu; ++j) {
-    int ct = j / 3;
-    for (int i = 0; i < 9; ++i)
-      fu[(t * 9 + i) * nu + j] = ((mask >> ct) & 1) ? Bcol_elem(prm, &rec[O_D + 3 * ct], j % 3, i) : 0.0;
+  double rec[SG];
+  const int mt = linearize_knot(prm, x, u, p, a, 0, rec);
+  double A[81];
+  dense_A(prm, &rec[SG_S], A);
+  for (int i = 0; i < 81; ++i) fx[t * 81 + i] = A[i];
+  for (int i = 0; i < 9 * nu; ++i) fu[t * 9 * nu + i] = 0.0;
+  const int ns = mt & 7;
+  for (int sl = 0; sl < ns; ++sl) {
+    const int ct = (mt >> (4 + 2 * sl)) & 3;
+    for (int ax = 0; ax < 3; ++ax) {
+      double col[9];
+      dense_Bcol(prm, &rec[SG_D + 3 * sl], ax, col);
+      for (int i = 0; i < 9; ++i) fu[(t * 9 + i) * nu + 3 * ct + ax] = col[i];
+    }
   }
 }
 
@@ -106,6 +108,7 @@ struct cmpc_handle_s {
   int device;
   int num_sms;
   Batch bt;          // device pointers
+  double* gtab;      // general friction-row table (used when the fast path does not apply)
   void* ws;          // one allocation
   long ws_bytes;
   int* queue;
@@ -131,19 +134,21 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   const int B = dims->batch, N = dims->N;
   WsSizes w = ws_sizes(B, N);
-  long nd = w.stg + w.sta + w.sta2 + w.fac + w.dvec + w.pol + w.info;
-  long ni = w.pmask + 3L * B + 64;
+  long nd = w.stg + w.sta + w.fac + w.dvec + w.pm + w.sol + w.gtab + w.info;
+  long ni = w.meta + w.pmask + 3L * B + 64;
   h->ws_bytes = nd * 8 + ni * 4;
   CUDA_TRY(cudaMalloc(&h->ws, h->ws_bytes));
   double* d = (double*)h->ws;
+  h->bt.fac = d; d += w.fac;      // 32-byte aligned records first
   h->bt.stg = d; d += w.stg;
   h->bt.sta = d; d += w.sta;
-  h->bt.sta2 = d; d += w.sta2;
-  h->bt.fac = d; d += w.fac;
   h->bt.dvec = d; d += w.dvec;
-  h->bt.pol = d; d += w.pol;
+  h->bt.pm = d; d += w.pm;
+  h->bt.sol = d; d += w.sol;
+  h->gtab = d; d += w.gtab;
   h->bt.info = d; d += w.info;
   int* ip = (int*)d;
+  h->bt.meta = ip; ip += w.meta;
   h->bt.pmask = ip; ip += w.pmask;
   h->d_nacc = ip; ip += B;
   h->d_qpit = ip; ip += B;
@@ -190,6 +195,7 @@ int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_sett
   if (rc) return fail(rc, rc == -2 ? "cost weights must be positive" : "bad dims");
   cudaStream_t st = (cudaStream_t)stream;
   Batch bt = h->bt;
+  bt.gtab = prm.fast ? nullptr : h->gtab;
   bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = (int*)scp_iters; bt.status = (int*)status;
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
@@ -209,7 +215,7 @@ int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* 
   const int B = h->dims.batch;
   if (qp_iters) CUDA_TRY(cudaMemcpy(qp_iters, h->d_qpit, B * sizeof(int), cudaMemcpyDeviceToDevice));
   if (n_factor) CUDA_TRY(cudaMemcpy(n_factor, h->d_nfac, B * sizeof(int), cudaMemcpyDeviceToDevice));
-  if (info) CUDA_TRY(cudaMemcpy(info, h->bt.info, (long)B * 8 * sizeof(double), cudaMemcpyDeviceToDevice));
+  if (info) CUDA_TRY(cudaMemcpy(info, h->bt.info, (long)B * INFO * sizeof(double), cudaMemcpyDeviceToDevice));
   return 0;
 }
 

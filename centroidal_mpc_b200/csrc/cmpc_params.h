@@ -9,18 +9,21 @@ namespace cmpc {
 inline void default_qp_settings(cmpc_qp_settings* s) {
   s->eps_abs = 1e-7;            // scp_solver.py:63
   s->eps_rel = 1e-7;
-  s->sigma = 1e-6;              // OSQP default
+  s->sigma = 1e-6;              // OSQP default (unused, see cmpc.h)
   s->alpha = 1.6;               // OSQP default
   s->rho = 2.0;                 // initial penalty in equilibrated units
   s->delta = 1e-6;              // OSQP polish regularisation
   s->adaptive_rho_tolerance = 5.0;
   s->max_iter = 4000;           // OSQP default
-  s->check_termination = 25;    // OSQP default
+  s->check_termination = 5;     // residuals are knot-local by-products of the forward sweep
   s->polish = 1;                // scp_solver.py:63
   s->polish_refine_iter = 3;    // OSQP default
   s->adaptive_rho = 1;
-  s->polish_active_set_rounds = 2;   // extra polish rounds with a corrected active set
   s->adaptive_rho_start = 200;  // early residuals are transient: adapting on them hurts
+  s->polish_active_set_rounds = 9;
+  s->active_set_start = 20;     // first certified-polish attempt after 20 ADMM iterations
+  s->active_set_step = 20;     // doubled after every failed attempt
+  s->active_set_tol = 1e-9;
 }
 
 inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const cmpc_scp_params* scp,
@@ -28,20 +31,38 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   if (d->N < 1 || d->nc < 1 || d->nc > MAXC || d->batch < 0) return -1;
   cmpc_qp_settings dq;
   if (!qp) { default_qp_settings(&dq); qp = &dq; }
+  memset(p, 0, sizeof(Params));
   p->N = d->N; p->nc = d->nc; p->nu = 3 * d->nc; p->identity_R = identity_R;
   p->m = m->robot_mass; p->g = m->gravity_constant; p->dt = m->dt; p->mu = m->mu;
+  p->kf = p->mu * 0.70710678118654752440;
+  p->dt_m = p->dt / p->m;
+  p->dtmg = p->dt * p->m * p->g;
   for (int i = 0; i < NX; ++i) p->Wx[i] = m->state_cost_weights[i];
   for (int i = 0; i < MAXU; ++i) p->Wu[i] = i < p->nu ? m->control_cost_weights[i] : 1.0;
   for (int i = 0; i < NX; ++i) if (!(p->Wx[i] > 0.0)) return -2;
   for (int i = 0; i < p->nu; ++i) if (!(p->Wu[i] > 0.0)) return -2;
-  p->sigma = qp->sigma; p->alpha = qp->alpha; p->rho0 = qp->rho; p->eps_abs = qp->eps_abs;
+  // fast path: identity contact frames and the same control weights for every contact, so the
+  // friction rows and their equilibration factors are the same for all contacts and knots
+  int uniform = 1;
+  for (int c = 1; c < p->nc; ++c)
+    for (int a = 0; a < 3; ++a) if (p->Wu[3 * c + a] != p->Wu[a]) uniform = 0;
+  p->fast = identity_R && uniform;
+  for (int row = 0; row < 4; ++row) {
+    const double gx = (row < 2) ? 1.0 / sqrt(p->Wu[0]) : 0.0, gy = (row >= 2) ? 1.0 / sqrt(p->Wu[1]) : 0.0;
+    const double gz = p->kf / sqrt(p->Wu[2]);
+    const double mx = fmax(fmax(gx, gy), gz);
+    p->e2[row] = 1.0 / (mx * mx);
+  }
+  p->alpha = qp->alpha; p->rho0 = qp->rho; p->eps_abs = qp->eps_abs;
   p->eps_rel = qp->eps_rel; p->delta = qp->delta; p->adapt_tol = qp->adaptive_rho_tolerance;
   p->rho_e_rel = 100.0; p->rho_k_rel = 1.0;
   p->rho_e_pol_rel = 1e4;   // terminal-equality penalty while polishing (x max W_x), DESIGN.md
-  p->max_iter = qp->max_iter; p->check_every = qp->check_termination > 0 ? qp->check_termination : 25;
+  p->max_iter = qp->max_iter; p->check_every = qp->check_termination > 0 ? qp->check_termination : 5;
   p->polish = qp->polish; p->refine = qp->polish_refine_iter; p->adaptive_rho = qp->adaptive_rho;
   p->adapt_start = qp->adaptive_rho_start;
-  p->polish_rounds = qp->polish_active_set_rounds;
+  p->as_rounds = qp->polish_active_set_rounds;
+  p->as_start = qp->active_set_start; p->as_step = qp->active_set_step > 0 ? qp->active_set_step : 10;
+  p->as_tol = qp->active_set_tol > 0.0 ? qp->active_set_tol : 1e-9;
   if (scp) {
     p->radius0 = scp->trust_region_radius0; p->omega0 = scp->omega0; p->omega_max = scp->omega_max;
     p->acc_rho0 = scp->rho0; p->acc_rho1 = scp->rho1; p->beta_succ = scp->beta_succ;
@@ -52,12 +73,13 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
 }
 
 // workspace sizes in doubles / ints for a batch
-struct WsSizes { long stg, sta, sta2, fac, dvec, pol, pmask, info; };
+struct WsSizes { long stg, sta, fac, dvec, pm, sol, gtab, info, meta, pmask; };
 inline WsSizes ws_sizes(int B, int N) {
   WsSizes w;
-  w.stg = (long)B * (N + 1) * STG; w.sta = (long)B * (N + 1) * STA; w.sta2 = w.sta;
-  w.fac = (long)B * N * FAC; w.dvec = (long)B * N * DVC; w.pol = (long)B * (N + 1) * POL;
-  w.pmask = (long)B * (N + 1); w.info = (long)B * 8;
+  w.stg = (long)B * (N + 1) * SG; w.sta = (long)B * (N + 1) * ST;
+  w.fac = (long)B * N * FAC; w.dvec = (long)B * N * DVC; w.pm = (long)B * (N + 1) * PM;
+  w.sol = (long)B * (N + 1) * SOL; w.gtab = (long)B * N * MAXC * 16;
+  w.info = (long)B * INFO; w.meta = (long)B * (N + 1); w.pmask = (long)B * (N + 1);
   return w;
 }
 

@@ -39,7 +39,7 @@ class BatchSolver:
         self.X = torch.empty((B, N + 1, 9), dtype=f64, device=self.device)
         self.U = torch.empty((B, N, nu), dtype=f64, device=self.device)
         self.ints = torch.zeros((5, B), dtype=torch.int32, device=self.device)
-        self.info = torch.zeros((B, 8), dtype=f64, device=self.device)
+        self.info = torch.zeros((B, 12), dtype=f64, device=self.device)
         self.d = {}
         self.upload(batch)
 

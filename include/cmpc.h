@@ -53,12 +53,20 @@ typedef struct {
 } cmpc_scp_params;
 
 /* QP settings; the defaults reproduce the reference's OSQP call (src/scp_solver.py:61-63:
- * eps_abs = eps_rel = 1e-7, polish on) with OSQP's own defaults for the rest. */
+ * eps_abs = eps_rel = 1e-7, polish on) with OSQP's own defaults where the setting has the same
+ * meaning.  The device QP solver is an ADMM whose x-update treats the dynamics exactly (Riccati),
+ * interleaved with OSQP-style polishes that are accepted early when they certify a KKT point. */
 typedef struct {
-  double eps_abs, eps_rel, sigma, alpha, rho, delta, adaptive_rho_tolerance;
+  double eps_abs, eps_rel;
+  double sigma;                  /* accepted for OSQP compatibility, unused: W_x, W_u > 0 make the
+                                    x-update strictly convex without a proximal term */
+  double alpha, rho, delta, adaptive_rho_tolerance;
   int32_t max_iter, check_termination, polish, polish_refine_iter, adaptive_rho;
-  int32_t adaptive_rho_start;   /* first ADMM iteration at which rho may be adapted */
+  int32_t adaptive_rho_start;    /* first ADMM iteration at which rho may be adapted */
   int32_t polish_active_set_rounds; /* extra polish rounds with a corrected active set (0 = OSQP) */
+  int32_t active_set_start;      /* ADMM iteration of the first early polish (0 = only after termination) */
+  int32_t active_set_step;       /* ADMM iterations between early polishes */
+  double active_set_tol;         /* certificate: primal residual / row-violation tolerance */
 } cmpc_qp_settings;
 
 /* status[] values */
@@ -97,8 +105,9 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
                         double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted);
 
 /* Per-instance statistics of the last solve (device pointers, each nullable):
- * qp_iters[B] total ADMM iterations, n_factor[B] Riccati factorisations, info[B][8] =
- * {sigma_max(X-Xbar), accuracy ratio, primal res, dual res, rho, radius, weight, polished}. */
+ * qp_iters[B] total ADMM iterations, n_factor[B] Riccati factorisations, info[B][12] =
+ * {sigma_max(X-Xbar), accuracy ratio, primal res, dual res, rho, radius, weight, polished,
+ *  multiplier-method sweeps, polish attempts, 0, 0}. */
 int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info);
 
 /* compute_trajectory_data (src/centroidal_model.py:257-291): f, A=df/dx, B=df/du along (X,U).

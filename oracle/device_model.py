@@ -11,11 +11,15 @@ import numpy as np
 
 from . import dynamics
 
-SIGMA = 1e-6
 ALPHA = 1.6
+CHECK = 5            # termination test every CHECK iterations (knot-local residuals, see iterate())
 PER_ROW_FRICTION = True
 RHO0 = 2.0
 ADAPT_START = 200    # early residuals are transient; adapting on them hurts
+AS_START = 20        # first certified-polish attempt after this many ADMM iterations
+AS_STEP = 20         # interval to the next attempt (doubled after every failure)
+AS_ROUNDS = 9        # active-set correction rounds per attempt
+AS_TOL = 1e-9        # certificate tolerance (primal residual / row violation)
 RHO_K_REL = 1.0       # kappa-copy penalty = rho * RHO_K_REL * min(W_kappa)
 RHO_E_POL_REL = 1e4   # terminal-equality penalty while polishing
 RHO_E_REL = 100.0     # terminal-equality penalty = RHO_E_REL * max(W_x), independent of rho
@@ -94,15 +98,18 @@ class RiccatiADMM:
     which is the reference QP with the slack t_k minimised out in closed form
     (t_k = omega*max(0, |kappa_k-kappa_bar_k|_1 - radius); constraints.py:277-289, cost.py:34-39).
     Split blocks: friction rows (w_f, y_f), a copy v_k of kappa_k with the prox of the exact
-    penalty (w_k, y_k), the terminal equality (w_e, y_e)."""
+    penalty (w_k, y_k), the terminal equality (w_e, y_e).
 
-    def __init__(self, st, radius, weight, rho=RHO0, sigma=SIGMA, alpha=ALPHA):
+    The x-update has no proximal term (OSQP's sigma): W_x, W_u > 0 make it strictly convex, so
+    the iteration only carries (w, y) — stored on the device as v = w + y/rho per row."""
+
+    def __init__(self, st, radius, weight, rho=RHO0, alpha=ALPHA):
         self.st = st
         self.radius, self.weight = radius, weight
-        self.sigma, self.alpha = sigma, alpha
+        self.alpha = alpha
         N, nu, nc = st.N, st.nu, st.nc
-        # start at the linearisation point (the device does the same; the answer of a convex
-        # QP does not depend on it, the reference cold-starts OSQP at zero)
+        # start at the linearisation point (the answer of a convex QP does not depend on it;
+        # the reference cold-starts OSQP at zero)
         self.x = st.Xbar.T.copy(); self.x[0] = st.x_init
         self.u = st.Ubar.T.copy() * np.repeat(st.act, 3, axis=1)
         cf0 = np.einsum("kiab,kib->kia", st.G, self.u.reshape(N, nc, 3))
@@ -114,6 +121,8 @@ class RiccatiADMM:
         self.n_fact = 0
         self.lin_k = np.zeros((N + 1, 3))      # polish only: linear penalty slope
         self.Mk = None                          # polish only: 3x3 kappa blocks
+        self.dynrow = max(float(np.abs(st.c).max()), float(np.abs(st.x_init).max()))
+        self.nq = float(np.abs(st.q).max())
         self.set_rho(rho)
         self.factor()
 
@@ -135,14 +144,12 @@ class RiccatiADMM:
         self.Mk = None
 
     # ---------------------------------------------------------------- factorisation
-    def factor(self, sigma=None):
+    def factor(self):
         st, N, nu = self.st, self.st.N, self.st.nu
-        sg = self.sigma if sigma is None else sigma
-        self.sg_f = sg
         self.K = np.zeros((N, nu, 9)); self.Hinv = np.zeros((N, nu, nu)); self.Pc = np.zeros((N, 9))
 
         def Qk(k):
-            Q = np.diag(st.Wx + sg)
+            Q = np.diag(st.Wx).copy()
             if self.Mk is not None:
                 Q[6:9, 6:9] += self.Mk[k]
             else:
@@ -150,7 +157,7 @@ class RiccatiADMM:
             return Q
         P = Qk(N) + self.re * np.eye(9)
         for k in range(N - 1, -1, -1):
-            Rk = np.diag(st.Wu + sg)
+            Rk = np.diag(st.Wu).copy()
             for i in range(st.nc):
                 Rk[3 * i:3 * i + 3, 3 * i:3 * i + 3] += st.G[k, i].T @ (self.rf[k, i][:, None] * st.G[k, i])
             A, B = st.A[k], st.B[k]
@@ -188,192 +195,217 @@ class RiccatiADMM:
         return x, u
 
     def x_update(self):
-        st, N, sg = self.st, self.st.N, self.sg_f
+        st, N = self.st, self.st.N
         vf = self.rf * self.wf - self.yf
         ve = self.re * self.we - self.ye
-        qx = st.q - sg * self.x
+        qx = st.q.copy()
         if self.Mk is None:
             qx[:, 6:9] -= self.rk[:, None] * self.wk - self.yk
         else:   # polish: general rows on kappa, see polish()
             qx[:, 6:9] += self.lin_k - np.einsum("kab,kb->ka", self.Mk, self.wk) + self.yk
         qx[N] -= ve
-        ru = -sg * self.u - np.einsum("kiab,kia->kib", st.G, vf).reshape(N, st.nu)
+        ru = -np.einsum("kiab,kia->kib", st.G, vf).reshape(N, st.nu)
         return self.lqr_solve(qx, ru)
 
-    def iterate(self):
+    def iterate(self, check=False):
+        """One ADMM iteration.  With check=True also returns (pri, dua, npri, ndua), OSQP's
+        unscaled infinity-norm residuals of the point (x~, w_new, y_new, nu~), nu~ being the
+        multipliers of the exactly-treated rows (dynamics, x_0) from the x-update itself.  With
+        that choice the stationarity residual is  A_s'(y_new - y_old - rho (A_s x~ - w_old)),
+        A_s the split rows, which is local to each knot: no costate recursion is needed."""
         st, al, N = self.st, self.alpha, self.st.N
         xt, ut = self.x_update()
         cf, ck, ce = self.rows(xt, ut)
-        self.x = al * xt + (1 - al) * self.x
-        self.u = al * ut + (1 - al) * self.u
+        self.x, self.u = xt, ut
+        wf0, yf0, wk0, yk0, ye0 = self.wf, self.yf, self.wk.copy(), self.yk.copy(), self.ye
         # friction rows: one-sided box
-        zr = al * cf + (1 - al) * self.wf
+        zr = al * cf + (1 - al) * wf0
         with np.errstate(divide="ignore", invalid="ignore"):
-            v = np.where(self.rf > 0, zr + self.yf / np.where(self.rf > 0, self.rf, 1.0), zr)
+            v = np.where(self.rf > 0, zr + yf0 / np.where(self.rf > 0, self.rf, 1.0), zr)
         wn = np.minimum(v, 0.0)
-        self.yf = self.yf + self.rf * (zr - wn)
+        self.yf = yf0 + self.rf * (zr - wn)
         self.wf = wn
         # kappa copies: prox of the exact trust-region penalty
         for k in range(1, N + 1):
-            zr = al * ck[k] + (1 - al) * self.wk[k]
-            wn, self.branch[k] = prox_trust(zr + self.yk[k] / self.rk[k], self.kbar[k], self.radius,
-                                            self.weight, self.rk[k])
-            self.yk[k] = self.yk[k] + self.rk[k] * (zr - wn)
-            self.wk[k] = wn
+            zk = al * ck[k] + (1 - al) * wk0[k]
+            wkn, self.branch[k] = prox_trust(zk + yk0[k] / self.rk[k], self.kbar[k], self.radius,
+                                             self.weight, self.rk[k])
+            self.yk[k] = yk0[k] + self.rk[k] * (zk - wkn)
+            self.wk[k] = wkn
         # terminal equality
-        zr = al * ce + (1 - al) * self.we
-        self.ye = self.ye + self.re * (zr - st.x_final)
+        ze = al * ce + (1 - al) * self.we
+        self.ye = ye0 + self.re * (ze - st.x_final)
         self.we = st.x_final.copy()
+        if not check:
+            return None
+        df = self.yf - yf0 - self.rf * (cf - wf0)
+        dk = self.yk - yk0 - self.rk[:, None] * (ck - wk0)
+        dk[0] = 0.0
+        # terminal rows are equalities: the certificate takes y_e + rho_e (x_N - x_f), the
+        # multiplier of the x-update itself, so they contribute no stationarity residual
+        rd_u = np.einsum("kiab,kia->kib", st.G, df).reshape(N, st.nu)
+        rd_x = np.zeros((N + 1, 9))
+        rd_x[:, 6:9] = dk
+        pri = max(np.abs(cf - self.wf).max(), np.abs(ck[1:] - self.wk[1:]).max(), np.abs(ce - st.x_final).max())
+        dua = max(np.abs(rd_u).max(), np.abs(rd_x).max())
+        npri = max(np.abs(cf).max(), np.abs(ck[1:]).max(), np.abs(ce).max(), np.abs(self.wf).max(),
+                   np.abs(self.wk[1:]).max(), np.abs(st.x_final).max(), self.dynrow)
+        Px, Pu = st.Wx * xt, st.Wu * ut
+        aty_x = rd_x - Px - st.q
+        aty_u = rd_u - Pu
+        ndua = max(np.abs(Px[1:]).max(), np.abs(Pu).max(), np.abs(aty_x[1:]).max(), np.abs(aty_u).max(), self.nq)
+        return pri, dua, npri, ndua
 
-    # ---------------------------------------------------------------- residuals
-    def residuals(self, polished=False):
-        """Primal residual over the split rows; dual residual through a costate recursion
-        (x-stationarity holds by construction, the u rows carry the residual).  With
-        polished=True the primal residual is the violation of the original constraints."""
-        st, N = self.st, self.st.N
-        cf, ck, ce = self.rows(self.x, self.u)
-        if polished:
-            pri = max(np.maximum(cf, 0).max(), np.abs(ce - st.x_final).max())
-            yk = self.yk_pol
-        else:
-            pri = max(np.abs(cf - self.wf).max(), np.abs(ck[1:] - self.wk[1:]).max(),
-                      np.abs(ce - self.we).max())
-            yk = self.yk
-        dynrow = np.abs(st.c).max()
-        nAz = max(np.abs(cf).max(), np.abs(ck[1:]).max(), np.abs(ce).max(), dynrow, np.abs(st.x_init).max())
-        nw = max(np.abs(self.wf).max(), np.abs(self.wk[1:]).max(), np.abs(self.we).max(), dynrow,
-                 np.abs(st.x_init).max())
-        cx = np.zeros((N + 1, 9))
-        cx[1:, 6:9] = yk[1:]
-        cx[N] += self.ye
-        cu = np.einsum("kiab,kia->kib", st.G, self.yf).reshape(N, st.nu)
-        lam = np.zeros((N + 1, 9))
-        Px = st.Wx * self.x
-        lam[N] = Px[N] + st.q[N] + cx[N]
-        nAty = np.abs(cx[N] - lam[N]).max()
-        res_u = np.zeros((N, st.nu))
-        for k in range(N - 1, -1, -1):
-            Atl = st.A[k].T @ lam[k + 1]
-            Btl = st.B[k].T @ lam[k + 1]
-            res_u[k] = st.Wu * self.u[k] + cu[k] + Btl
-            nAty = max(nAty, np.abs(cu[k] + Btl).max())
-            lam[k] = Px[k] + st.q[k] + cx[k] + Atl
-            if k > 0:
-                nAty = max(nAty, np.abs(cx[k] + Atl - lam[k]).max())
-        dua = np.abs(res_u).max()
-        nPx = max(np.abs(Px[1:]).max(), np.abs(st.Wu * self.u).max())
-        nq = np.abs(st.q).max()
-        return pri, dua, max(nAz, nw), max(nPx, nAty, nq)
-
-    def solve(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=4000, check=25, adapt=True, adapt_tol=5.0,
-              polish=True, verbose=False):
+    def solve(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=4000, check=CHECK, adapt=True, adapt_tol=5.0,
+              polish=True, verbose=False, adapt_start=ADAPT_START, as_start=AS_START, as_step=AS_STEP,
+              as_rounds=AS_ROUNDS, as_tol=AS_TOL, refine=3):
+        """ADMM (active-set predictor and globally convergent fallback) interleaved with
+        certified active-set polishes: the first attempt after `as_start` iterations, later ones
+        with a doubling interval; an attempt that certifies a KKT point ends the solve.  When the
+        OSQP termination test passes first, the polish is accepted by OSQP's rule (it improves)."""
         status, it = "maximum iterations reached", max_iter
-        pri = dua = np.inf
-        for it in range(1, max_iter + 1):
-            self.iterate()
-            if it % check == 0:
-                pri, dua, npri, ndua = self.residuals()
-                if verbose:
-                    print(it, "pri %.3e dua %.3e rho %.3g" % (pri, dua, self.rho))
-                if pri <= eps_abs + eps_rel * npri and dua <= eps_abs + eps_rel * ndua:
-                    status = "solved"
-                    break
-                if adapt and it >= ADAPT_START:
-                    est = self.rho * np.sqrt((pri / (npri + 1e-10)) / (dua / (ndua + 1e-10) + 1e-10))
-                    est = float(np.clip(est, 1e-6, 1e6))
-                    if est > self.rho * adapt_tol or est < self.rho / adapt_tol:
-                        self.set_rho(est)       # x, w, y are kept (as OSQP does)
-                        self.factor()
         self.polished = False
         self.pol_res = (np.nan, np.nan)
-        if status == "solved" and polish:
-            self.polish(pri, dua)
+        next_as = as_start if (polish and as_start > 0) else -1
+        for it in range(1, max_iter + 1):
+            chk = (it % check == 0) or it == next_as
+            res = self.iterate(check=chk)
+            if res is None:
+                continue
+            pri, dua, npri, ndua = res
+            if verbose:
+                print(it, "pri %.3e dua %.3e rho %.3g" % (pri, dua, self.rho))
+            term = pri <= eps_abs + eps_rel * npri and dua <= eps_abs + eps_rel * ndua
+            if term or it == next_as:
+                if polish:
+                    cert, ppri, pnpri = self.polish(rounds=as_rounds, refine=refine, tol=as_tol)
+                    m0 = max(pri / (eps_abs + eps_rel * npri), dua / (eps_abs + eps_rel * ndua))
+                    m1 = ppri / (eps_abs + eps_rel * pnpri)
+                    if cert or (term and m1 < m0):
+                        self.x, self.u = self.x_pol, self.u_pol
+                        self.polished = True
+                        self.pol_res = (ppri, 0.0)
+                        status = "solved"
+                        break
+                if term:
+                    status = "solved"
+                    self.x, self.u = self.x_update()     # the device re-runs the LQR solve read-only
+                    break
+                next_as = it + as_step
+                as_step *= 2
+                self.factor()
+            if adapt and it >= adapt_start and it % check == 0:
+                est = self.rho * np.sqrt((pri / (npri + 1e-10)) / (dua / (ndua + 1e-10) + 1e-10))
+                est = float(np.clip(est, 1e-6, 1e6))
+                if est > self.rho * adapt_tol or est < self.rho / adapt_tol:
+                    self.set_rho(est)       # w, y are kept (as OSQP does)
+                    self.factor()
         return status, it
 
     # ---------------------------------------------------------------- polish
-    def polish(self, pri0, dua0, delta=1e-6, refine=3, eps_abs=1e-7, eps_rel=1e-7):
-        """OSQP-style polish (guess the active set, solve the equality-constrained QP) done
-        as a proximal method of multipliers with penalty 1/delta — algebraically OSQP's
+    def polish(self, delta=1e-6, refine=3, rounds=AS_ROUNDS, tol=AS_TOL):
+        """OSQP-style polish (guess the active set, solve the equality-constrained QP) done as a
+        method of multipliers with penalty 1/delta on the active rows — algebraically OSQP's
         regularised KKT solve + iterative refinement — reusing factor / x_update.
 
         Active structure: friction row active iff -w < y (OSQP's test u - z < y); terminal rows
         always; trust-region penalty per knot by the branch its prox took last:
           0 inside  -> nothing;  1 outside -> linear cost omega*sign on the non-zero
           components, zero components pinned to kappa_bar;  2 surface -> the equality
-          sign'(kappa-kappa_bar) = radius, zero components pinned."""
+          sign'(kappa-kappa_bar) = radius, zero components pinned.
+        After each round the friction active set is corrected (rows that came out violated by
+        more than tol join, rows whose multiplier came out negative leave) and the round is
+        repeated, at most 1 + rounds times or until the number of changes stops decreasing.
+
+        Returns (certified, pri, npri).  certified: no row wants to change and the primal
+        residual is <= tol; stationarity is exact by construction, so the polished point
+        (x_pol, u_pol) is a KKT point of the QP however far the ADMM iterate still was.  The ADMM
+        state (w, y, rho) is left untouched."""
         st, N = self.st, self.st.N
-        _, _, npri0, ndua0 = self.residuals()
         names = ("x", "u", "wf", "yf", "wk", "yk", "we", "ye", "rf", "rk", "re", "lin_k")
         keep = {n: np.copy(getattr(self, n)) for n in names}
         inv = 1.0 / delta
         af = ((0.0 - self.wf) < self.yf) & st.act[:, :, None]
-        self.rf = af * inv
-        self.yf = self.yf * af
-        self.wf = np.zeros_like(self.wf)
+        ypol = self.yf * af
         self.re = RHO_E_POL_REL * float(np.max(st.Wx))
         self.we = st.x_final.copy()
-        # kappa rows: up to three pins e_i and one sign row per knot -> 3x3 block Mk, target wk
+        # kappa rows: up to three pins e_i and one sign row per knot -> 3x3 block Mk
         self.Mk = np.zeros((N + 1, 3, 3))
         rows_k = [[] for _ in range(N + 1)]       # list of (row vector, rhs) per knot
         self.lin_k = np.zeros((N + 1, 3))
         ymul = [[] for _ in range(N + 1)]
         for k in range(1, N + 1):
-            if self.branch[k] == 0:
+            v = self.wk[k] + self.yk[k] / self.rk[k]
+            wk, br = prox_trust(v, self.kbar[k], self.radius, self.weight, self.rk[k])
+            if br == 0:
                 continue
-            d = self.wk[k] - self.kbar[k]
+            d = wk - self.kbar[k]
+            yk = self.rk[k] * (v - wk)
             sgn = np.sign(d)
             for i in range(3):
                 if sgn[i] == 0.0:
                     e = np.zeros(3); e[i] = 1.0
-                    rows_k[k].append((e, self.kbar[k][i])); ymul[k].append(self.yk[k][i])
-            if self.branch[k] == 1:
+                    rows_k[k].append((e, self.kbar[k][i])); ymul[k].append(yk[i])
+            if br == 1:
                 self.lin_k[k] = self.weight * sgn
             else:
                 nz = sgn != 0
-                mult = float(np.mean((self.yk[k] / np.where(nz, sgn, 1.0))[nz])) if nz.any() else 0.0
+                mult = float(np.mean((yk / np.where(nz, sgn, 1.0))[nz])) if nz.any() else 0.0
                 rows_k[k].append((sgn.copy(), self.radius + sgn @ self.kbar[k])); ymul[k].append(mult)
-        # PMM in row form for kappa: penalty inv on each row, multipliers ymul
-        self.factor_rows = rows_k
         for k in range(N + 1):
             for (a, b) in rows_k[k]:
                 self.Mk[k] += inv * np.outer(a, a)
-        self.factor(sigma=delta)
-        for _ in range(1 + refine):
-            # encode rows into the generic kappa linear term: -sum a (inv*b - y)
+        lin_keep = self.lin_k.copy()
+        certified, prev_chg = False, 1 << 30
+        pri = npri = np.inf
+
+        def sweep():
             self.wk = np.zeros((N + 1, 3)); self.yk = np.zeros((N + 1, 3))
             extra = np.zeros((N + 1, 3))
             for k in range(N + 1):
                 for (a, b), y in zip(rows_k[k], ymul[k]):
                     extra[k] += a * (inv * b - y)
-            lin_keep = self.lin_k.copy()
-            self.lin_k = self.lin_k - extra
+            self.lin_k = lin_keep - extra
             xt, ut = self.x_update()
             self.lin_k = lin_keep
             cf, ck, ce = self.rows(xt, ut)
-            self.x, self.u = xt, ut
-            self.yf = self.yf + self.rf * (cf - self.wf)
+            self.x_pol, self.u_pol = xt, ut
+            self.yf = self.yf + self.rf * cf
             self.ye = self.ye + self.re * (ce - self.we)
             for k in range(N + 1):
                 ymul[k] = [y + inv * (a @ ck[k] - b) for (a, b), y in zip(rows_k[k], ymul[k])]
-        # multiplier on kappa for the KKT check
-        self.yk_pol = self.lin_k.copy()
-        for k in range(N + 1):
-            for (a, b), y in zip(rows_k[k], ymul[k]):
-                self.yk_pol[k] += a * y
-        pri, dua, npri, ndua = self.residuals(polished=True)
-        # judged on residuals normalised by their tolerances (see csrc/cmpc_solver.cuh polish())
-        m0 = max(pri0 / (eps_abs + eps_rel * npri0), dua0 / (eps_abs + eps_rel * ndua0))
-        m1 = max(pri / (eps_abs + eps_rel * npri), dua / (eps_abs + eps_rel * ndua))
-        ok = m1 < m0
-        self.pol_res = (pri, dua)
+            p = max(np.abs(cf * af).max(), np.maximum(cf * ~af, 0).max(), np.abs(ce - st.x_final).max())
+            n = max(np.abs(cf).max(), np.abs(ck[1:]).max(), np.abs(ce).max(), np.abs(st.x_final).max(), self.dynrow)
+            return cf, p, n
+
+        for rnd in range(1 + rounds):
+            self.rf = af * inv
+            self.yf = ypol * af
+            self.wf = np.zeros_like(self.wf)
+            self.factor()
+            sweep()
+            chg = 0
+            for sw in range(1 + refine):
+                cf, pri, npri = sweep()
+                keep_r = af & ~(self.yf < 0.0)
+                join = (~af) & st.act[:, :, None] & (cf > tol)
+                new_af = keep_r | join
+                chg = int((new_af != af).sum())
+                self.yf = np.where(keep_r, self.yf, 0.0)
+                af = new_af
+                if chg or pri <= tol:
+                    break
+            ypol = self.yf.copy()
+            if chg == 0:
+                certified = pri <= tol
+                break
+            if chg > prev_chg:
+                break
+            prev_chg = chg
         self.Mk = None
-        if ok:
-            self.polished = True
-            self.wk, self.yk = ck, self.yk_pol
-            self.rf, self.rk, self.re = keep["rf"], keep["rk"], keep["re"]
-        else:
-            for n in names:
-                setattr(self, n, keep[n])
+        for n in names:
+            setattr(self, n, keep[n])
+        return certified, pri, npri
 
 
 def spectral_norm_9xn(D):

@@ -13,14 +13,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "emu", "cmpc_emu.cpp")
 _SO = os.path.join(_HERE, "emu", "libcmpc_emu.so")
 _DEPS = [os.path.join(_HERE, "..", "centroidal_mpc_b200", "csrc", f)
-         for f in ("cmpc_core.cuh", "cmpc_solver.cuh", "cmpc_params.h")] + [_SRC]
+         for f in ("cmpc_simt.cuh", "cmpc_core.cuh", "cmpc_solver.cuh", "cmpc_params.h")] + [_SRC]
 _lib = None
 
 
 def build(force=False):
     newest = max(os.path.getmtime(f) for f in _DEPS)
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", _SO, _SRC])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-x", "c++", "-o", _SO, _SRC])
     return _SO
 
 
@@ -45,7 +45,7 @@ def solve_scp(batch, scp_params, qp_overrides=None):
     qp = L.make_qp_struct(qp_overrides)
     out = dict(X=np.zeros((B, N + 1, 9)), U=np.zeros((B, N, nu)), scp_iters=np.zeros(B, np.int32),
                status=np.zeros(B, np.int32), n_accepted=np.zeros(B, np.int32),
-               qp_iters=np.zeros(B, np.int32), n_factor=np.zeros(B, np.int32), info=np.zeros((B, 8)))
+               qp_iters=np.zeros(B, np.int32), n_factor=np.zeros(B, np.int32), info=np.zeros((B, 12)))
     rc = lib.cmpc_emu_solve_scp(C.byref(dims), C.byref(model), C.byref(scp), C.byref(qp), _p(batch.x_init),
                                 _p(batch.x_final), _p(batch.X_ref), _p(batch.U_init), _p(batch.contact_pos),
                                 _p(batch.contact_R), _p(batch.contact_active), _p(out["X"]), _p(out["U"]),
