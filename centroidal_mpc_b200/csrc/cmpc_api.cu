@@ -8,7 +8,7 @@
 #include <string>
 
 #include "cmpc_params.h"
-#include "cmpc_solver.cuh"
+#include "cmpc_tile.cuh"
 
 using namespace cmpc;
 
@@ -27,28 +27,65 @@ int fail(int code, const std::string& msg) {
     if (e_ != cudaSuccess) return fail(-100 - (int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr int WARPS_PER_BLOCK = 4;
+// ------------------------------------------------------------------------------------------
+// The SCP kernel: one thread per MPC instance, one warp per tile of 32 instances, persistent
+// over a queue of tiles.  Each lane runs the driver state machine of its instance
+// (cmpc_tile.cuh: advance()); the warp executes one whole-horizon operation at a time for the
+// lanes that asked for it, lowest operation code first, so that lanes that are ahead wait at
+// the later operations (evaluate, write) and the tile does those together.  Warps never
+// synchronise with each other.
+// ------------------------------------------------------------------------------------------
+constexpr int WARPS_PER_BLOCK = 1;
 constexpr int THREADS = 32 * WARPS_PER_BLOCK;
-constexpr int BLOCKS_PER_SM = 7;   // 28 instances in flight per SM
+constexpr int BLOCKS_PER_SM = 4;   // cap of resident tiles per SM for batches beyond 148 tiles
 
-// ------------------------------------------------------------------------------------------
-// The SCP kernel: one warp per MPC instance, persistent over a work queue.  Warps never
-// synchronise with each other, so instances that need more ADMM iterations do not hold up the
-// block.  __launch_bounds__(128, 7): 28 warps/SM (4.7 KB shared each), <= 72 registers.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue) {
-  extern __shared__ double smem_raw[];
-  WarpMem* s = reinterpret_cast<WarpMem*>(smem_raw) + (threadIdx.x >> 5);
+template <bool FAST>
+__device__ void run_tile(const Params& prm, const Batch& bt, int tile) {
+  const unsigned lane = threadIdx.x & 31u;
+  TileCtx T;
+  bind_tile(T, prm, bt, tile);
+  const int b = tile * TL + (int)lane;
+  const bool live = b < bt.B;
+  Inst I;
+  Sv S;
+  Drv D;
+  if (live) {
+    bind_instance(I, prm, bt, b);
+    setup_op(prm, T, I, S);
+  }
+  for (int k = 0; k <= prm.N; ++k) {   // slots per knot of the tile
+    const int ns = live ? (meta_of(T, I, k)[0] & 7) : 0;
+    const int mx = __reduce_max_sync(0xffffffffu, ns);
+    if (lane == 0) T.nst[k] = mx;
+  }
+  __syncwarp();
+  int op = OP_DONE;
+  if (live) {
+    drv_init(prm, S, D);
+    op = advance(prm, S, D);
+  }
+  for (;;) {
+    const int sel = __reduce_min_sync(0xffffffffu, op);
+    if (sel == OP_DONE) break;
+    if (op == sel) {
+      execute<FAST>(sel, prm, T, I, bt, S, D);
+      op = advance(prm, S, D);
+    }
+    __syncwarp();
+  }
+  if (live) write_stats(bt, I, S, D);
+}
+
+__global__ void __launch_bounds__(THREADS)
+cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tiles) {
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(queue, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= bt.B) break;
-    Ctx c;
-    bind_instance(c, &prm, bt, s, b);
-    solve_instance(c);
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(queue, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= tiles) break;
+    if (prm.fast) run_tile<true>(prm, bt, tile);
+    else run_tile<false>(prm, bt, tile);
     __syncwarp();
   }
 }
@@ -71,10 +108,11 @@ __global__ void cmpc_linearize_kernel(const __grid_constant__ Params prm, int B,
   step_knot(prm, x, u, p, a, xn);
   for (int i = 0; i < 9; ++i) f[t * 9 + i] = xn[i];
   if (!fx) return;
-  double rec[SG];
-  const int mt = linearize_knot(prm, x, u, p, a, 0, rec);
+  KnotLin L;
+  linearize_knot(prm, x, u, p, a, 0, L);
+  const int mt = L.meta;
   double A[81];
-  dense_A(prm, &rec[SG_S], A);
+  dense_A(prm, L.S, A);
   for (int i = 0; i < 81; ++i) fx[t * 81 + i] = A[i];
   for (int i = 0; i < 9 * nu; ++i) fu[t * 9 * nu + i] = 0.0;
   const int ns = mt & 7;
@@ -82,7 +120,7 @@ __global__ void cmpc_linearize_kernel(const __grid_constant__ Params prm, int B,
     const int ct = (mt >> (4 + 2 * sl)) & 3;
     for (int ax = 0; ax < 3; ++ax) {
       double col[9];
-      dense_Bcol(prm, &rec[SG_D + 3 * sl], ax, col);
+      dense_Bcol(prm, &L.d[3 * sl], ax, col);
       for (int i = 0; i < 9; ++i) fu[(t * 9 + i) * nu + 3 * ct + ax] = col[i];
     }
   }
@@ -109,6 +147,7 @@ struct cmpc_handle_s {
   int num_sms;
   Batch bt;          // device pointers
   double* gtab;      // general friction-row table (used when the fast path does not apply)
+  int tiles;
   void* ws;          // one allocation
   long ws_bytes;
   int* queue;
@@ -134,30 +173,23 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   const int B = dims->batch, N = dims->N;
   WsSizes w = ws_sizes(B, N);
-  long nd = w.stg + w.sta + w.fac + w.dvec + w.pm + w.sol + w.gtab + w.info;
-  long ni = w.meta + w.pmask + 3L * B + 64;
+  const long nd = w.ws + w.gtab + w.info;
+  const long ni = w.nst + 3L * B + 64;
   h->ws_bytes = nd * 8 + ni * 4;
   CUDA_TRY(cudaMalloc(&h->ws, h->ws_bytes));
   double* d = (double*)h->ws;
-  h->bt.fac = d; d += w.fac;      // 32-byte aligned records first
-  h->bt.stg = d; d += w.stg;
-  h->bt.sta = d; d += w.sta;
-  h->bt.dvec = d; d += w.dvec;
-  h->bt.pm = d; d += w.pm;
-  h->bt.sol = d; d += w.sol;
+  h->bt.ws = d; d += w.ws;        // 256-byte aligned records first
   h->gtab = d; d += w.gtab;
   h->bt.info = d; d += w.info;
   int* ip = (int*)d;
-  h->bt.meta = ip; ip += w.meta;
-  h->bt.pmask = ip; ip += w.pmask;
+  h->bt.nst = ip; ip += w.nst;
   h->d_nacc = ip; ip += B;
   h->d_qpit = ip; ip += B;
   h->d_nfac = ip; ip += B;
   h->queue = ip;
+  h->tiles = (int)w.tiles;
   h->bt.B = B;
   h->bt.plan_stride = dims->shared_plan ? 0 : 1;
-  CUDA_TRY(cudaFuncSetAttribute(cmpc_scp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(WARPS_PER_BLOCK * sizeof(WarpMem))));
   *out = h;
   return 0;
 }
@@ -200,11 +232,10 @@ int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_sett
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
   CUDA_TRY(cudaMemsetAsync(h->queue, 0, sizeof(int), st));
-  const int B = h->dims.batch;
-  int blocks = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  int blocks = (h->tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   const int cap = h->num_sms * BLOCKS_PER_SM;
   if (blocks > cap) blocks = cap;
-  cmpc_scp_kernel<<<blocks, THREADS, WARPS_PER_BLOCK * sizeof(WarpMem), st>>>(prm, bt, h->queue);
+  cmpc_scp_kernel<<<blocks, THREADS, 0, st>>>(prm, bt, h->queue, h->tiles);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -1,21 +1,26 @@
 // cmpc_core.cuh — data layout, parameters and the closed-form centroidal model.
-// One warp per MPC instance; cmpc_simt.cuh is the execution model, cmpc_solver.cuh the solver.
+// Execution model: one THREAD per MPC instance, 32 instances ("a tile") per warp, every
+// per-instance quantity stored lane-interleaved so that each load / store of a warp is one
+// coalesced 256-byte access.  cmpc_tile.cuh is the solver written against this layout.
 //
 // What this replaces in the reference (paths relative to /root/reference):
 //   src/centroidal_model.py:189-232,257-291   dynamics + Jacobians  -> linearize_knot()
 //   src/cost.py:9-39, src/constraints.py:12-50,104-109,153-185,260-293, src/scp_solver.py:10-48
 //                                             QP assembly           -> never materialised: the
-//                                             stage records below ARE the block-banded KKT data
+//                                             knot records below ARE the block-banded KKT data
 //   src/scp_solver.py:59-68 (OSQP)            QP solve              -> admm + active-set polish
-//   src/scp_solver.py:71-87,151               accuracy ratio, spectral trust test -> evaluate()
-//   src/scp_solver.py:118-179                 trust-region loop     -> solve_instance()
+//   src/scp_solver.py:71-87,151               accuracy ratio, spectral trust test -> evaluate
+//   src/scp_solver.py:118-179                 trust-region loop     -> the per-lane driver
 #pragma once
-#include "cmpc_simt.cuh"
+#include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CMPC_HD __host__ __device__ __forceinline__
+#define CMPC_FN __host__ __device__
 #else
 #define CMPC_HD inline
+#define CMPC_FN
 #endif
 
 namespace cmpc {
@@ -23,30 +28,32 @@ namespace cmpc {
 constexpr int NX = 9;
 constexpr int MAXC = 4;    // contacts
 constexpr int MAXU = 12;   // 3 * MAXC
+constexpr int TL = 32;     // instances per tile (= lanes of a warp)
 
-// ---- per-instance, per-knot records in global memory (doubles).  "slot" = position of a contact
-// among the knot's ACTIVE contacts; controls (3 per slot) and friction rows (4 per slot) are
-// stored compactly by slot, na = 3 * slots.  Every record starts 32-byte aligned.
-constexpr int SG = 28;       // stage record, constant during a solve (built by setup_instance)
-constexpr int SG_XB = 0;     //   xbar[9]   linearisation point: q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
-constexpr int SG_S = 9;      //   S[3]      sum of active fbar:  A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
-constexpr int SG_CK = 12;    //   ck[3]     affine term rows 6..8: -dt S x cbar  (row 5 is dt m g, rows 0..4 are 0)
-constexpr int SG_D = 16;     //   d[slot][3] = p_contact - cbar:  B_k[:,3s:3s+3] = dt [0; I; [d]x]
-constexpr int ST = 20;       // ADMM iterate record
-constexpr int ST_VF = 0;     //   vf[slot*4+row] friction rows: w = min(v,0), y = rho e2 max(v,0)
-constexpr int ST_VK = 16;    //   vk[3]          kappa copy:    w = prox(v),  y = rho_k (v - w)
-constexpr int FAC = 372;     // factor record
-constexpr int F_HI = 0;      //   Hinv[na x na] (symmetric), then K[na x 9] at even(na*na), Pc[9] after it
-constexpr int F_KT = 264;    //   Kt[9 x na]   (K transposed: the forward sweep reads columns)
-constexpr int DVC = 12;      // feed-forward d_k (compact)
-constexpr int PM = 20;       // multiplier-method record: yf[16] (compact rows), yk[4] (3 pins + surface row)
-constexpr int SOL = 24;      // solution record: x[9] at 0, u[12] (compact) at 12
-constexpr int SOL_U = 12;
+// ---- knot record: REC doubles per instance and knot.  A tile's workspace is
+// [N+1 knots][REC fields][32 lanes]; field f of lane l at knot k lives at ((k*REC + f)*32 + l).
+// "slot" = position of a contact among the knot's ACTIVE contacts; controls (3 per slot) and
+// friction rows (4 per slot) are stored compactly by slot.  The number of slots of a knot is
+// tile-uniform (the maximum over the tile's lanes); a lane with fewer active contacts pads with
+// slots whose B columns are zero, which leaves exact zeros in their controls.
+constexpr int R_PC = 0;      // Pc[9]      = P_{k+1} c_k                      (factor)
+constexpr int R_HI = 9;      // Hinv       packed lower triangle (j,l), l <= j, at j(j+1)/2 + l
+constexpr int R_K = 87;      // K[j*9+i]   feedback gain, na x 9
+constexpr int R_XB = 195;    // xbar[9]    linearisation point: q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
+constexpr int R_S = 204;     // S[3]       sum of active fbar:  A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
+constexpr int R_CK = 207;    // ck[3]      affine term rows 6..8: -dt S x cbar (row 5 is dt m g)
+constexpr int R_D = 210;     // d[slot][3] = p_contact - cbar:  B_k[:,3s:3s+3] = dt [0; I; [d]x]
+constexpr int R_VF = 222;    // vf[4*slot+row]  friction rows: w = min(v,0), y = rho e2 max(v,0)
+constexpr int R_VK = 238;    // vk[3]           kappa copy:    w = prox(v),  y = rho_k (v - w)
+constexpr int R_DV = 241;    // feed-forward d_k (compact, 12)
+constexpr int R_YF = 253;    // multiplier method: yf[16] (compact rows)
+constexpr int R_YK = 269;    //                    yk[4]  (3 pins + surface row)
+constexpr int R_X = 273;     // solution x[9]
+constexpr int R_U = 282;     // solution u[12] (compact)
+constexpr int R_META = 294;  // 64 int32: [lane] meta (bits 0..2 slots, 4..11 contact id per slot), [32+lane] active set
+constexpr int REC = 296;     // 2368 bytes per instance and knot
+constexpr int GT = 64;       // general friction table per knot: per slot G (12, row-major 4x3) + e2 (4)
 constexpr int INFO = 12;     // per-instance statistics (cmpc_get_stats)
-
-CMPC_HD int even_up(int n) { return (n + 1) & ~1; }
-CMPC_HD int fac_off_K(int na) { return even_up(na * na); }
-CMPC_HD int fac_off_Pc(int na) { return even_up(na * na) + even_up(9 * na); }
 
 enum Status { ST_OK = 0, ST_QP_MAXITER = 1, ST_QP_NUMERIC = 2 };
 
@@ -76,15 +83,9 @@ struct Batch {
   const int* cact;        // [Bp][N][nc]
   long plan_stride;       // 0 (shared plan) or 1
   // workspace
-  double* stg;            // [B][N+1][SG]
-  double* sta;            // [B][N+1][ST]
-  double* fac;            // [B][N][FAC]
-  double* dvec;           // [B][N][DVC]
-  double* pm;             // [B][N+1][PM]
-  double* sol;            // [B][N+1][SOL]
-  double* gtab;           // [B][N][MAXC][16]  general friction rows G (12) + e2 (4) per slot; null when fast
-  int* meta;              // [B][N+1]  bits 0..2: slots, bits 4..11: contact id per slot (2 bits each)
-  int* pmask;             // [B][N+1]  active set of the multiplier method
+  double* ws;             // [tiles][N+1][REC][32]
+  double* gtab;           // [tiles][N][GT][32]   general friction rows; null on the fast path
+  int* nst;               // [tiles][N+1]         slots per knot of the tile
   // outputs
   double* X_out;          // [B][N+1][9]
   double* U_out;          // [B][N][nu]
@@ -97,29 +98,6 @@ struct Batch {
                           //            multiplier-method sweeps, polish attempts, 2 spare
 };
 
-// Per-warp shared-memory scratch (factorisation, evaluate); 4.6 KB -> 28 instances per SM.
-constexpr int MS = 21;     // row stride of the Gauss-Jordan tableau [Huu | Hux]
-struct WarpMem {
-  double P[81];            // P_{k+1} (row-major 9x9)
-  double PA[81];           // P A
-  double W[9 * MAXU];      // P B  (row stride 12)
-  double M[MAXU * MS];     // [Huu | Hux] -> [Hinv | Huu^-1 Hux]
-  double HX[MAXU * 9];     // Hux kept for the P update
-  double pcol[MAXU + 4];   // pivot column
-  double T[81];            // P_k before symmetrisation / Gram matrix in evaluate()
-};
-
-struct Ctx {
-  const Params* prm;
-  Batch bt;
-  WarpMem* s;
-  int b;   // instance
-  const double* cpos; const double* cR; const int* cact;   // this instance's plan
-  const double* Xr; const double* Ui; const double* xi; const double* xf;
-  double* stg; double* sta; double* fac; double* dvec; double* pm; double* sol; double* gtab;
-  int* meta; int* pmask;
-};
-
 // ------------------------------------------------------------------------------------------
 // closed-form model pieces (scalar; used by setup, evaluate and the linearise/rollout kernels)
 // ------------------------------------------------------------------------------------------
@@ -128,36 +106,39 @@ CMPC_HD void cross3(const double* a, const double* b, double* o) {
   o[1] = a[2] * b[0] - a[0] * b[2];
   o[2] = a[0] * b[1] - a[1] * b[0];
 }
-CMPC_HD int nxt3(int a) { return a == 2 ? 0 : a + 1; }
-CMPC_HD int prv3(int a) { return a == 0 ? 2 : a - 1; }
+CMPC_HD constexpr int nxt3(int a) { return a == 2 ? 0 : a + 1; }
+CMPC_HD constexpr int prv3(int a) { return a == 0 ? 2 : a - 1; }
 
-// K1: dynamics, closed-form Jacobian data and affine term for one knot
+// K1: closed-form Jacobian data and affine term of one knot
 //     (centroidal_model.py:189-232), point-contact model:
 //     A_k = I + dt [[0, I/m, 0],[0,0,0],[[S]x,0,0]],  S = sum_i a_i fbar_i
 //     B_k[:,3s:3s+3] = dt [0; I; [d_s]x],              d_s = p_s - cbar
 //     c_k = fbar - A xbar - B ubar = [0; dt m g e_z; -dt S x cbar]
-// Writes the stage record and returns the meta word (slots | contact ids << 4).
-CMPC_HD int linearize_knot(const Params& P, const double* xbar, const double* ubar, const double* cpos,
-                           const int* cact, int terminal, double* rec) {
-  for (int i = 0; i < SG; ++i) rec[i] = 0.0;
-  for (int i = 0; i < NX; ++i) rec[SG_XB + i] = xbar[i];
-  if (terminal) return 0;   // terminal knot: no dynamics, no controls
-  double S[3] = {0.0, 0.0, 0.0};
+struct KnotLin {
+  double S[3], ck[3], d[MAXU];
+  int meta;   // slots | contact id per slot << 4
+};
+CMPC_HD void linearize_knot(const Params& P, const double* xbar, const double* ubar, const double* cpos,
+                            const int* cact, int terminal, KnotLin& o) {
+  for (int i = 0; i < 3; ++i) o.S[i] = o.ck[i] = 0.0;
+  for (int i = 0; i < MAXU; ++i) o.d[i] = 0.0;
+  o.meta = 0;
+  if (terminal) return;   // terminal knot: no dynamics, no controls
   int slot = 0, code = 0;
   for (int c = 0; c < P.nc; ++c) {
     if (cact[c]) {
       for (int a = 0; a < 3; ++a) {
-        S[a] += ubar[3 * c + a];
-        rec[SG_D + 3 * slot + a] = cpos[3 * c + a] - xbar[a];
+        o.S[a] += ubar[3 * c + a];
+        o.d[3 * slot + a] = cpos[3 * c + a] - xbar[a];
       }
       code |= c << (2 * slot);
       ++slot;
     }
   }
   double Sxc[3];
-  cross3(S, xbar, Sxc);
-  for (int a = 0; a < 3; ++a) { rec[SG_S + a] = S[a]; rec[SG_CK + a] = -P.dt * Sxc[a]; }
-  return slot | (code << 4);
+  cross3(o.S, xbar, Sxc);
+  for (int a = 0; a < 3; ++a) o.ck[a] = -P.dt * Sxc[a];
+  o.meta = slot | (code << 4);
 }
 
 // x+ = f(x,u) (centroidal_model.py:189-212), full (per-contact) control layout

@@ -72,14 +72,15 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   return 0;
 }
 
-// workspace sizes in doubles / ints for a batch
-struct WsSizes { long stg, sta, fac, dvec, pm, sol, gtab, info, meta, pmask; };
+// workspace sizes for a batch: doubles of the knot records / friction table, ints of the slot table
+struct WsSizes { long tiles, ws, gtab, nst, info; };
 inline WsSizes ws_sizes(int B, int N) {
   WsSizes w;
-  w.stg = (long)B * (N + 1) * SG; w.sta = (long)B * (N + 1) * ST;
-  w.fac = (long)B * N * FAC; w.dvec = (long)B * N * DVC; w.pm = (long)B * (N + 1) * PM;
-  w.sol = (long)B * (N + 1) * SOL; w.gtab = (long)B * N * MAXC * 16;
-  w.info = (long)B * INFO; w.meta = (long)B * (N + 1); w.pmask = (long)B * (N + 1);
+  w.tiles = (B + TL - 1) / TL;
+  w.ws = w.tiles * (N + 1) * (long)(REC * TL);
+  w.gtab = w.tiles * N * (long)(GT * TL);
+  w.nst = w.tiles * (N + 1);
+  w.info = (long)B * INFO;
   return w;
 }
 

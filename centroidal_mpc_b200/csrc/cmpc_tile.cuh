@@ -1,0 +1,1216 @@
+// cmpc_tile.cuh — the SCP solver of one MPC instance, written as plain scalar code that runs
+// once per LANE: Riccati factorisation, ADMM / multiplier-method sweeps, certified active-set
+// polish, trust-region loop.  32 instances (a tile) share a warp; each lane walks its own
+// column of the lane-interleaved knot records (cmpc_core.cuh), so every load and store of the
+// warp is one coalesced 256-byte access and no lane ever talks to another.  DESIGN.md "device
+// algorithm" has the mathematics; oracle/device_model.py is the executable numpy specification.
+//
+// Control flow: every lane owns a small state machine (advance()) that names the next whole-
+// horizon operation it needs (factorise, sweep, build active set, evaluate, ...).  The warp
+// executes one operation at a time for the lanes that asked for it (run_tile in cmpc_api.cu),
+// so lanes whose QPs need more iterations or polish rounds do not change what the others
+// compute.  The host build (tests/emu) runs the same state machine one lane at a time: the
+// arithmetic of a lane does not depend on its neighbours, so both builds are bit-identical
+// (FMA contraction is explicit, automatic contraction is off in both).
+#pragma once
+#include "cmpc_core.cuh"
+
+namespace cmpc {
+
+constexpr int MODE_ADMM = 0, MODE_PMM = 1;
+// forward-sweep kinds
+constexpr int FW_ADMM = 0, FW_ADMM_CHECK = 1, FW_PMM = 2, FW_PMM_UPD = 3, FW_COPY = 4;
+
+#define CMPC_R(p, f) (p)[(f) * TL]
+
+struct TileCtx {
+  const Params* prm;
+  double* ws;      // tile workspace [N+1][REC][32]
+  double* gt;      // tile friction table [N][GT][32], null on the fast path
+  int* nst;        // [N+1] slots per knot (tile maximum; 0 at the terminal knot)
+};
+
+struct Inst {
+  int b, lane;
+  const double *Xr, *Ui, *xi, *xf, *cpos, *cR;
+  const int* cact;
+};
+
+CMPC_HD double* rec_of(const TileCtx& T, const Inst& I, int k) { return T.ws + (long)k * (REC * TL) + I.lane; }
+CMPC_HD int* meta_of(const TileCtx& T, const Inst& I, int k) {
+  return reinterpret_cast<int*>(T.ws + (long)k * (REC * TL) + R_META * TL) + I.lane;   // [0] meta, [32] active set
+}
+CMPC_HD double* gt_of(const TileCtx& T, const Inst& I, int k) { return T.gt ? T.gt + (long)k * (GT * TL) + I.lane : nullptr; }
+
+// Solver scalars of one lane.
+struct Sv {
+  double rho, rhok, rhoe, rhoep, radius, weight;
+  double pri, dua, npri, ndua;     // last residuals
+  double nq, dynrow;               // constant parts of the residual norms
+  int kap;                         // multiplier method: some knot has trust-region rows
+  int fail;                        // a pivot was not positive
+  int n_pmm, n_polish;             // statistics: multiplier-method sweeps, polish attempts
+  double ye[9];                    // multiplier of x_N = x_final
+};
+
+// ---------------------------------------------------------------- friction rows
+// G = pyr4 * R^T, pyr4 = [[1,0,-k],[-1,0,-k],[0,1,-k],[0,-1,-k]], k = mu/sqrt2
+// (utils.py:9-16, constraints.py:178-184); e2 = row equilibration under D_u = 1/sqrt(W_u).
+// Fast path (identity R, same W_u for all contacts): constants; else the per-knot table.
+CMPC_HD double pyr4(const Params& P, int row, int a) {
+  if (a == 2) return -P.kf;
+  if (a == 0) return row == 0 ? 1.0 : (row == 1 ? -1.0 : 0.0);
+  return row == 2 ? 1.0 : (row == 3 ? -1.0 : 0.0);
+}
+
+template <bool FAST> struct Fric;
+template <> struct Fric<true> {
+  double kf, ea, eb;
+  CMPC_HD void load(const Params& P, const double*, int) { kf = P.kf; ea = P.e2[0]; eb = P.e2[2]; }
+  CMPC_HD double e2(int r) const { return r < 2 ? ea : eb; }
+  CMPC_HD double G(int r, int a) const {
+    if (a == 2) return -kf;
+    if (a == 0) return r == 0 ? 1.0 : (r == 1 ? -1.0 : 0.0);
+    return r == 2 ? 1.0 : (r == 3 ? -1.0 : 0.0);
+  }
+  CMPC_HD void rows(const double* u, double* cf) const {          // cf = G u
+    cf[0] = fma(-kf, u[2], u[0]);
+    cf[1] = fma(-kf, u[2], -u[0]);
+    cf[2] = fma(-kf, u[2], u[1]);
+    cf[3] = fma(-kf, u[2], -u[1]);
+  }
+  CMPC_HD void trans(const double* t, double* o) const {          // o = G' t
+    o[0] = t[0] - t[1];
+    o[1] = t[2] - t[3];
+    o[2] = -kf * ((t[0] + t[1]) + (t[2] + t[3]));
+  }
+};
+template <> struct Fric<false> {
+  double g[12], e[4];
+  CMPC_HD void load(const Params&, const double* gt, int s) {
+    for (int i = 0; i < 12; ++i) g[i] = CMPC_R(gt, s * 16 + i);
+    for (int i = 0; i < 4; ++i) e[i] = CMPC_R(gt, s * 16 + 12 + i);
+  }
+  CMPC_HD double e2(int r) const { return e[r]; }
+  CMPC_HD double G(int r, int a) const { return g[r * 3 + a]; }
+  CMPC_HD void rows(const double* u, double* cf) const {
+    for (int r = 0; r < 4; ++r) cf[r] = fma(g[r * 3 + 2], u[2], fma(g[r * 3 + 1], u[1], g[r * 3] * u[0]));
+  }
+  CMPC_HD void trans(const double* t, double* o) const {
+    for (int a = 0; a < 3; ++a) o[a] = fma(g[9 + a], t[3], fma(g[6 + a], t[2], fma(g[3 + a], t[1], g[a] * t[0])));
+  }
+};
+
+// ---------------------------------------------------------------- trust-region prox
+// argmin_v omega*max(0, |v - kbar|_1 - r) + rho/2 |v - a|^2  (oracle/device_model.py prox_trust)
+// branch 0: inside the L1 ball; 1: outside after soft-thresholding; 2: on the surface.
+CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double omega, double rho, double* w) {
+  double b[3], ab[3];
+  double s1 = 0.0;
+  for (int i = 0; i < 3; ++i) { b[i] = a[i] - kbar[i]; ab[i] = fabs(b[i]); s1 += ab[i]; }
+  if (s1 <= r) { for (int i = 0; i < 3; ++i) w[i] = a[i]; return 0; }
+  double tau = omega / rho, s2 = 0.0, d[3];
+  for (int i = 0; i < 3; ++i) { d[i] = fmax(ab[i] - tau, 0.0); s2 += d[i]; }
+  if (s2 >= r) {
+    for (int i = 0; i < 3; ++i) w[i] = kbar[i] + (b[i] < 0.0 ? -d[i] : d[i]);
+    return 1;
+  }
+  double s[3] = {ab[0], ab[1], ab[2]};   // projection onto the L1 ball: sort descending
+  if (s[0] < s[1]) { double t = s[0]; s[0] = s[1]; s[1] = t; }
+  if (s[1] < s[2]) { double t = s[1]; s[1] = s[2]; s[2] = t; }
+  if (s[0] < s[1]) { double t = s[0]; s[0] = s[1]; s[1] = t; }
+  double css = 0.0;
+  tau = 0.0;
+  for (int j = 0; j < 3; ++j) {
+    css += s[j];
+    double t = (css - r) / (double)(j + 1);
+    if (s[j] - t > 0.0) tau = t;
+  }
+  for (int i = 0; i < 3; ++i) {
+    double di = fmax(ab[i] - tau, 0.0);
+    w[i] = kbar[i] + (b[i] < 0.0 ? -di : di);
+  }
+  return 2;
+}
+CMPC_HD void prox_kappa(const Sv& S, const double* v, const double* kbar, double* w) {
+  prox_trust(v, kbar, S.radius, S.weight, S.rhok, w);
+}
+
+// ---------------------------------------------------------------- multiplier-method kappa rows
+// Penalty block kM (3x3) and linear term kl (3) of knot k from the active-set word pm and the
+// multipliers yk (only reached when S.kap).  Codes per component: 0 pinned to kbar, 1 sign +,
+// 2 sign -; branch (bits 16..17): 1 linear penalty, 2 surface row.
+CMPC_HD void pmm_kappa_terms(const Params& P, const Sv& S, int pm, const double* kbar, const double* yk, double* M,
+                             double* kl) {
+  for (int i = 0; i < 9; ++i) M[i] = 0.0;
+  for (int i = 0; i < 3; ++i) kl[i] = 0.0;
+  const int br = (pm >> 16) & 3;
+  if (br == 0) return;
+  const double inv = 1.0 / P.delta;
+  double sg[3];
+  for (int i = 0; i < 3; ++i) {
+    const int code = (pm >> (18 + 2 * i)) & 3;
+    sg[i] = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
+    if (code == 0) {   // pinned component: kappa_i = kbar_i
+      M[4 * i] += inv;
+      kl[i] -= inv * kbar[i] - yk[i];
+    }
+  }
+  if (br == 1) {
+    for (int i = 0; i < 3; ++i) kl[i] += S.weight * sg[i];
+  } else {             // surface: sg'(kappa - kbar) = radius
+    double bb = S.radius;
+    for (int i = 0; i < 3; ++i) bb += sg[i] * kbar[i];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) M[3 * i + j] += inv * sg[i] * sg[j];
+      kl[i] -= sg[i] * (inv * bb - yk[3]);
+    }
+  }
+}
+
+CMPC_HD void set_rho(const Params& P, double rho, double* rho_out, double* rhok_out, double* rhoe, double* rhoep) {
+  const double wk = fmin(P.Wx[6], fmin(P.Wx[7], P.Wx[8]));
+  double wm = 0.0;
+  for (int i = 0; i < 9; ++i) wm = fmax(wm, P.Wx[i]);
+  *rho_out = rho;
+  *rhok_out = rho * P.rho_k_rel * wk;
+  if (rhoe) *rhoe = P.rho_e_rel * wm;
+  if (rhoep) *rhoep = P.rho_e_pol_rel * wm;
+}
+
+// ---------------------------------------------------------------- Riccati factorisation
+// Backward over k.  The symmetric tableau  T = [[Huu, Hux],[Hux', Q + A'PA]]  (Huu = R + B'PB,
+// Hux = B'PA; lower triangle, u indices first) is swept on its na control pivots (SPD, no
+// pivoting):  T -> [[-Huu^-1, .],[Hux' Huu^-1, Q + A'PA - Hux' Huu^-1 Hux]], which delivers Hinv,
+// K = -Huu^-1 Hux and P_k in one pass and keeps all three exactly symmetric.  Pc = P c.
+// ADMM mode: R = W_u + rho G'E2G, Q = W_x + rho_k I (kappa); multiplier mode: active friction
+// rows and kappa rows carry the penalty 1/delta.
+CMPC_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <int MODE, bool FAST>
+CMPC_FN void factor_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
+  const int N = P.N;
+  const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
+  const double inv = 1.0 / P.delta;
+  double Pm[81], PA[81], W[9 * MAXU], Tb[231], col[21], kM[9], kl[3];
+  for (int i = 0; i < 81; ++i) Pm[i] = 0.0;
+  for (int i = 0; i < 9; ++i) Pm[10 * i] = P.Wx[i] + rho_e;
+  if (MODE == MODE_ADMM) {
+    for (int i = 6; i < 9; ++i) Pm[10 * i] += S.rhok;
+  } else if (S.kap) {
+    const double* r = rec_of(T, I, N);
+    const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+    const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
+    pmm_kappa_terms(P, S, meta_of(T, I, N)[32], kb, yk, kM, kl);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Pm[(6 + i) * 9 + 6 + j] += kM[3 * i + j];
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    double* r = rec_of(T, I, k);
+    const int* im = meta_of(T, I, k);
+    const double* gt = gt_of(T, I, k);
+    const int ns = T.nst[k], na = 3 * ns, n = na + 9;
+    const int mt = im[0], nsl = mt & 7;
+    const int pm = (MODE == MODE_PMM) ? im[32] : 0;
+    const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+    const double ck[3] = {CMPC_R(r, R_CK), CMPC_R(r, R_CK + 1), CMPC_R(r, R_CK + 2)};
+    double d[MAXU];
+    for (int j = 0; j < na; ++j) d[j] = CMPC_R(r, R_D + j);
+    // PA = P A, Pc = P c
+    for (int i = 0; i < 9; ++i) {
+      const double* pr = Pm + 9 * i;
+      for (int q = 0; q < 3; ++q) {     // (P [S]x)[i][q] = P[i][6+q1] S[q2] - P[i][6+q2] S[q1]
+        const int q1 = nxt3(q), q2 = prv3(q);
+        PA[9 * i + q] = fma(P.dt, fma(pr[6 + q1], S3[q2], -(pr[6 + q2] * S3[q1])), pr[q]);
+        PA[9 * i + 3 + q] = fma(P.dt_m, pr[q], pr[3 + q]);
+        PA[9 * i + 6 + q] = pr[6 + q];
+      }
+      double pc = pr[5] * P.dtmg;
+      pc = fma(pr[6], ck[0], pc);
+      pc = fma(pr[7], ck[1], pc);
+      pc = fma(pr[8], ck[2], pc);
+      CMPC_R(r, R_PC + i) = pc;
+    }
+    // W = P B:  (P B)[i][(s,a)] = dt_s (P[i][3+a] + P[i][6+a1] d[a2] - P[i][6+a2] d[a1])
+    for (int s = 0; s < ns; ++s) {
+      const double dts = s < nsl ? P.dt : 0.0;
+      const double* ds = d + 3 * s;
+      for (int a = 0; a < 3; ++a) {
+        const int a1 = nxt3(a), a2 = prv3(a);
+        for (int i = 0; i < 9; ++i) {
+          const double* pr = Pm + 9 * i;
+          W[i * MAXU + 3 * s + a] = dts * fma(pr[6 + a1], ds[a2], fma(-pr[6 + a2], ds[a1], pr[3 + a]));
+        }
+      }
+    }
+    // tableau: rows (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
+    for (int s = 0; s < ns; ++s) {
+      const double dts = s < nsl ? P.dt : 0.0;
+      const double* ds = d + 3 * s;
+      Fric<FAST> fr;
+      fr.load(P, gt, s);
+      double rr[4];
+      for (int row = 0; row < 4; ++row) {
+        if (MODE == MODE_ADMM) rr[row] = S.rho * fr.e2(row);
+        else rr[row] = ((pm >> (4 * s + row)) & 1) ? inv : 0.0;
+      }
+      const int cid = (s < nsl) ? ((mt >> (4 + 2 * s)) & 3) : 0;
+      for (int a = 0; a < 3; ++a) {
+        const int a1 = nxt3(a), a2 = prv3(a), j = 3 * s + a;
+        for (int l = 0; l <= j; ++l) {
+          double v = dts * fma(W[(6 + a1) * MAXU + l], ds[a2], fma(-W[(6 + a2) * MAXU + l], ds[a1], W[(3 + a) * MAXU + l]));
+          if (l >= 3 * s) {   // R block of the slot: W_u + G' diag(rr) G
+            const int b2 = l - 3 * s;
+            double radd = (b2 == a) ? (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) : 0.0;
+            for (int row = 0; row < 4; ++row) radd = fma(rr[row] * fr.G(row, a), fr.G(row, b2), radd);
+            v += radd;
+          }
+          Tb[tri(j, l)] = v;
+        }
+        for (int q = 0; q < 9; ++q)
+          Tb[tri(na + q, j)] = dts * fma(PA[(6 + a1) * 9 + q], ds[a2], fma(-PA[(6 + a2) * 9 + q], ds[a1], PA[(3 + a) * 9 + q]));
+      }
+    }
+    // Q + A'(PA), lower triangle
+    if (MODE == MODE_PMM && S.kap && k >= 1) {
+      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+      const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
+      pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
+    }
+    for (int rr2 = 0; rr2 < 9; ++rr2) {
+      const int g3 = rr2 / 3, a = rr2 - 3 * g3, a1 = nxt3(a), a2 = prv3(a);
+      for (int c = 0; c <= rr2; ++c) {
+        double v = PA[rr2 * 9 + c];
+        if (g3 == 0) v = fma(P.dt, fma(PA[(6 + a1) * 9 + c], S3[a2], -(PA[(6 + a2) * 9 + c] * S3[a1])), v);
+        else if (g3 == 1) v = fma(P.dt_m, PA[a * 9 + c], v);
+        if (c == rr2) {
+          v += P.Wx[rr2];
+          if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
+        }
+        if (MODE == MODE_PMM && S.kap && k >= 1 && c >= 6) v += kM[3 * (rr2 - 6) + (c - 6)];
+        Tb[tri(na + rr2, na + c)] = v;
+      }
+    }
+    // sweep the control pivots
+    for (int pv = 0; pv < na; ++pv) {
+      const double piv = Tb[tri(pv, pv)];
+      if (!(piv > 0.0)) S.fail = 1;
+      const double ip = 1.0 / piv;
+      for (int i = 0; i < n; ++i) col[i] = i < pv ? Tb[tri(pv, i)] : Tb[tri(i, pv)];
+      for (int i = 0; i < n; ++i) {
+        if (i == pv) continue;
+        const double bi = col[i] * ip;
+        double* row = Tb + tri(i, 0);
+        for (int j = 0; j <= i; ++j)
+          if (j != pv) row[j] = fma(-bi, col[j], row[j]);
+      }
+      for (int i = 0; i < pv; ++i) Tb[tri(pv, i)] = col[i] * ip;
+      for (int i = pv + 1; i < n; ++i) Tb[tri(i, pv)] = col[i] * ip;
+      Tb[tri(pv, pv)] = -ip;
+    }
+    // factor record and P_k
+    for (int j = 0; j < na; ++j) {
+      for (int l = 0; l <= j; ++l) CMPC_R(r, R_HI + tri(j, l)) = -Tb[tri(j, l)];
+      for (int i = 0; i < 9; ++i) CMPC_R(r, R_K + 9 * j + i) = -Tb[tri(na + i, j)];
+    }
+    for (int i = 0; i < 9; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const double v = Tb[tri(na + i, na + j)];
+        Pm[9 * i + j] = v;
+        Pm[9 * j + i] = v;
+      }
+  }
+}
+
+// ---------------------------------------------------------------- backward sweep (linear term)
+// p_N = qx_N;  g = p + Pc;  hu = ru + B'g;  d = -Hinv hu;  p = qx + A'g + K'hu.
+// qx = -Wx xbar (+ kappa / terminal penalty terms), ru = friction penalty terms.
+template <int MODE>
+CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, const double* r, int pm, double* p) {
+  const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+  if (MODE == MODE_ADMM) {
+    const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+    double w[3];
+    prox_kappa(S, vk, kb, w);
+    for (int a = 0; a < 3; ++a) p[6 + a] += -S.rhok * (w[a] + w[a] - vk[a]);
+  } else if (S.kap) {
+    const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
+    double kM[9], kl[3];
+    pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
+    for (int a = 0; a < 3; ++a) p[6 + a] += kl[a];
+  }
+}
+
+template <int NS, int MODE, bool FAST>
+CMPC_HD void bwd_knot(const Params& P, const Sv& S, double* r, const int* im, const double* gt, int k, double* p) {
+  constexpr int NA = 3 * NS;
+  const int nsl = im[0] & 7;
+  const int pm = (MODE == MODE_PMM) ? im[32] : 0;
+  double g[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) g[i] = p[i] + CMPC_R(r, R_PC + i);
+  double hu[NA > 0 ? NA : 1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const double dts = s < nsl ? P.dt : 0.0;
+    const double ds[3] = {CMPC_R(r, R_D + 3 * s), CMPC_R(r, R_D + 3 * s + 1), CMPC_R(r, R_D + 3 * s + 2)};
+    Fric<FAST> fr;
+    fr.load(P, gt, s);
+    double t[4], o[3];
+#pragma unroll
+    for (int row = 0; row < 4; ++row) {
+      if (MODE == MODE_ADMM) {
+        t[row] = S.rho * fr.e2(row) * fabs(CMPC_R(r, R_VF + 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
+      } else {
+        const double y = CMPC_R(r, R_YF + 4 * s + row);
+        t[row] = ((pm >> (4 * s + row)) & 1) ? y : 0.0;
+      }
+    }
+    fr.trans(t, o);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int a1 = nxt3(a), a2 = prv3(a);
+      hu[3 * s + a] = dts * fma(g[6 + a1], ds[a2], fma(-g[6 + a2], ds[a1], g[3 + a])) + o[a];
+    }
+  }
+  // d = -Hinv hu (packed symmetric), K'hu
+  double acc[NA > 0 ? NA : 1], kh[9];
+#pragma unroll
+  for (int j = 0; j < NA; ++j) acc[j] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) kh[i] = 0.0;
+#pragma unroll
+  for (int j = 0; j < NA; ++j) {
+#pragma unroll
+    for (int l = 0; l <= j; ++l) {
+      const double h = CMPC_R(r, R_HI + j * (j + 1) / 2 + l);
+      acc[j] = fma(h, hu[l], acc[j]);
+      if (l < j) acc[l] = fma(h, hu[j], acc[l]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NA; ++j) CMPC_R(r, R_DV + j) = -acc[j];
+#pragma unroll
+  for (int j = 0; j < NA; ++j) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) kh[i] = fma(CMPC_R(r, R_K + 9 * j + i), hu[j], kh[i]);
+  }
+  // p = qx + A'g + K'hu
+  const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int a1 = nxt3(a), a2 = prv3(a);
+    p[a] = fma(P.dt, fma(g[6 + a1], S3[a2], -(g[6 + a2] * S3[a1])), g[a]) + kh[a] - P.Wx[a] * CMPC_R(r, R_XB + a);
+    p[3 + a] = fma(P.dt_m, g[a], g[3 + a]) + kh[3 + a] - P.Wx[3 + a] * CMPC_R(r, R_XB + 3 + a);
+    p[6 + a] = g[6 + a] + kh[6 + a] - P.Wx[6 + a] * CMPC_R(r, R_XB + 6 + a);
+  }
+  if (k >= 1) kappa_linear_term<MODE>(P, S, r, pm, p);
+}
+
+template <int MODE, bool FAST>
+CMPC_FN void backward_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S) {
+  const int N = P.N;
+  const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
+  double p[9];
+  {
+    const double* r = rec_of(T, I, N);
+    for (int i = 0; i < 9; ++i) p[i] = -(P.Wx[i] * CMPC_R(r, R_XB + i)) - (rho_e * I.xf[i] - S.ye[i]);
+    kappa_linear_term<MODE>(P, S, r, meta_of(T, I, N)[32], p);
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    double* r = rec_of(T, I, k);
+    const int* im = meta_of(T, I, k);
+    const double* gt = gt_of(T, I, k);
+    switch (T.nst[k]) {
+      case 0: bwd_knot<0, MODE, FAST>(P, S, r, im, gt, k, p); break;
+      case 1: bwd_knot<1, MODE, FAST>(P, S, r, im, gt, k, p); break;
+      case 2: bwd_knot<2, MODE, FAST>(P, S, r, im, gt, k, p); break;
+      case 3: bwd_knot<3, MODE, FAST>(P, S, r, im, gt, k, p); break;
+      default: bwd_knot<4, MODE, FAST>(P, S, r, im, gt, k, p); break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- forward sweep + local updates
+// u~ = K x~ + d,  x~+ = A x~ + B u~ + c.
+// ADMM kinds: relaxation, friction / kappa / terminal updates of (w, y) stored as v, all
+// knot-local; with CHECK also OSQP's residuals (oracle/device_model.py iterate()).
+// Multiplier kinds: y += (1/delta) row on the active rows, solution record, primal residual,
+// and (UPD) the corrected friction active set: violated rows join, rows with a negative
+// multiplier leave; the number of changes is accumulated in nchg.
+// COPY: read-only LQR roll-out of the ADMM iterate into the solution record.
+struct Res { double pri, dua, npri, ndua; };
+
+template <int KIND>
+CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, double* r, const int* im, const Inst& I, int k, const double* x) {
+  constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
+  constexpr bool PMMK = KIND == FW_PMM || KIND == FW_PMM_UPD, COPY = KIND == FW_COPY;
+  const int N = P.N;
+  const double al = ADMM ? P.alpha : 1.0;
+  if (PMMK || COPY) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) CMPC_R(r, R_X + i) = x[i];
+  }
+  double rdx[3] = {0.0, 0.0, 0.0};
+  if (k >= 1) {
+    if (ADMM) {
+      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+      const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+      double w[3], vn[3];
+      prox_kappa(S, vk, kb, w);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        vn[a] = fma(al, x[6 + a], fma(1.0 - al, w[a], vk[a] - w[a]));
+        CMPC_R(r, R_VK + a) = vn[a];
+      }
+      if (CHK) {
+        double wn[3];
+        prox_kappa(S, vn, kb, wn);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          R.pri = fmax(R.pri, fabs(x[6 + a] - wn[a]));
+          R.npri = fmax(R.npri, fmax(fabs(x[6 + a]), fabs(wn[a])));
+          rdx[a] = S.rhok * ((vn[a] - wn[a]) - (vk[a] - w[a]) - (x[6 + a] - w[a]));
+        }
+      }
+    } else if (PMMK) {
+      if (S.kap) {
+        const int pm = im[32];
+        const int br = (pm >> 16) & 3;
+        if (br != 0) {
+          const double inv = 1.0 / P.delta;
+          double accv = -S.radius;
+          for (int i = 0; i < 3; ++i) {
+            const int code = (pm >> (18 + 2 * i)) & 3;
+            const double sgn = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
+            const double dk = x[6 + i] - CMPC_R(r, R_XB + 6 + i);
+            if (code == 0) CMPC_R(r, R_YK + i) += inv * dk;
+            accv += sgn * dk;
+          }
+          if (br == 2) CMPC_R(r, R_YK + 3) += inv * accv;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) R.npri = fmax(R.npri, fabs(x[6 + a]));
+    }
+  }
+  if (k == N && !COPY) {   // terminal equality
+    const double re = ADMM ? S.rhoe : S.rhoep;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double dx = x[i] - I.xf[i];
+      S.ye[i] = S.ye[i] + (re * al) * dx;
+      if (CHK || PMMK) {
+        R.pri = fmax(R.pri, fabs(dx));
+        R.npri = fmax(R.npri, fmax(fabs(x[i]), fabs(I.xf[i])));
+        // no stationarity term: the certificate uses y_e + rho_e (x_N - x_f) for these equality
+        // rows, the multiplier of the x-update itself (any value is admissible on an equality)
+      }
+    }
+  }
+  if (CHK && k >= 1) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double Px = P.Wx[i] * x[i];
+      const double rd = i >= 6 ? rdx[i - 6] : 0.0;
+      const double aty = rd - Px + P.Wx[i] * CMPC_R(r, R_XB + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
+      R.dua = fmax(R.dua, fabs(rd));
+      R.ndua = fmax(R.ndua, fmax(fabs(Px), fabs(aty)));
+    }
+  }
+}
+
+template <int NS, int KIND, bool FAST>
+CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, double* r, int* im, const double* gt, double* x, int& nchg) {
+  constexpr int NA = 3 * NS;
+  constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
+  constexpr bool PMMK = KIND == FW_PMM || KIND == FW_PMM_UPD, UPD = KIND == FW_PMM_UPD, COPY = KIND == FW_COPY;
+  const double al = ADMM ? P.alpha : 1.0;
+  const double inv = 1.0 / P.delta;
+  // controls u~ = K x + d
+  double u[NA > 0 ? NA : 1];
+#pragma unroll
+  for (int j = 0; j < NA; ++j) {
+    double t = CMPC_R(r, R_DV + j);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t = fma(CMPC_R(r, R_K + 9 * j + i), x[i], t);
+    u[j] = t;
+  }
+  if (PMMK || COPY) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) CMPC_R(r, R_U + j) = u[j];
+  }
+  // next state
+  double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const double ds[3] = {CMPC_R(r, R_D + 3 * s), CMPC_R(r, R_D + 3 * s + 1), CMPC_R(r, R_D + 3 * s + 2)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int a1 = nxt3(a), a2 = prv3(a);
+      sF[a] = sF[a] + u[3 * s + a];
+      sT[a] = sT[a] + fma(ds[a1], u[3 * s + a2], -(ds[a2] * u[3 * s + a1]));
+    }
+  }
+  double xn[9];
+  {
+    const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int a1 = nxt3(a), a2 = prv3(a);
+      xn[a] = fma(P.dt_m, x[3 + a], x[a]);
+      xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
+      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_R(r, R_CK + a));
+    }
+  }
+  // friction rows of the knot
+  if (!COPY) {
+    const int mt = im[0];
+    const int pm = PMMK ? im[32] : 0;
+    int newpm = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      Fric<FAST> fr;
+      fr.load(P, gt, s);
+      double cf[4];
+      fr.rows(u + 3 * s, cf);
+      if (ADMM) {
+        double dl[4];
+#pragma unroll
+        for (int row = 0; row < 4; ++row) {
+          const double v = CMPC_R(r, R_VF + 4 * s + row);
+          const double w0 = fmin(v, 0.0), y0 = fmax(v, 0.0);
+          const double vn = fma(al, cf[row], fma(1.0 - al, w0, y0));
+          CMPC_R(r, R_VF + 4 * s + row) = vn;
+          if (CHK) {
+            const double wn = fmin(vn, 0.0);
+            R.pri = fmax(R.pri, fabs(cf[row] - wn));
+            R.npri = fmax(R.npri, fmax(fabs(cf[row]), fabs(wn)));
+            dl[row] = S.rho * fr.e2(row) * (fmax(vn, 0.0) - y0 - cf[row] + w0);
+          }
+        }
+        if (CHK) {   // u rows of the stationarity residual: G' delta; norms of P u and A'y
+          double rdu[3];
+          fr.trans(dl, rdu);
+          const int cid = (s < (mt & 7)) ? ((mt >> (4 + 2 * s)) & 3) : 0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const double Pu = (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) * u[3 * s + a];
+            R.dua = fmax(R.dua, fabs(rdu[a]));
+            R.ndua = fmax(R.ndua, fmax(fabs(Pu), fabs(rdu[a] - Pu)));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int row = 0; row < 4; ++row) {
+          const int bit = 4 * s + row;
+          const bool on = (pm >> bit) & 1;
+          const double yold = CMPC_R(r, R_YF + bit);
+          const double yn = fma(inv, cf[row], on ? yold : 0.0);
+          R.pri = fmax(R.pri, on ? fabs(cf[row]) : fmax(cf[row], 0.0));
+          R.npri = fmax(R.npri, fabs(cf[row]));
+          if (UPD) {
+            const bool keep = on && !(yn < 0.0);
+            const bool join = !on && (cf[row] > P.as_tol);
+            const bool nb = keep || join;
+            nchg += (nb != on) ? 1 : 0;
+            CMPC_R(r, R_YF + bit) = keep ? yn : 0.0;
+            newpm |= (nb ? 1 : 0) << bit;
+          } else {
+            CMPC_R(r, R_YF + bit) = on ? yn : yold;
+          }
+        }
+      }
+    }
+    if (UPD) im[32] = (pm & ~0xffff) | newpm;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) x[i] = xn[i];
+}
+
+template <int KIND, bool FAST>
+CMPC_FN void forward_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S, int* changes) {
+  constexpr bool CHK = KIND == FW_ADMM_CHECK, PMMK = KIND == FW_PMM || KIND == FW_PMM_UPD;
+  const int N = P.N;
+  Res R;
+  R.pri = R.dua = R.npri = R.ndua = 0.0;
+  int nchg = 0;
+  double x[9];
+  for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
+  for (int k = 0; k <= N; ++k) {
+    double* r = rec_of(T, I, k);
+    int* im = meta_of(T, I, k);
+    fwd_state<KIND>(P, S, R, r, im, I, k, x);
+    if (k == N) break;
+    const double* gt = gt_of(T, I, k);
+    switch (T.nst[k]) {
+      case 0: fwd_knot<0, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
+      case 1: fwd_knot<1, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
+      case 2: fwd_knot<2, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
+      case 3: fwd_knot<3, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
+      default: fwd_knot<4, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
+    }
+  }
+  if (CHK || PMMK) {
+    S.pri = R.pri;
+    S.npri = fmax(R.npri, S.dynrow);
+    if (CHK) {
+      S.dua = R.dua;
+      S.ndua = fmax(R.ndua, S.nq);
+    }
+  }
+  if (changes) *changes = nchg;
+}
+
+// ---------------------------------------------------------------- rho change: keep (w, y), move v
+CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, double rho_new, double rhok_new) {
+  const double ratio = S.rho / rho_new;
+  for (int k = 0; k <= P.N; ++k) {
+    double* r = rec_of(T, I, k);
+    if (k < P.N) {
+      const int nr = 4 * T.nst[k];
+      for (int j = 0; j < nr; ++j) {
+        const double v = CMPC_R(r, R_VF + j);
+        CMPC_R(r, R_VF + j) = fma(ratio, fmax(v, 0.0), fmin(v, 0.0));
+      }
+    }
+    if (k >= 1) {
+      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+      const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+      double w[3];
+      prox_kappa(S, vk, kb, w);
+      for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = fma(S.rhok / rhok_new, vk[a] - w[a], w[a]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- active set of the polish
+// Friction row active iff its multiplier is positive (OSQP's rule -w < y <=> v > 0); trust-
+// region rows by the branch the prox took.  Returns 1 when some knot has trust-region rows.
+template <bool FAST>
+CMPC_FN int build_active_set_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S) {
+  const int N = P.N;
+  int kap = 0;
+  for (int k = 0; k <= N; ++k) {
+    double* r = rec_of(T, I, k);
+    int* im = meta_of(T, I, k);
+    int pm = 0;
+    if (k < N) {
+      const int ns = T.nst[k];
+      const double* gt = gt_of(T, I, k);
+      for (int s = 0; s < ns; ++s) {
+        Fric<FAST> fr;
+        fr.load(P, gt, s);
+        for (int row = 0; row < 4; ++row) {
+          const double v = CMPC_R(r, R_VF + 4 * s + row);
+          const bool on = v > 0.0;
+          if (on) pm |= 1 << (4 * s + row);
+          CMPC_R(r, R_YF + 4 * s + row) = on ? S.rho * fr.e2(row) * v : 0.0;
+        }
+      }
+    }
+    if (k >= 1) {
+      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+      const double a3[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+      double w[3], yk4[4] = {0.0, 0.0, 0.0, 0.0};
+      const int br = prox_trust(a3, kb, S.radius, S.weight, S.rhok, w);
+      if (br != 0) {
+        kap = 1;
+        pm |= br << 16;
+        double msum = 0.0;
+        int nz = 0;
+        for (int i = 0; i < 3; ++i) {
+          const double d = w[i] - kb[i];
+          const double yk = S.rhok * (a3[i] - w[i]);
+          const int code = d > 0.0 ? 1 : (d < 0.0 ? 2 : 0);
+          pm |= code << (18 + 2 * i);
+          if (code == 0) yk4[i] = yk;
+          else { msum += (code == 1 ? yk : -yk); ++nz; }
+        }
+        if (br == 2) yk4[3] = nz ? msum / nz : 0.0;
+      }
+      for (int i = 0; i < 4; ++i) CMPC_R(r, R_YK + i) = yk4[i];
+    }
+    im[32] = pm;
+  }
+  return kap;
+}
+
+// ---------------------------------------------------------------- trust test and accuracy ratio
+// sigma_max(X - Xbar) via the 9x9 Gram matrix + cyclic Jacobi (scp_solver.py:151: np.linalg.norm(.,2));
+// rho = sum ||(f(x,u) - lin)[6:9]||^2 / sum ||lin||^2 (scp_solver.py:71-87).
+CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, double* snorm, double* num_out, double* den_out) {
+  const int N = P.N;
+  double A[81];
+  for (int i = 0; i < 81; ++i) A[i] = 0.0;
+  double num = 0.0, den = 0.0;
+  for (int k = 0; k <= N; ++k) {
+    const double* r = rec_of(T, I, k);
+    double x[9], dx[9];
+    for (int i = 0; i < 9; ++i) { x[i] = CMPC_R(r, R_X + i); dx[i] = x[i] - I.Xr[k * 9 + i]; }
+    for (int i = 0; i < 9; ++i)
+      for (int j = i; j < 9; ++j) A[i * 9 + j] = fma(dx[i], dx[j], A[i * 9 + j]);
+    if (k == N) break;
+    const int mt = meta_of(T, I, k)[0];
+    const int ns = mt & 7;
+    double u[MAXU];
+    for (int i = 0; i < MAXU; ++i) u[i] = 0.0;
+    double F[3] = {0, 0, 0}, Tq[3] = {0, 0, 0};
+    for (int sl = 0; sl < ns; ++sl) {
+      const int cid = (mt >> (4 + 2 * sl)) & 3;
+      const double ds[3] = {CMPC_R(r, R_D + 3 * sl), CMPC_R(r, R_D + 3 * sl + 1), CMPC_R(r, R_D + 3 * sl + 2)};
+      const double us[3] = {CMPC_R(r, R_U + 3 * sl), CMPC_R(r, R_U + 3 * sl + 1), CMPC_R(r, R_U + 3 * sl + 2)};
+      double t[3];
+      cross3(ds, us, t);
+      for (int a = 0; a < 3; ++a) {
+        u[3 * cid + a] = us[a];
+        F[a] += us[a];
+        Tq[a] += t[a];
+      }
+    }
+    // lin = A x + B u + c with the structured A, B
+    const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+    double lin[9], nl[9], Sxc[3];
+    cross3(S3, x, Sxc);
+    for (int a = 0; a < 3; ++a) {
+      lin[a] = x[a] + P.dt_m * x[3 + a];
+      lin[3 + a] = x[3 + a] + P.dt * F[a] + (a == 2 ? P.dtmg : 0.0);
+      lin[6 + a] = x[6 + a] + P.dt * Sxc[a] + P.dt * Tq[a] + CMPC_R(r, R_CK + a);
+    }
+    step_knot(P, x, u, I.cpos + (long)k * P.nc * 3, I.cact + (long)k * P.nc, nl);
+    for (int i = 6; i < 9; ++i) num += (nl[i] - lin[i]) * (nl[i] - lin[i]);
+    for (int i = 0; i < 9; ++i) den += lin[i] * lin[i];
+  }
+  *num_out = num;
+  *den_out = den;
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < i; ++j) A[i * 9 + j] = A[j * 9 + i];
+  // largest eigenvalue of the Gram matrix: cyclic Jacobi
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < 9; ++i)
+      for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
+    double dg = 0.0;
+    for (int i = 0; i < 9; ++i) dg += A[i * 9 + i] * A[i * 9 + i];
+    if (off <= 1e-30 * dg || off == 0.0) break;
+    for (int p = 0; p < 8; ++p) {
+      for (int q = p + 1; q < 9; ++q) {
+        double apq = A[p * 9 + q];
+        if (apq == 0.0) continue;
+        double th = (A[q * 9 + q] - A[p * 9 + p]) / (2.0 * apq);
+        double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+        double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (int rr = 0; rr < 9; ++rr) {
+          double arp = A[rr * 9 + p], arq = A[rr * 9 + q];
+          A[rr * 9 + p] = cs * arp - sn * arq;
+          A[rr * 9 + q] = sn * arp + cs * arq;
+        }
+        for (int rr = 0; rr < 9; ++rr) {
+          double apr = A[p * 9 + rr], aqr = A[q * 9 + rr];
+          A[p * 9 + rr] = cs * apr - sn * aqr;
+          A[q * 9 + rr] = sn * apr + cs * aqr;
+        }
+      }
+    }
+  }
+  double mx = 0.0;
+  for (int i = 0; i < 9; ++i) mx = fmax(mx, A[i * 9 + i]);
+  *snorm = sqrt(mx);
+}
+
+// ---------------------------------------------------------------- per-instance setup
+// K1 for every knot, friction table when not on the fast path, start of the iterate at the
+// linearisation point, constant parts of the residual norms.
+CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
+  const int N = P.N;
+  double mq = 0.0, mc = 0.0;
+  for (int k = 0; k <= N; ++k) {
+    double* r = rec_of(T, I, k);
+    int* im = meta_of(T, I, k);
+    const int kk = k < N ? k : N - 1;
+    const double* xb = I.Xr + k * 9;
+    KnotLin L;
+    linearize_knot(P, xb, I.Ui + kk * P.nu, I.cpos + (long)kk * P.nc * 3, I.cact + (long)kk * P.nc, k == N, L);
+    for (int i = 0; i < 9; ++i) {
+      CMPC_R(r, R_XB + i) = xb[i];
+      mq = fmax(mq, fabs(P.Wx[i] * xb[i]));
+    }
+    for (int a = 0; a < 3; ++a) { CMPC_R(r, R_S + a) = L.S[a]; CMPC_R(r, R_CK + a) = L.ck[a]; }
+    for (int j = 0; j < MAXU; ++j) { CMPC_R(r, R_D + j) = L.d[j]; CMPC_R(r, R_DV + j) = 0.0; CMPC_R(r, R_U + j) = 0.0; }
+    for (int j = 0; j < 16; ++j) { CMPC_R(r, R_VF + j) = 0.0; CMPC_R(r, R_YF + j) = 0.0; }
+    for (int j = 0; j < 4; ++j) CMPC_R(r, R_YK + j) = 0.0;
+    for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = xb[6 + a];
+    im[0] = L.meta;
+    im[32] = 0;
+    if (k < N) {
+      mc = fmax(mc, fabs(P.dtmg));
+      for (int a = 0; a < 3; ++a) mc = fmax(mc, fabs(L.ck[a]));
+      const int ns = L.meta & 7;
+      double* gt = gt_of(T, I, k);
+      for (int sl = 0; sl < MAXC; ++sl) {
+        const int cid = sl < ns ? ((L.meta >> (4 + 2 * sl)) & 3) : 0;
+        double G[12];
+        for (int row = 0; row < 4; ++row) {
+          double mx = 0.0;
+          for (int a = 0; a < 3; ++a) {
+            double g = pyr4(P, row, a);
+            if (sl < ns && I.cR) {
+              const double* Rm = I.cR + ((long)k * P.nc + cid) * 9;
+              g = 0.0;
+              for (int b2 = 0; b2 < 3; ++b2) g += pyr4(P, row, b2) * Rm[a * 3 + b2];
+            }
+            G[row * 3 + a] = g;
+            mx = fmax(mx, fabs(g) / sqrt(P.Wu[3 * cid + a]));
+          }
+          if (gt) {
+            for (int a = 0; a < 3; ++a) CMPC_R(gt, sl * 16 + row * 3 + a) = G[row * 3 + a];
+            CMPC_R(gt, sl * 16 + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
+          }
+        }
+        if (sl < ns) {
+          const double* ub = I.Ui + k * P.nu + 3 * cid;
+          for (int row = 0; row < 4; ++row) {
+            double cf = 0.0;
+            for (int a = 0; a < 3; ++a) cf += G[row * 3 + a] * ub[a];
+            CMPC_R(r, R_VF + 4 * sl + row) = fmin(cf, 0.0);
+          }
+        }
+      }
+    }
+  }
+  S.nq = mq;
+  double mi = 0.0;
+  for (int i = 0; i < 9; ++i) mi = fmax(mi, fabs(I.xi[i]));
+  S.dynrow = fmax(mc, mi);
+  for (int i = 0; i < 9; ++i) S.ye[i] = 0.0;
+  S.kap = 0;
+  S.fail = 0;
+  S.n_pmm = S.n_polish = 0;
+  S.pri = S.dua = S.npri = S.ndua = 0.0;
+}
+
+CMPC_FN void write_solution_op(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out) {
+  const int N = P.N;
+  double* Xo = X_out + (long)I.b * (N + 1) * 9;
+  double* Uo = U_out + (long)I.b * N * P.nu;
+  for (int k = 0; k <= N; ++k) {
+    const double* r = rec_of(T, I, k);
+    for (int i = 0; i < 9; ++i) Xo[k * 9 + i] = CMPC_R(r, R_X + i);
+    if (k == N) break;
+    const int mt = meta_of(T, I, k)[0];
+    const int ns = mt & 7;
+    for (int j = 0; j < P.nu; ++j) Uo[k * P.nu + j] = 0.0;
+    for (int sl = 0; sl < ns; ++sl) {
+      const int cid = (mt >> (4 + 2 * sl)) & 3;
+      for (int a = 0; a < 3; ++a) Uo[k * P.nu + 3 * cid + a] = CMPC_R(r, R_U + 3 * sl + a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the per-lane driver
+// scp_solver.py:118-179 with the QP solve (ADMM interleaved with certified active-set polishes)
+// flattened into a state machine: advance() runs the scalar decisions of a lane until the lane
+// needs a whole-horizon operation and returns its code; the caller executes it and calls
+// advance() again.  The linearisation point never moves (:129-130), so the stage data are built
+// once; each SCP iteration re-solves the QP for the current (radius, weight).
+enum Op {
+  OP_FACTOR_ADMM = 0, OP_SWEEP_ADMM, OP_BUILD_AS, OP_FACTOR_PMM, OP_SWEEP_PMM, OP_RESCALE, OP_COPY_SOL,
+  OP_EVAL, OP_WRITE, OP_DONE
+};
+enum Pc {
+  PC_SCP_TOP = 0, PC_AFTER_FACTOR0, PC_LOOP_NEXT, PC_AFTER_SWEEP, PC_AFTER_BUILD, PC_ROUND_TOP, PC_AFTER_FACTOR_PMM,
+  PC_AFTER_PMM0, PC_SW_TOP, PC_AFTER_PMM1, PC_ROUND_CHECK, PC_POLISH_END, PC_NO_POLISH, PC_AFTER_REFACTOR, PC_ADAPT,
+  PC_AFTER_RESCALE, PC_AFTER_ADAPT_FACTOR, PC_QP_END, PC_QP_DONE, PC_AFTER_EVAL, PC_FINISH, PC_END
+};
+
+struct Drv {
+  int pc;
+  // SCP loop
+  int it_scp, success, n_acc, status, qp_total, nf_total, polished;
+  double radius, weight, snorm, acc, num, den;
+  // QP solve
+  int it, next_as, as_step, nfact, solved, check, term;
+  double pri0, dua0, npri0, ndua0;
+  // polish
+  int round, sw, prev_chg, chg, certified, upd;
+  double ye_keep[9];
+  double rho_new, rhok_new;
+};
+
+CMPC_HD void drv_init(const Params& P, Sv& S, Drv& D) {
+  D.pc = PC_SCP_TOP;
+  D.it_scp = D.success = D.n_acc = D.qp_total = D.nf_total = D.polished = 0;
+  D.status = ST_OK;
+  D.radius = P.radius0;
+  D.weight = P.omega0;
+  D.snorm = D.acc = D.num = 0.0;
+  D.den = 1.0;
+  D.it = D.nfact = D.solved = D.check = D.term = 0;
+  D.next_as = -1;
+  D.as_step = P.as_step;
+  D.pri0 = D.dua0 = D.npri0 = D.ndua0 = 0.0;
+  D.round = D.sw = D.chg = D.certified = D.upd = 0;
+  D.prev_chg = 1 << 30;
+  for (int i = 0; i < 9; ++i) D.ye_keep[i] = 0.0;
+  D.rho_new = D.rhok_new = 0.0;
+  set_rho(P, P.rho0, &S.rho, &S.rhok, &S.rhoe, &S.rhoep);
+  S.radius = D.radius;
+  S.weight = D.weight;
+}
+
+CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
+  for (;;) {
+    switch (D.pc) {
+      case PC_SCP_TOP:
+        if (!(D.it_scp < P.max_scp && D.weight < P.omega_max && !(D.it_scp != 0 && D.success && 0.0 < P.conv_thresh))) {
+          D.pc = PC_FINISH;
+          break;
+        }
+        D.success = 0;
+        S.radius = D.radius;
+        S.weight = D.weight;
+        D.nfact = 0; D.solved = 0; D.polished = 0; D.it = 0;
+        S.fail = 0;
+        D.pc = PC_AFTER_FACTOR0;
+        return OP_FACTOR_ADMM;
+      case PC_AFTER_FACTOR0:
+        ++D.nfact;
+        if (S.fail) { D.pc = PC_QP_DONE; break; }
+        D.next_as = (P.polish && P.as_start > 0) ? P.as_start : -1;
+        D.as_step = P.as_step;
+        D.pc = PC_LOOP_NEXT;
+        break;
+      case PC_LOOP_NEXT:
+        ++D.it;
+        if (D.it > P.max_iter) { D.pc = PC_QP_END; break; }
+        D.check = (D.it % P.check_every == 0) || (D.it == D.next_as);
+        D.pc = PC_AFTER_SWEEP;
+        return OP_SWEEP_ADMM;
+      case PC_AFTER_SWEEP:
+        if (!D.check) { D.pc = PC_LOOP_NEXT; break; }
+        if (!(S.pri == S.pri) || !(S.dua == S.dua)) { D.pc = PC_QP_END; break; }   // NaN
+        D.term = S.pri <= P.eps_abs + P.eps_rel * S.npri && S.dua <= P.eps_abs + P.eps_rel * S.ndua;
+        if (D.term || D.it == D.next_as) {
+          D.pri0 = S.pri; D.dua0 = S.dua; D.npri0 = S.npri; D.ndua0 = S.ndua;
+          if (P.polish) {
+            for (int i = 0; i < 9; ++i) D.ye_keep[i] = S.ye[i];
+            D.pc = PC_AFTER_BUILD;
+            return OP_BUILD_AS;
+          }
+          D.pc = PC_NO_POLISH;
+          break;
+        }
+        D.pc = PC_ADAPT;
+        break;
+      // ---- certified active-set polish: solve the equality-constrained QP of the guessed active
+      // set by the method of multipliers (penalty 1/delta; OSQP: regularised KKT + iterative
+      // refinement), correct the friction active set, repeat at most 1 + rounds times.
+      case PC_AFTER_BUILD:
+        ++S.n_polish;
+        D.certified = 0;
+        D.prev_chg = 1 << 30;
+        D.round = 0;
+        D.pc = PC_ROUND_TOP;
+        break;
+      case PC_ROUND_TOP:
+        S.fail = 0;
+        D.pc = PC_AFTER_FACTOR_PMM;
+        return OP_FACTOR_PMM;
+      case PC_AFTER_FACTOR_PMM:
+        ++D.nfact;
+        if (S.fail) { D.pc = PC_POLISH_END; break; }
+        D.chg = 0;
+        D.upd = 0;
+        D.pc = PC_AFTER_PMM0;
+        return OP_SWEEP_PMM;
+      case PC_AFTER_PMM0:
+        ++S.n_pmm;
+        D.sw = 0;
+        D.pc = PC_SW_TOP;
+        break;
+      case PC_SW_TOP:
+        if (D.sw < 1 + P.refine) {
+          ++S.n_pmm;
+          D.upd = 1;
+          D.pc = PC_AFTER_PMM1;
+          return OP_SWEEP_PMM;
+        }
+        D.pc = PC_ROUND_CHECK;
+        break;
+      case PC_AFTER_PMM1:
+        if (D.chg || S.pri <= P.as_tol) { D.pc = PC_ROUND_CHECK; break; }
+        ++D.sw;
+        D.pc = PC_SW_TOP;
+        break;
+      case PC_ROUND_CHECK:
+        if (!(S.pri == S.pri)) { D.pc = PC_POLISH_END; break; }   // NaN
+        if (D.chg == 0) {
+          D.certified = S.pri <= P.as_tol;
+          D.pc = PC_POLISH_END;
+          break;
+        }
+        if (D.chg > D.prev_chg) { D.pc = PC_POLISH_END; break; }   // the active set is not settling: back to ADMM
+        D.prev_chg = D.chg;
+        ++D.round;
+        D.pc = D.round > P.as_rounds ? PC_POLISH_END : PC_ROUND_TOP;
+        break;
+      case PC_POLISH_END: {
+        S.kap = 0;
+        for (int i = 0; i < 9; ++i) S.ye[i] = D.ye_keep[i];   // the ADMM multiplier comes back
+        // OSQP's rule for an uncertified polish after normal termination: keep it if it improves
+        const double m0 = fmax(D.pri0 / (P.eps_abs + P.eps_rel * D.npri0), D.dua0 / (P.eps_abs + P.eps_rel * D.ndua0));
+        const double m1 = S.pri / (P.eps_abs + P.eps_rel * S.npri);
+        if (D.certified || (D.term && !S.fail && m1 < m0)) {
+          D.solved = 1;
+          D.polished = 1;
+          S.dua = 0.0;
+          S.ndua = D.ndua0;
+          D.pc = PC_QP_END;
+          break;
+        }
+        S.pri = D.pri0; S.dua = D.dua0; S.npri = D.npri0; S.ndua = D.ndua0;
+        S.fail = 0;
+        D.pc = PC_NO_POLISH;
+        break;
+      }
+      case PC_NO_POLISH:
+        if (D.term) { D.solved = 1; D.pc = PC_QP_END; break; }
+        D.next_as = D.it + D.as_step;
+        D.as_step *= 2;
+        D.pc = PC_AFTER_REFACTOR;   // the polish overwrote the factor records
+        return OP_FACTOR_ADMM;
+      case PC_AFTER_REFACTOR:
+        ++D.nfact;
+        if (S.fail) { D.pc = PC_QP_END; break; }
+        D.pc = PC_ADAPT;
+        break;
+      case PC_ADAPT:
+        if (P.adaptive_rho && D.it >= P.adapt_start && D.it % P.check_every == 0) {
+          double est = S.rho * sqrt((S.pri / (S.npri + 1e-10)) / (S.dua / (S.ndua + 1e-10) + 1e-10));
+          est = fmin(fmax(est, 1e-6), 1e6);
+          if (est > S.rho * P.adapt_tol || est < S.rho / P.adapt_tol) {
+            set_rho(P, est, &D.rho_new, &D.rhok_new, nullptr, nullptr);
+            D.pc = PC_AFTER_RESCALE;
+            return OP_RESCALE;
+          }
+        }
+        D.pc = PC_LOOP_NEXT;
+        break;
+      case PC_AFTER_RESCALE:
+        S.rho = D.rho_new;
+        S.rhok = D.rhok_new;
+        D.pc = PC_AFTER_ADAPT_FACTOR;
+        return OP_FACTOR_ADMM;
+      case PC_AFTER_ADAPT_FACTOR:
+        ++D.nfact;
+        if (S.fail) { D.pc = PC_QP_END; break; }
+        D.pc = PC_LOOP_NEXT;
+        break;
+      case PC_QP_END:
+        D.pc = PC_QP_DONE;
+        if (D.solved && !D.polished) return OP_COPY_SOL;   // unpolished answer: one more x-update, read-only
+        break;
+      case PC_QP_DONE:
+        D.qp_total += D.it > P.max_iter ? P.max_iter : D.it;
+        D.nf_total += D.nfact;
+        if (!D.solved) {
+          D.status = S.fail ? ST_QP_NUMERIC : ST_QP_MAXITER;
+          D.pc = PC_FINISH;
+          break;
+        }
+        D.pc = PC_AFTER_EVAL;
+        return OP_EVAL;
+      case PC_AFTER_EVAL: {
+        int write = 0;
+        if (D.snorm < D.radius) {
+          D.acc = D.num / D.den;
+          if (D.acc > P.acc_rho1) {
+            D.radius *= P.beta_fail;
+          } else {
+            write = 1;
+            D.success = 1;
+            ++D.n_acc;
+            if (D.acc < P.acc_rho0) D.radius = fmin(P.beta_succ * D.radius, P.radius0);
+          }
+        } else {
+          D.weight *= P.gamma_fail;
+        }
+        ++D.it_scp;
+        D.pc = PC_SCP_TOP;
+        if (write) return OP_WRITE;
+        break;
+      }
+      case PC_FINISH:
+        // nothing accepted: hand back the last QP solution (n_accepted == 0 tells the caller; the
+        // reference returns empty lists in that case)
+        D.pc = PC_END;
+        if (D.n_acc == 0 && D.status == ST_OK && D.it_scp > 0) return OP_WRITE;
+        break;
+      default:
+        return OP_DONE;
+    }
+  }
+}
+
+// Executes one operation for one lane.
+template <bool FAST>
+CMPC_FN void execute(int op, const Params& P, const TileCtx& T, const Inst& I, const Batch& bt, Sv& S, Drv& D) {
+  switch (op) {
+    case OP_FACTOR_ADMM: factor_op<MODE_ADMM, FAST>(P, T, I, S); break;
+    case OP_SWEEP_ADMM:
+      backward_op<MODE_ADMM, FAST>(P, T, I, S);
+      if (D.check) forward_op<FW_ADMM_CHECK, FAST>(P, T, I, S, nullptr);
+      else forward_op<FW_ADMM, FAST>(P, T, I, S, nullptr);
+      break;
+    case OP_BUILD_AS: S.kap = build_active_set_op<FAST>(P, T, I, S); break;
+    case OP_FACTOR_PMM: factor_op<MODE_PMM, FAST>(P, T, I, S); break;
+    case OP_SWEEP_PMM:
+      backward_op<MODE_PMM, FAST>(P, T, I, S);
+      if (D.upd) forward_op<FW_PMM_UPD, FAST>(P, T, I, S, &D.chg);
+      else forward_op<FW_PMM, FAST>(P, T, I, S, nullptr);
+      break;
+    case OP_RESCALE: rescale_op(P, T, I, S, D.rho_new, D.rhok_new); break;
+    case OP_COPY_SOL:
+      backward_op<MODE_ADMM, FAST>(P, T, I, S);
+      forward_op<FW_COPY, FAST>(P, T, I, S, nullptr);
+      break;
+    case OP_EVAL: evaluate_op(P, T, I, &D.snorm, &D.num, &D.den); break;
+    case OP_WRITE: write_solution_op(P, T, I, bt.X_out, bt.U_out); break;
+    default: break;
+  }
+}
+
+CMPC_FN void write_stats(const Batch& bt, const Inst& I, const Sv& S, const Drv& D) {
+  bt.scp_iters[I.b] = D.it_scp;
+  bt.status[I.b] = D.status;
+  bt.n_accepted[I.b] = D.n_acc;
+  bt.qp_iters[I.b] = D.qp_total;
+  bt.n_factor[I.b] = D.nf_total;
+  double* inf = bt.info + (long)I.b * INFO;
+  inf[0] = D.snorm; inf[1] = D.acc; inf[2] = S.pri; inf[3] = S.dua;
+  inf[4] = S.rho; inf[5] = D.radius; inf[6] = D.weight; inf[7] = (double)D.polished;
+  inf[8] = (double)S.n_pmm; inf[9] = (double)S.n_polish; inf[10] = 0.0; inf[11] = 0.0;
+}
+
+// bind the per-instance input pointers
+CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b) {
+  const int N = P.N;
+  const long plan = (long)b * bt.plan_stride;
+  I.b = b;
+  I.lane = b & (TL - 1);
+  I.cpos = bt.cpos + plan * N * P.nc * 3;
+  I.cR = bt.cR ? bt.cR + plan * N * P.nc * 9 : nullptr;
+  I.cact = bt.cact + plan * N * P.nc;
+  I.Xr = bt.X_ref + (long)b * (N + 1) * 9;
+  I.Ui = bt.U_init + (long)b * N * P.nu;
+  I.xi = bt.x_init + (long)b * 9;
+  I.xf = bt.x_final + (long)b * 9;
+}
+CMPC_HD void bind_tile(TileCtx& T, const Params& P, const Batch& bt, int tile) {
+  T.prm = &P;
+  T.ws = bt.ws + (long)tile * (P.N + 1) * (REC * TL);
+  T.gt = bt.gtab ? bt.gtab + (long)tile * P.N * (GT * TL) : nullptr;
+  T.nst = bt.nst + (long)tile * (P.N + 1);
+}
+
+}  // namespace cmpc

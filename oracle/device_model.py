@@ -1,4 +1,4 @@
-"""numpy model of the DEVICE algorithm (csrc/cmpc_solver.cuh) — test infrastructure only.
+"""numpy model of the DEVICE algorithm (csrc/cmpc_tile.cuh) — test infrastructure only.
 
 The CUDA solver does not restate OSQP's linear algebra; it solves the same QP with an ADMM
 whose x-update treats the linearised dynamics exactly (a time-varying LQR solved by a

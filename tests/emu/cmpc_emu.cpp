@@ -1,18 +1,49 @@
-// cmpc_emu.cpp — TEST-ONLY host build of the device solver source (csrc/cmpc_solver.cuh).
+// cmpc_emu.cpp — TEST-ONLY host build of the device solver source (csrc/cmpc_tile.cuh).
 //
-// The solver is written against the 32-lane vector abstraction of csrc/cmpc_simt.cuh; compiled
-// with g++ every varying value is a 32-element array and every operation a loop over the lanes,
-// so this library executes the same arithmetic in the same order as the CUDA kernel.  It exists
-// so that the kernel logic can be unit-tested on a machine without a GPU (pytest -m "not gpu").
+// The solver is plain scalar code per MPC instance (one CUDA thread per instance, 32 instances
+// per tile with lane-interleaved records).  Compiled with g++ the same functions run one lane
+// after the other over the same interleaved layout; a lane's arithmetic does not depend on its
+// neighbours and FMA contraction is explicit in both builds, so this library executes the same
+// arithmetic in the same order as the CUDA kernel.  It exists so that the kernel logic can be
+// unit-tested on a machine without a GPU (pytest -m "not gpu").
 // It is NOT part of libcmpc_b200.so, exports different symbol names (cmpc_emu_*), and nothing
 // in the product package loads it: the product path fails loudly without CUDA.
 #include <stdlib.h>
 #include <vector>
 
 #include "../../centroidal_mpc_b200/csrc/cmpc_params.h"
-#include "../../centroidal_mpc_b200/csrc/cmpc_solver.cuh"
+#include "../../centroidal_mpc_b200/csrc/cmpc_tile.cuh"
 
 using namespace cmpc;
+
+template <bool FAST>
+static void run_tile_host(const Params& prm, const Batch& bt, int tile) {
+  TileCtx T;
+  bind_tile(T, prm, bt, tile);
+  Inst I[TL];
+  Sv S[TL];
+  Drv D[TL];
+  int live[TL];
+  for (int k = 0; k <= prm.N; ++k) T.nst[k] = 0;
+  for (int l = 0; l < TL; ++l) {
+    const int b = tile * TL + l;
+    live[l] = b < bt.B;
+    if (!live[l]) continue;
+    bind_instance(I[l], prm, bt, b);
+    setup_op(prm, T, I[l], S[l]);
+    for (int k = 0; k <= prm.N; ++k) {
+      const int ns = meta_of(T, I[l], k)[0] & 7;
+      if (ns > T.nst[k]) T.nst[k] = ns;
+    }
+  }
+  for (int l = 0; l < TL; ++l) {
+    if (!live[l]) continue;
+    drv_init(prm, S[l], D[l]);
+    for (int op = advance(prm, S[l], D[l]); op != OP_DONE; op = advance(prm, S[l], D[l]))
+      execute<FAST>(op, prm, T, I[l], bt, S[l], D[l]);
+    write_stats(bt, I[l], S[l], D[l]);
+  }
+}
 
 extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model, const cmpc_scp_params* scp,
                                   const cmpc_qp_settings* qp, const double* x_init, const double* x_final,
@@ -24,31 +55,27 @@ extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model
   int rc = fill_params(&prm, dims, model, scp, qp, contact_R == nullptr);
   if (rc) return rc;
   const int B = dims->batch, N = dims->N;
-  WsSizes w = ws_sizes(1, N);   // instances run one after the other: one instance of workspace
-  std::vector<double> stg(w.stg), sta(w.sta), fac(w.fac), dvec(w.dvec), pm(w.pm), sol(w.sol), gtab(w.gtab);
-  std::vector<int> meta(w.meta), pmask(w.pmask);
-  WarpMem* s = new WarpMem;
-  for (int b = 0; b < B; ++b) {
+  WsSizes w1 = ws_sizes(TL, N);   // tiles run one after the other: one tile of workspace
+  WsSizes wb = ws_sizes(B, N);
+  std::vector<double> ws(w1.ws), gtab(w1.gtab);
+  std::vector<int> nst(w1.nst);
+  for (int tile = 0; tile < wb.tiles; ++tile) {
     Batch bt;
     memset(&bt, 0, sizeof(bt));
     bt.B = B; bt.x_init = x_init; bt.x_final = x_final; bt.X_ref = X_ref; bt.U_init = U_init;
     bt.cpos = contact_pos; bt.cR = contact_R; bt.cact = contact_active;
     bt.plan_stride = dims->shared_plan ? 0 : 1;
-    // workspace views shifted so that instance b lands on the single-instance buffers
-    bt.stg = stg.data() - (long)b * (N + 1) * SG; bt.sta = sta.data() - (long)b * (N + 1) * ST;
-    bt.fac = fac.data() - (long)b * N * FAC; bt.dvec = dvec.data() - (long)b * N * DVC;
-    bt.pm = pm.data() - (long)b * (N + 1) * PM; bt.sol = sol.data() - (long)b * (N + 1) * SOL;
-    bt.gtab = prm.fast ? nullptr : gtab.data() - (long)b * N * MAXC * 16;
-    bt.meta = meta.data() - (long)b * (N + 1); bt.pmask = pmask.data() - (long)b * (N + 1);
+    // workspace views shifted so that this tile lands on the single-tile buffers
+    bt.ws = ws.data() - (long)tile * w1.ws;
+    bt.gtab = prm.fast ? nullptr : gtab.data() - (long)tile * w1.gtab;
+    bt.nst = nst.data() - (long)tile * w1.nst;
     bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = scp_iters; bt.status = status;
     bt.n_accepted = n_accepted; bt.qp_iters = qp_iters; bt.n_factor = n_factor; bt.info = info;
-    memset(s, 0, sizeof(WarpMem));
-    Ctx c;
-    bind_instance(c, &prm, bt, s, b);
-    solve_instance(c);
+    std::fill(ws.begin(), ws.end(), 0.0);
+    if (prm.fast) run_tile_host<true>(prm, bt, tile);
+    else run_tile_host<false>(prm, bt, tile);
   }
-  delete s;
   return 0;
 }
 
-extern "C" int cmpc_emu_warpmem_bytes(void) { return (int)sizeof(WarpMem); }
+extern "C" int cmpc_emu_record_doubles(void) { return REC; }

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "emu", "cmpc_emu.cpp")
 _SO = os.path.join(_HERE, "emu", "libcmpc_emu.so")
 _DEPS = [os.path.join(_HERE, "..", "centroidal_mpc_b200", "csrc", f)
-         for f in ("cmpc_simt.cuh", "cmpc_core.cuh", "cmpc_solver.cuh", "cmpc_params.h")] + [_SRC]
+         for f in ("cmpc_core.cuh", "cmpc_tile.cuh", "cmpc_params.h")] + [_SRC]
 _lib = None
 
 
