@@ -35,20 +35,21 @@ int fail(int code, const std::string& msg) {
 // the later operations (evaluate, write) and the tile does those together.  Warps never
 // synchronise with each other.
 // ------------------------------------------------------------------------------------------
-constexpr int WARPS_PER_BLOCK = 1;
-constexpr int THREADS = 32 * WARPS_PER_BLOCK;
-constexpr int BLOCKS_PER_SM = 4;   // cap of resident tiles per SM for batches beyond 148 tiles
+constexpr int THREADS = 32;                      // one warp (one tile at a time) per block
+constexpr long RING_BYTES = (long)RING_DEPTH * R_STAGED * TL * 8;
+inline long scp_smem_bytes(int N) { return RING_BYTES + 64 + ((N + 1 + 15) & ~15); }
 
 template <bool FAST>
-__device__ void run_tile(const Params& prm, const Batch& bt, int tile) {
-  const unsigned lane = threadIdx.x & 31u;
-  TileCtx T;
+__device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& T, unsigned char* nst_s) {
+  const int lane = (int)(threadIdx.x & 31u);
   bind_tile(T, prm, bt, tile);
-  const int b = tile * TL + (int)lane;
-  const bool live = b < bt.B;
+  const int b = tile * TL + lane;
+  const bool live = lane < TL && b < bt.B;
   Inst I;
   Sv S;
   Drv D;
+  I.lane = lane & (TL - 1);
+  D.check = D.upd = 0;
   if (live) {
     bind_instance(I, prm, bt, b);
     setup_op(prm, T, I, S);
@@ -56,7 +57,7 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile) {
   for (int k = 0; k <= prm.N; ++k) {   // slots per knot of the tile
     const int ns = live ? (meta_of(T, I, k)[0] & 7) : 0;
     const int mx = __reduce_max_sync(0xffffffffu, ns);
-    if (lane == 0) T.nst[k] = mx;
+    if (lane == 0) { T.nst[k] = mx; nst_s[k] = (unsigned char)mx; }
   }
   __syncwarp();
   int op = OP_DONE;
@@ -67,10 +68,10 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile) {
   for (;;) {
     const int sel = __reduce_min_sync(0xffffffffu, op);
     if (sel == OP_DONE) break;
-    if (op == sel) {
-      execute<FAST>(sel, prm, T, I, bt, S, D);
-      op = advance(prm, S, D);
-    }
+    const bool on = op == sel;
+    const bool anycheck = __any_sync(0xffffffffu, on && D.check);
+    execute<FAST>(sel, prm, T, I, bt, S, D, on, anycheck);
+    if (on) op = advance(prm, S, D);
     __syncwarp();
   }
   if (live) write_stats(bt, I, S, D);
@@ -78,14 +79,28 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile) {
 
 __global__ void __launch_bounds__(THREADS)
 cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31u;
+  TileCtx T;
+  T.ring = reinterpret_cast<double*>(smem_raw);
+  T.ring_sa = smem_addr(smem_raw);
+  T.bars_sa = T.ring_sa + (unsigned)RING_BYTES;
+  T.phases = 0;
+  unsigned char* nst_s = smem_raw + RING_BYTES + 64;
+  T.nst_s = nst_s;
+  if (lane == 0) {
+    for (int d = 0; d < RING_DEPTH; ++d)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(T.bars_sa + 8u * d) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = atomicAdd(queue, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= tiles) break;
-    if (prm.fast) run_tile<true>(prm, bt, tile);
-    else run_tile<false>(prm, bt, tile);
+    if (prm.fast) run_tile<true>(prm, bt, tile, T, nst_s);
+    else run_tile<false>(prm, bt, tile, T, nst_s);
     __syncwarp();
   }
 }
@@ -148,6 +163,7 @@ struct cmpc_handle_s {
   Batch bt;          // device pointers
   double* gtab;      // general friction-row table (used when the fast path does not apply)
   int tiles;
+  long smem_max;
   void* ws;          // one allocation
   long ws_bytes;
   int* queue;
@@ -188,6 +204,11 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   h->d_nfac = ip; ip += B;
   h->queue = ip;
   h->tiles = (int)w.tiles;
+  int smem_optin = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  h->smem_max = smem_optin;
+  if (scp_smem_bytes(N) > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
+  CUDA_TRY(cudaFuncSetAttribute(cmpc_scp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scp_smem_bytes(N)));
   h->bt.B = B;
   h->bt.plan_stride = dims->shared_plan ? 0 : 1;
   *out = h;
@@ -232,10 +253,15 @@ int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_sett
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
   CUDA_TRY(cudaMemsetAsync(h->queue, 0, sizeof(int), st));
-  int blocks = (h->tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  const int cap = h->num_sms * BLOCKS_PER_SM;
+  const long smem = scp_smem_bytes(h->dims.N);
+  if (smem > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
+  int per_sm = (int)(h->smem_max / (smem + 1024));   // 1 KB per block is reserved by the driver
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;                        // 255 registers per thread
+  int blocks = h->tiles;
+  const int cap = h->num_sms * per_sm;
   if (blocks > cap) blocks = cap;
-  cmpc_scp_kernel<<<blocks, THREADS, 0, st>>>(prm, bt, h->queue, h->tiles);
+  cmpc_scp_kernel<<<blocks, THREADS, smem, st>>>(prm, bt, h->queue, h->tiles);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

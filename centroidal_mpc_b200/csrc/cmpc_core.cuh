@@ -15,9 +15,9 @@
 #include <math.h>
 #include <string.h>
 
-#if defined(__CUDACC__)
-#define CMPC_HD __host__ __device__ __forceinline__
-#define CMPC_FN __host__ __device__
+#if defined(__CUDACC__)   // the solver is device code in the CUDA build, host code in the test build (g++)
+#define CMPC_HD __device__ __forceinline__
+#define CMPC_FN __device__
 #else
 #define CMPC_HD inline
 #define CMPC_FN
@@ -28,32 +28,47 @@ namespace cmpc {
 constexpr int NX = 9;
 constexpr int MAXC = 4;    // contacts
 constexpr int MAXU = 12;   // 3 * MAXC
-constexpr int TL = 32;     // instances per tile (= lanes of a warp)
+#ifndef CMPC_TL
+#define CMPC_TL 32
+#endif
+constexpr int TL = CMPC_TL;   // instances per tile (lanes of the warp that carry an instance)
 
 // ---- knot record: REC doubles per instance and knot.  A tile's workspace is
-// [N+1 knots][REC fields][32 lanes]; field f of lane l at knot k lives at ((k*REC + f)*32 + l).
+// [N+1 knots][REC fields][TL lanes]; field f of lane l at knot k lives at ((k*REC + f)*TL + l).
 // "slot" = position of a contact among the knot's ACTIVE contacts; controls (3 per slot) and
 // friction rows (4 per slot) are stored compactly by slot.  The number of slots of a knot is
 // tile-uniform (the maximum over the tile's lanes); a lane with fewer active contacts pads with
 // slots whose B columns are zero, which leaves exact zeros in their controls.
-constexpr int R_PC = 0;      // Pc[9]      = P_{k+1} c_k                      (factor)
-constexpr int R_HI = 9;      // Hinv       packed lower triangle (j,l), l <= j, at j(j+1)/2 + l
-constexpr int R_K = 87;      // K[j*9+i]   feedback gain, na x 9
-constexpr int R_XB = 195;    // xbar[9]    linearisation point: q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
-constexpr int R_S = 204;     // S[3]       sum of active fbar:  A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
-constexpr int R_CK = 207;    // ck[3]      affine term rows 6..8: -dt S x cbar (row 5 is dt m g)
-constexpr int R_D = 210;     // d[slot][3] = p_contact - cbar:  B_k[:,3s:3s+3] = dt [0; I; [d]x]
-constexpr int R_VF = 222;    // vf[4*slot+row]  friction rows: w = min(v,0), y = rho e2 max(v,0)
-constexpr int R_VK = 238;    // vk[3]           kappa copy:    w = prox(v),  y = rho_k (v - w)
-constexpr int R_DV = 241;    // feed-forward d_k (compact, 12)
-constexpr int R_YF = 253;    // multiplier method: yf[16] (compact rows)
-constexpr int R_YK = 269;    //                    yk[4]  (3 pins + surface row)
-constexpr int R_X = 273;     // solution x[9]
-constexpr int R_U = 282;     // solution u[12] (compact)
-constexpr int R_META = 294;  // 64 int32: [lane] meta (bits 0..2 slots, 4..11 contact id per slot), [32+lane] active set
+// Fields are grouped into SEGMENTS, the units the sweeps stage into shared memory with one bulk
+// copy each (cp.async.bulk); variable-length fields sit at the end of their segment so that only
+// the used prefix (a function of the knot's slot count) is moved.
+//   A  Pc, Hinv          factor -> backward sweep
+//   B  K                 factor -> both sweeps
+//   C  meta, xbar, S, ck, d      stage data, constant during a solve
+//   D  vk, vf            ADMM iterate
+//   E  d_k               backward -> forward sweep
+//   F  yk, yf            multiplier method
+constexpr int R_PC = 0;      // Pc[9]      = P_{k+1} c_k
+constexpr int R_HI = 9;      // Hinv       packed lower triangle (j,l), l <= j, at j(j+1)/2 + l   (78)
+constexpr int R_K = 87;      // K[j*9+i]   feedback gain, na x 9                                   (108)
+constexpr int R_META = 195;  // 2*TL int32: [lane] meta (bits 0..2 slots, 4..11 contact id per slot), [TL+lane] active set
+constexpr int R_XB = 196;    // xbar[9]    linearisation point: q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
+constexpr int R_S = 205;     // S[3]       sum of active fbar:  A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
+constexpr int R_CK = 208;    // ck[3]      affine term rows 6..8: -dt S x cbar (row 5 is dt m g)
+constexpr int R_D = 211;     // d[slot][3] = p_contact - cbar:  B_k[:,3s:3s+3] = dt [0; I; [d]x]
+constexpr int R_VK = 223;    // vk[3]           kappa copy:    w = prox(v),  y = rho_k (v - w)
+constexpr int R_VF = 226;    // vf[4*slot+row]  friction rows: w = min(v,0), y = rho e2 max(v,0)
+constexpr int R_DV = 242;    // feed-forward d_k (compact, 12)
+constexpr int R_YK = 254;    // multiplier method: yk[4]  (3 pins + surface row)
+constexpr int R_YF = 258;    //                    yf[16] (compact rows)
+constexpr int R_X = 274;     // solution x[9]
+constexpr int R_U = 283;     // solution u[12] (compact)
 constexpr int REC = 296;     // 2368 bytes per instance and knot
+constexpr int R_STAGED = 274;  // fields [0, R_STAGED) can be staged by the sweeps
+constexpr int SEG_A = 1, SEG_B = 2, SEG_C = 4, SEG_D = 8, SEG_E = 16, SEG_F = 32;
 constexpr int GT = 64;       // general friction table per knot: per slot G (12, row-major 4x3) + e2 (4)
 constexpr int INFO = 12;     // per-instance statistics (cmpc_get_stats)
+constexpr int RING_DEPTH = 3;  // knots in flight per tile
 
 enum Status { ST_OK = 0, ST_QP_MAXITER = 1, ST_QP_NUMERIC = 2 };
 

@@ -19,15 +19,25 @@ namespace cmpc {
 
 constexpr int MODE_ADMM = 0, MODE_PMM = 1;
 // forward-sweep kinds
-constexpr int FW_ADMM = 0, FW_ADMM_CHECK = 1, FW_PMM = 2, FW_PMM_UPD = 3, FW_COPY = 4;
+constexpr int FW_ADMM = 0, FW_ADMM_CHECK = 1, FW_PMM = 2, FW_COPY = 4;
 
 #define CMPC_R(p, f) (p)[(f) * TL]
 
 struct TileCtx {
   const Params* prm;
-  double* ws;      // tile workspace [N+1][REC][32]
-  double* gt;      // tile friction table [N][GT][32], null on the fast path
-  int* nst;        // [N+1] slots per knot (tile maximum; 0 at the terminal knot)
+  double* ws;      // tile workspace [N+1][REC][TL]
+  double* gt;      // tile friction table [N][GT][TL], null on the fast path
+  int* nst;        // [N+1] slots per knot (tile maximum; 0 at the terminal knot), global memory
+#if defined(__CUDACC__)
+  // the warp's shared-memory ring (RING_DEPTH slots of R_STAGED fields), its mbarriers and a
+  // shared copy of nst; all warp-uniform
+  double* ring;
+  unsigned ring_sa, bars_sa, phases;
+  const unsigned char* nst_s;
+  CMPC_HD int ns(int k) const { return nst_s[k]; }
+#else
+  CMPC_HD int ns(int k) const { return nst[k]; }
+#endif
 };
 
 struct Inst {
@@ -38,9 +48,105 @@ struct Inst {
 
 CMPC_HD double* rec_of(const TileCtx& T, const Inst& I, int k) { return T.ws + (long)k * (REC * TL) + I.lane; }
 CMPC_HD int* meta_of(const TileCtx& T, const Inst& I, int k) {
-  return reinterpret_cast<int*>(T.ws + (long)k * (REC * TL) + R_META * TL) + I.lane;   // [0] meta, [32] active set
+  return reinterpret_cast<int*>(T.ws + (long)k * (REC * TL) + R_META * TL) + I.lane;   // [0] meta, [TL] active set
+}
+// the same two words through a (possibly staged) record pointer r = base + lane
+CMPC_HD const int* meta_rd(const double* r, int lane) {
+  return reinterpret_cast<const int*>(r - lane + R_META * TL) + lane;
 }
 CMPC_HD double* gt_of(const TileCtx& T, const Inst& I, int k) { return T.gt ? T.gt + (long)k * (GT * TL) + I.lane : nullptr; }
+
+// ---------------------------------------------------------------- knot stream
+// Walks the knots of a tile in one direction and hands out a pointer through which the fields
+// of the requested segments of the current knot can be read (CMPC_R(r, field)).
+// Device: a ring of RING_DEPTH shared-memory slots filled by cp.async.bulk (one elected lane,
+// one bulk copy per segment, completion on an mbarrier), so the HBM latency of knot k+3 hides
+// behind the arithmetic of knots k..k+2 and every operand read is a shared-memory read.
+// Host build: the pointer is the global record itself.
+CMPC_HD int seg_start(int seg) {
+  return seg == SEG_A ? R_PC : seg == SEG_B ? R_K : seg == SEG_C ? R_META : seg == SEG_D ? R_VK : seg == SEG_E ? R_DV : R_YK;
+}
+CMPC_HD int seg_len(int seg, int ns) {
+  const int na = 3 * ns;
+  return seg == SEG_A ? 9 + na * (na + 1) / 2 : seg == SEG_B ? 9 * na : seg == SEG_C ? 16 + na
+       : seg == SEG_D ? 3 + 4 * ns : seg == SEG_E ? na : 4 + 4 * ns;
+}
+
+#if defined(__CUDACC__)
+CMPC_HD unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct KnotStream {
+  TileCtx* T;
+  int lane, segs, dir, base_f, slot_f, k_issue, n_issue, s_issue, s_wait;
+
+  CMPC_HD void issue_one() {
+    if (n_issue <= 0) return;
+    if (lane == 0) {
+      const int ns = T->nst_s[k_issue];
+      const unsigned bar = T->bars_sa + 8u * s_issue;
+      const unsigned dst0 = T->ring_sa + (unsigned)(s_issue * slot_f - base_f) * (TL * 8);
+      const double* src0 = T->ws + (long)k_issue * (REC * TL);
+      unsigned bytes = 0;
+#pragma unroll
+      for (int sg = 1; sg <= SEG_F; sg <<= 1)
+        if (segs & sg) bytes += (unsigned)seg_len(sg, ns) * (TL * 8);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+      for (int sg = 1; sg <= SEG_F; sg <<= 1) {
+        if (!(segs & sg)) continue;
+        const unsigned len = (unsigned)seg_len(sg, ns) * (TL * 8);
+        if (len == 0) continue;
+        const int st = seg_start(sg);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst0 + (unsigned)st * (TL * 8)), "l"(src0 + st * TL), "r"(len), "r"(bar) : "memory");
+      }
+    }
+    k_issue += dir;
+    --n_issue;
+    s_issue = (s_issue + 1 == RING_DEPTH) ? 0 : s_issue + 1;
+  }
+  // knots k_first, k_first + dir, ... (count of them); fields below base_f are not staged
+  CMPC_HD void open(TileCtx& Tc, const Inst& I, int segments, int base_field, int k_first, int count, int direction) {
+    T = &Tc; lane = I.lane; segs = segments; dir = direction; base_f = base_field; slot_f = R_STAGED - base_field;
+    k_issue = k_first; n_issue = count; s_issue = s_wait = 0;
+    // earlier generic-proxy writes of this warp (records written by the previous operation) must
+    // be visible to the async proxy before the bulk copies read them
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+    for (int d = 0; d < RING_DEPTH; ++d) issue_one();
+  }
+  CMPC_HD const double* acquire() {
+    const unsigned bar = T->bars_sa + 8u * s_wait;
+    const unsigned parity = (T->phases >> s_wait) & 1u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CMPC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CMPC_DONE;\n"
+        "bra CMPC_WAIT;\n"
+        "CMPC_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+    T->phases ^= 1u << s_wait;
+    return T->ring + (long)(s_wait * slot_f - base_f) * TL + lane;
+  }
+  CMPC_HD void release() {
+    __syncwarp();          // every lane is done reading the slot
+    issue_one();           // refill it (s_issue == s_wait whenever something is left to issue)
+    s_wait = (s_wait + 1 == RING_DEPTH) ? 0 : s_wait + 1;
+  }
+};
+#else
+struct KnotStream {
+  const double* ws;
+  int lane, dir, k;
+  CMPC_HD void open(TileCtx& T, const Inst& I, int, int, int k_first, int, int direction) {
+    ws = T.ws; lane = I.lane; dir = direction; k = k_first;
+  }
+  CMPC_HD const double* acquire() const { return ws + (long)k * (REC * TL) + lane; }
+  CMPC_HD void release() { k += dir; }
+};
+#endif
 
 // Solver scalars of one lane.
 struct Sv {
@@ -185,146 +291,214 @@ CMPC_HD void set_rho(const Params& P, double rho, double* rho_out, double* rhok_
 // K = -Huu^-1 Hux and P_k in one pass and keeps all three exactly symmetric.  Pc = P c.
 // ADMM mode: R = W_u + rho G'E2G, Q = W_x + rho_k I (kappa); multiplier mode: active friction
 // rows and kappa rows carry the penalty 1/delta.
-CMPC_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+// The tableau lives in per-lane scratch tb (stride TS: shared memory on the device, a local
+// array in the host build); P (packed lower triangle) stays in registers across the knots.
+CMPC_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+CMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
-template <int MODE, bool FAST>
-CMPC_FN void factor_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
-  const int N = P.N;
-  const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
+template <int NS, int MODE, bool FAST, int TS>
+CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int lane, const double* gt, int k,
+                         double* Pm, double* tb) {
+  constexpr int NA = 3 * NS, n = NA + 9;
   const double inv = 1.0 / P.delta;
-  double Pm[81], PA[81], W[9 * MAXU], Tb[231], col[21], kM[9], kl[3];
-  for (int i = 0; i < 81; ++i) Pm[i] = 0.0;
-  for (int i = 0; i < 9; ++i) Pm[10 * i] = P.Wx[i] + rho_e;
-  if (MODE == MODE_ADMM) {
-    for (int i = 6; i < 9; ++i) Pm[10 * i] += S.rhok;
-  } else if (S.kap) {
-    const double* r = rec_of(T, I, N);
-    const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-    const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
-    pmm_kappa_terms(P, S, meta_of(T, I, N)[32], kb, yk, kM, kl);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) Pm[(6 + i) * 9 + 6 + j] += kM[3 * i + j];
+  const int* im = meta_rd(r, lane);
+  const int mt = im[0], nsl = mt & 7;
+  const int pm = (MODE == MODE_PMM) ? im[TL] : 0;
+  const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+  const double ck[3] = {CMPC_R(r, R_CK), CMPC_R(r, R_CK + 1), CMPC_R(r, R_CK + 2)};
+  // Pc = P c
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    double pc = Pm[trs(i, 5)] * P.dtmg;
+    pc = fma(Pm[trs(i, 6)], ck[0], pc);
+    pc = fma(Pm[trs(i, 7)], ck[1], pc);
+    pc = fma(Pm[trs(i, 8)], ck[2], pc);
+    CMPC_R(w, R_PC + i) = pc;
   }
-  for (int k = N - 1; k >= 0; --k) {
-    double* r = rec_of(T, I, k);
-    const int* im = meta_of(T, I, k);
-    const double* gt = gt_of(T, I, k);
-    const int ns = T.nst[k], na = 3 * ns, n = na + 9;
-    const int mt = im[0], nsl = mt & 7;
-    const int pm = (MODE == MODE_PMM) ? im[32] : 0;
-    const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
-    const double ck[3] = {CMPC_R(r, R_CK), CMPC_R(r, R_CK + 1), CMPC_R(r, R_CK + 2)};
-    double d[MAXU];
-    for (int j = 0; j < na; ++j) d[j] = CMPC_R(r, R_D + j);
-    // PA = P A, Pc = P c
-    for (int i = 0; i < 9; ++i) {
-      const double* pr = Pm + 9 * i;
-      for (int q = 0; q < 3; ++q) {     // (P [S]x)[i][q] = P[i][6+q1] S[q2] - P[i][6+q2] S[q1]
+  // control part of the tableau, one slot at a time:  W = P B (rows 3..8 kept), Hux = W'A, Huu = R + B'W
+  double Wm[6][NA > 0 ? NA : 1];   // rows 3..8 of P B
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const double dts = s < nsl ? P.dt : 0.0;
+    const double ds[3] = {CMPC_R(r, R_D + 3 * s), CMPC_R(r, R_D + 3 * s + 1), CMPC_R(r, R_D + 3 * s + 2)};
+    Fric<FAST> fr;
+    fr.load(P, gt, s);
+    double rr[4];
+#pragma unroll
+    for (int row = 0; row < 4; ++row) {
+      if (MODE == MODE_ADMM) rr[row] = S.rho * fr.e2(row);
+      else rr[row] = ((pm >> (4 * s + row)) & 1) ? inv : 0.0;
+    }
+    const int cid = (s < nsl) ? ((mt >> (4 + 2 * s)) & 3) : 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int a1 = nxt3(a), a2 = prv3(a), j = 3 * s + a;
+      // (P B)[i][(s,a)] = dt_s (P[i][3+a] + P[i][6+a1] d[a2] - P[i][6+a2] d[a1])
+      double wc[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        wc[i] = dts * fma(Pm[trs(i, 6 + a1)], ds[a2], fma(-Pm[trs(i, 6 + a2)], ds[a1], Pm[trs(i, 3 + a)]));
+#pragma unroll
+      for (int i = 0; i < 6; ++i) Wm[i][j] = wc[3 + i];
+      // Hux[j][q] = (W'A)[j][q]
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
         const int q1 = nxt3(q), q2 = prv3(q);
-        PA[9 * i + q] = fma(P.dt, fma(pr[6 + q1], S3[q2], -(pr[6 + q2] * S3[q1])), pr[q]);
-        PA[9 * i + 3 + q] = fma(P.dt_m, pr[q], pr[3 + q]);
-        PA[9 * i + 6 + q] = pr[6 + q];
+        tb[tri(NA + q, j) * TS] = fma(P.dt, fma(wc[6 + q1], S3[q2], -(wc[6 + q2] * S3[q1])), wc[q]);
+        tb[tri(NA + 3 + q, j) * TS] = fma(P.dt_m, wc[q], wc[3 + q]);
+        tb[tri(NA + 6 + q, j) * TS] = wc[6 + q];
       }
-      double pc = pr[5] * P.dtmg;
-      pc = fma(pr[6], ck[0], pc);
-      pc = fma(pr[7], ck[1], pc);
-      pc = fma(pr[8], ck[2], pc);
-      CMPC_R(r, R_PC + i) = pc;
-    }
-    // W = P B:  (P B)[i][(s,a)] = dt_s (P[i][3+a] + P[i][6+a1] d[a2] - P[i][6+a2] d[a1])
-    for (int s = 0; s < ns; ++s) {
-      const double dts = s < nsl ? P.dt : 0.0;
-      const double* ds = d + 3 * s;
-      for (int a = 0; a < 3; ++a) {
-        const int a1 = nxt3(a), a2 = prv3(a);
-        for (int i = 0; i < 9; ++i) {
-          const double* pr = Pm + 9 * i;
-          W[i * MAXU + 3 * s + a] = dts * fma(pr[6 + a1], ds[a2], fma(-pr[6 + a2], ds[a1], pr[3 + a]));
+      // Huu[j][l], l <= j:  row (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
+#pragma unroll
+      for (int l = 0; l <= j; ++l) {
+        double v = dts * fma(Wm[3 + a1][l], ds[a2], fma(-Wm[3 + a2][l], ds[a1], Wm[a][l]));
+        if (l >= 3 * s) {   // R block of the slot: W_u + G' diag(rr) G
+          const int b2 = l - 3 * s;
+          double radd = (b2 == a) ? (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) : 0.0;
+#pragma unroll
+          for (int row = 0; row < 4; ++row) radd = fma(rr[row] * fr.G(row, a), fr.G(row, b2), radd);
+          v += radd;
         }
+        tb[tri(j, l) * TS] = v;
       }
     }
-    // tableau: rows (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
-    for (int s = 0; s < ns; ++s) {
-      const double dts = s < nsl ? P.dt : 0.0;
-      const double* ds = d + 3 * s;
-      Fric<FAST> fr;
-      fr.load(P, gt, s);
-      double rr[4];
-      for (int row = 0; row < 4; ++row) {
-        if (MODE == MODE_ADMM) rr[row] = S.rho * fr.e2(row);
-        else rr[row] = ((pm >> (4 * s + row)) & 1) ? inv : 0.0;
-      }
-      const int cid = (s < nsl) ? ((mt >> (4 + 2 * s)) & 3) : 0;
-      for (int a = 0; a < 3; ++a) {
-        const int a1 = nxt3(a), a2 = prv3(a), j = 3 * s + a;
-        for (int l = 0; l <= j; ++l) {
-          double v = dts * fma(W[(6 + a1) * MAXU + l], ds[a2], fma(-W[(6 + a2) * MAXU + l], ds[a1], W[(3 + a) * MAXU + l]));
-          if (l >= 3 * s) {   // R block of the slot: W_u + G' diag(rr) G
-            const int b2 = l - 3 * s;
-            double radd = (b2 == a) ? (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) : 0.0;
-            for (int row = 0; row < 4; ++row) radd = fma(rr[row] * fr.G(row, a), fr.G(row, b2), radd);
-            v += radd;
-          }
-          Tb[tri(j, l)] = v;
-        }
-        for (int q = 0; q < 9; ++q)
-          Tb[tri(na + q, j)] = dts * fma(PA[(6 + a1) * 9 + q], ds[a2], fma(-PA[(6 + a2) * 9 + q], ds[a1], PA[(3 + a) * 9 + q]));
-      }
-    }
-    // Q + A'(PA), lower triangle
-    if (MODE == MODE_PMM && S.kap && k >= 1) {
+  }
+  // Q + A'(PA), lower triangle
+  {
+    double kM[9], kl[3];
+    const bool kap = MODE == MODE_PMM && S.kap && k >= 1;
+    if (kap) {
       const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
       const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
       pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
     }
+    double PA[9][9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {     // (P [S]x)[i][q] = P[i][6+q1] S[q2] - P[i][6+q2] S[q1]
+        const int q1 = nxt3(q), q2 = prv3(q);
+        PA[i][q] = fma(P.dt, fma(Pm[trs(i, 6 + q1)], S3[q2], -(Pm[trs(i, 6 + q2)] * S3[q1])), Pm[trs(i, q)]);
+        PA[i][3 + q] = fma(P.dt_m, Pm[trs(i, q)], Pm[trs(i, 3 + q)]);
+        PA[i][6 + q] = Pm[trs(i, 6 + q)];
+      }
+    }
+#pragma unroll
     for (int rr2 = 0; rr2 < 9; ++rr2) {
       const int g3 = rr2 / 3, a = rr2 - 3 * g3, a1 = nxt3(a), a2 = prv3(a);
+#pragma unroll
       for (int c = 0; c <= rr2; ++c) {
-        double v = PA[rr2 * 9 + c];
-        if (g3 == 0) v = fma(P.dt, fma(PA[(6 + a1) * 9 + c], S3[a2], -(PA[(6 + a2) * 9 + c] * S3[a1])), v);
-        else if (g3 == 1) v = fma(P.dt_m, PA[a * 9 + c], v);
+        double v = PA[rr2][c];
+        if (g3 == 0) v = fma(P.dt, fma(PA[6 + a1][c], S3[a2], -(PA[6 + a2][c] * S3[a1])), v);
+        else if (g3 == 1) v = fma(P.dt_m, PA[a][c], v);
         if (c == rr2) {
           v += P.Wx[rr2];
           if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
         }
-        if (MODE == MODE_PMM && S.kap && k >= 1 && c >= 6) v += kM[3 * (rr2 - 6) + (c - 6)];
-        Tb[tri(na + rr2, na + c)] = v;
+        if (MODE == MODE_PMM && c >= 6 && kap) v += kM[3 * (rr2 - 6) + (c - 6)];
+        tb[tri(NA + rr2, NA + c) * TS] = v;
       }
     }
-    // sweep the control pivots
-    for (int pv = 0; pv < na; ++pv) {
-      const double piv = Tb[tri(pv, pv)];
-      if (!(piv > 0.0)) S.fail = 1;
-      const double ip = 1.0 / piv;
-      for (int i = 0; i < n; ++i) col[i] = i < pv ? Tb[tri(pv, i)] : Tb[tri(i, pv)];
-      for (int i = 0; i < n; ++i) {
-        if (i == pv) continue;
-        const double bi = col[i] * ip;
-        double* row = Tb + tri(i, 0);
-        for (int j = 0; j <= i; ++j)
-          if (j != pv) row[j] = fma(-bi, col[j], row[j]);
-      }
-      for (int i = 0; i < pv; ++i) Tb[tri(pv, i)] = col[i] * ip;
-      for (int i = pv + 1; i < n; ++i) Tb[tri(i, pv)] = col[i] * ip;
-      Tb[tri(pv, pv)] = -ip;
+  }
+  // sweep the control pivots.  Row / column pv of the generic update is garbage and is
+  // overwritten afterwards, so that the update itself has no pv-dependent addressing.
+  for (int pv = 0; pv < NA; ++pv) {
+    const int tpv = pv * (pv + 1) / 2;
+    const double piv = tb[(tpv + pv) * TS];
+    if (!(piv > 0.0)) S.fail = 1;
+    const double ip = 1.0 / piv;
+    double c[n], bc[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const int idx = i < pv ? tpv + i : i * (i + 1) / 2 + pv;
+      c[i] = tb[idx * TS];
+      bc[i] = c[i] * ip;
     }
-    // factor record and P_k
-    for (int j = 0; j < na; ++j) {
-      for (int l = 0; l <= j; ++l) CMPC_R(r, R_HI + tri(j, l)) = -Tb[tri(j, l)];
-      for (int i = 0; i < 9; ++i) CMPC_R(r, R_K + 9 * j + i) = -Tb[tri(na + i, j)];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) tb[tri(i, j) * TS] = fma(-bc[i], c[j], tb[tri(i, j) * TS]);
     }
-    for (int i = 0; i < 9; ++i)
-      for (int j = 0; j <= i; ++j) {
-        const double v = Tb[tri(na + i, na + j)];
-        Pm[9 * i + j] = v;
-        Pm[9 * j + i] = v;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const int idx = i < pv ? tpv + i : i * (i + 1) / 2 + pv;
+      tb[idx * TS] = (i == pv) ? -ip : bc[i];
+    }
+  }
+  // factor record and P_k
+#pragma unroll
+  for (int j = 0; j < NA; ++j) {
+#pragma unroll
+    for (int l = 0; l <= j; ++l) CMPC_R(w, R_HI + tri(j, l)) = -tb[tri(j, l) * TS];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) CMPC_R(w, R_K + 9 * j + i) = -tb[tri(NA + i, j) * TS];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) Pm[tri(i, j)] = tb[tri(NA + i, NA + j) * TS];
+  }
+}
+
+template <int MODE, bool FAST>
+CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool on) {
+  const int N = P.N;
+  const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
+  KnotStream ks;
+  ks.open(T, I, SEG_C | (MODE == MODE_PMM ? SEG_F : 0), R_META, N, N + 1, -1);
+#if defined(__CUDACC__)
+  constexpr int TS = TL;
+  double* tb = T.ring + RING_DEPTH * (R_STAGED - R_META) * TL + I.lane;   // behind the stream's slots
+#else
+  constexpr int TS = 1;
+  double tbl[231];
+  double* tb = tbl;
+#endif
+  double Pm[45];
+  {
+    const double* r = ks.acquire();
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 45; ++i) Pm[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Pm[tri(i, i)] = P.Wx[i] + rho_e;
+      if (MODE == MODE_ADMM) {
+#pragma unroll
+        for (int i = 6; i < 9; ++i) Pm[tri(i, i)] += S.rhok;
+      } else if (S.kap) {
+        double kM[9], kl[3];
+        const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+        const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
+        pmm_kappa_terms(P, S, meta_rd(r, I.lane)[TL], kb, yk, kM, kl);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j) Pm[tri(6 + i, 6 + j)] += kM[3 * i + j];
       }
+    }
+    ks.release();
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    const double* r = ks.acquire();
+    if (on) {
+      double* w = rec_of(T, I, k);
+      const double* gt = gt_of(T, I, k);
+      switch (T.ns(k)) {
+        case 0: factor_knot<0, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
+        case 1: factor_knot<1, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
+        case 2: factor_knot<2, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
+        case 3: factor_knot<3, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
+        default: factor_knot<4, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
+      }
+    }
+    ks.release();
   }
 }
 
 // ---------------------------------------------------------------- backward sweep (linear term)
 // p_N = qx_N;  g = p + Pc;  hu = ru + B'g;  d = -Hinv hu;  p = qx + A'g + K'hu.
 // qx = -Wx xbar (+ kappa / terminal penalty terms), ru = friction penalty terms.
+// r: staged read pointer, w: the knot's record in global memory (writes).
 template <int MODE>
 CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, const double* r, int pm, double* p) {
   const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
@@ -332,20 +506,23 @@ CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, const double* r, in
     const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
     double w[3];
     prox_kappa(S, vk, kb, w);
+#pragma unroll
     for (int a = 0; a < 3; ++a) p[6 + a] += -S.rhok * (w[a] + w[a] - vk[a]);
   } else if (S.kap) {
     const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
     double kM[9], kl[3];
     pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
+#pragma unroll
     for (int a = 0; a < 3; ++a) p[6 + a] += kl[a];
   }
 }
 
 template <int NS, int MODE, bool FAST>
-CMPC_HD void bwd_knot(const Params& P, const Sv& S, double* r, const int* im, const double* gt, int k, double* p) {
+CMPC_HD void bwd_knot(const Params& P, const Sv& S, const double* r, double* w, int lane, const double* gt, int k, double* p) {
   constexpr int NA = 3 * NS;
+  const int* im = meta_rd(r, lane);
   const int nsl = im[0] & 7;
-  const int pm = (MODE == MODE_PMM) ? im[32] : 0;
+  const int pm = (MODE == MODE_PMM) ? im[TL] : 0;
   double g[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) g[i] = p[i] + CMPC_R(r, R_PC + i);
@@ -389,7 +566,7 @@ CMPC_HD void bwd_knot(const Params& P, const Sv& S, double* r, const int* im, co
     }
   }
 #pragma unroll
-  for (int j = 0; j < NA; ++j) CMPC_R(r, R_DV + j) = -acc[j];
+  for (int j = 0; j < NA; ++j) CMPC_R(w, R_DV + j) = -acc[j];
 #pragma unroll
   for (int j = 0; j < NA; ++j) {
 #pragma unroll
@@ -408,26 +585,35 @@ CMPC_HD void bwd_knot(const Params& P, const Sv& S, double* r, const int* im, co
 }
 
 template <int MODE, bool FAST>
-CMPC_FN void backward_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S) {
+CMPC_FN void backward_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S, bool on) {
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
+  KnotStream ks;
+  ks.open(T, I, SEG_A | SEG_B | SEG_C | (MODE == MODE_ADMM ? SEG_D : SEG_F), 0, N, N + 1, -1);
   double p[9];
   {
-    const double* r = rec_of(T, I, N);
-    for (int i = 0; i < 9; ++i) p[i] = -(P.Wx[i] * CMPC_R(r, R_XB + i)) - (rho_e * I.xf[i] - S.ye[i]);
-    kappa_linear_term<MODE>(P, S, r, meta_of(T, I, N)[32], p);
+    const double* r = ks.acquire();
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) p[i] = -(P.Wx[i] * CMPC_R(r, R_XB + i)) - (rho_e * I.xf[i] - S.ye[i]);
+      kappa_linear_term<MODE>(P, S, r, meta_rd(r, I.lane)[TL], p);
+    }
+    ks.release();
   }
   for (int k = N - 1; k >= 0; --k) {
-    double* r = rec_of(T, I, k);
-    const int* im = meta_of(T, I, k);
-    const double* gt = gt_of(T, I, k);
-    switch (T.nst[k]) {
-      case 0: bwd_knot<0, MODE, FAST>(P, S, r, im, gt, k, p); break;
-      case 1: bwd_knot<1, MODE, FAST>(P, S, r, im, gt, k, p); break;
-      case 2: bwd_knot<2, MODE, FAST>(P, S, r, im, gt, k, p); break;
-      case 3: bwd_knot<3, MODE, FAST>(P, S, r, im, gt, k, p); break;
-      default: bwd_knot<4, MODE, FAST>(P, S, r, im, gt, k, p); break;
+    const double* r = ks.acquire();
+    if (on) {
+      double* w = rec_of(T, I, k);
+      const double* gt = gt_of(T, I, k);
+      switch (T.ns(k)) {
+        case 0: bwd_knot<0, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
+        case 1: bwd_knot<1, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
+        case 2: bwd_knot<2, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
+        case 3: bwd_knot<3, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
+        default: bwd_knot<4, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
+      }
     }
+    ks.release();
   }
 }
 
@@ -435,33 +621,33 @@ CMPC_FN void backward_op(const Params& P, const TileCtx& T, const Inst& I, const
 // u~ = K x~ + d,  x~+ = A x~ + B u~ + c.
 // ADMM kinds: relaxation, friction / kappa / terminal updates of (w, y) stored as v, all
 // knot-local; with CHECK also OSQP's residuals (oracle/device_model.py iterate()).
-// Multiplier kinds: y += (1/delta) row on the active rows, solution record, primal residual,
-// and (UPD) the corrected friction active set: violated rows join, rows with a negative
+// Multiplier kind: y += (1/delta) row on the active rows, solution record, primal residual,
+// and (upd) the corrected friction active set: violated rows join, rows with a negative
 // multiplier leave; the number of changes is accumulated in nchg.
 // COPY: read-only LQR roll-out of the ADMM iterate into the solution record.
 struct Res { double pri, dua, npri, ndua; };
 
 template <int KIND>
-CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, double* r, const int* im, const Inst& I, int k, const double* x) {
+CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, const double* r, double* w, const Inst& I, int k, const double* x) {
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
-  constexpr bool PMMK = KIND == FW_PMM || KIND == FW_PMM_UPD, COPY = KIND == FW_COPY;
+  constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const int N = P.N;
   const double al = ADMM ? P.alpha : 1.0;
   if (PMMK || COPY) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) CMPC_R(r, R_X + i) = x[i];
+    for (int i = 0; i < 9; ++i) CMPC_R(w, R_X + i) = x[i];
   }
   double rdx[3] = {0.0, 0.0, 0.0};
   if (k >= 1) {
     if (ADMM) {
       const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
       const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
-      double w[3], vn[3];
-      prox_kappa(S, vk, kb, w);
+      double wk[3], vn[3];
+      prox_kappa(S, vk, kb, wk);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        vn[a] = fma(al, x[6 + a], fma(1.0 - al, w[a], vk[a] - w[a]));
-        CMPC_R(r, R_VK + a) = vn[a];
+        vn[a] = fma(al, x[6 + a], fma(1.0 - al, wk[a], vk[a] - wk[a]));
+        CMPC_R(w, R_VK + a) = vn[a];
       }
       if (CHK) {
         double wn[3];
@@ -470,12 +656,12 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, double* r, const int* im,
         for (int a = 0; a < 3; ++a) {
           R.pri = fmax(R.pri, fabs(x[6 + a] - wn[a]));
           R.npri = fmax(R.npri, fmax(fabs(x[6 + a]), fabs(wn[a])));
-          rdx[a] = S.rhok * ((vn[a] - wn[a]) - (vk[a] - w[a]) - (x[6 + a] - w[a]));
+          rdx[a] = S.rhok * ((vn[a] - wn[a]) - (vk[a] - wk[a]) - (x[6 + a] - wk[a]));
         }
       }
     } else if (PMMK) {
       if (S.kap) {
-        const int pm = im[32];
+        const int pm = meta_rd(r, I.lane)[TL];
         const int br = (pm >> 16) & 3;
         if (br != 0) {
           const double inv = 1.0 / P.delta;
@@ -484,10 +670,10 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, double* r, const int* im,
             const int code = (pm >> (18 + 2 * i)) & 3;
             const double sgn = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
             const double dk = x[6 + i] - CMPC_R(r, R_XB + 6 + i);
-            if (code == 0) CMPC_R(r, R_YK + i) += inv * dk;
+            if (code == 0) CMPC_R(w, R_YK + i) = CMPC_R(r, R_YK + i) + inv * dk;
             accv += sgn * dk;
           }
-          if (br == 2) CMPC_R(r, R_YK + 3) += inv * accv;
+          if (br == 2) CMPC_R(w, R_YK + 3) = CMPC_R(r, R_YK + 3) + inv * accv;
         }
       }
 #pragma unroll
@@ -521,10 +707,11 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, double* r, const int* im,
 }
 
 template <int NS, int KIND, bool FAST>
-CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, double* r, int* im, const double* gt, double* x, int& nchg) {
+CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, double* w, int* imw, int lane,
+                      const double* gt, double* x, bool upd, int& nchg) {
   constexpr int NA = 3 * NS;
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
-  constexpr bool PMMK = KIND == FW_PMM || KIND == FW_PMM_UPD, UPD = KIND == FW_PMM_UPD, COPY = KIND == FW_COPY;
+  constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const double al = ADMM ? P.alpha : 1.0;
   const double inv = 1.0 / P.delta;
   // controls u~ = K x + d
@@ -538,7 +725,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, double* r, int* im, 
   }
   if (PMMK || COPY) {
 #pragma unroll
-    for (int j = 0; j < NA; ++j) CMPC_R(r, R_U + j) = u[j];
+    for (int j = 0; j < NA; ++j) CMPC_R(w, R_U + j) = u[j];
   }
   // next state
   double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
@@ -565,8 +752,9 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, double* r, int* im, 
   }
   // friction rows of the knot
   if (!COPY) {
+    const int* im = meta_rd(r, lane);
     const int mt = im[0];
-    const int pm = PMMK ? im[32] : 0;
+    const int pm = PMMK ? im[TL] : 0;
     int newpm = 0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -581,7 +769,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, double* r, int* im, 
           const double v = CMPC_R(r, R_VF + 4 * s + row);
           const double w0 = fmin(v, 0.0), y0 = fmax(v, 0.0);
           const double vn = fma(al, cf[row], fma(1.0 - al, w0, y0));
-          CMPC_R(r, R_VF + 4 * s + row) = vn;
+          CMPC_R(w, R_VF + 4 * s + row) = vn;
           if (CHK) {
             const double wn = fmin(vn, 0.0);
             R.pri = fmax(R.pri, fabs(cf[row] - wn));
@@ -605,53 +793,64 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, double* r, int* im, 
         for (int row = 0; row < 4; ++row) {
           const int bit = 4 * s + row;
           const bool on = (pm >> bit) & 1;
-          const double yold = CMPC_R(r, R_YF + bit);
-          const double yn = fma(inv, cf[row], on ? yold : 0.0);
+          const double yn = fma(inv, cf[row], on ? CMPC_R(r, R_YF + bit) : 0.0);
           R.pri = fmax(R.pri, on ? fabs(cf[row]) : fmax(cf[row], 0.0));
           R.npri = fmax(R.npri, fabs(cf[row]));
-          if (UPD) {
+          if (upd) {
             const bool keep = on && !(yn < 0.0);
             const bool join = !on && (cf[row] > P.as_tol);
             const bool nb = keep || join;
             nchg += (nb != on) ? 1 : 0;
-            CMPC_R(r, R_YF + bit) = keep ? yn : 0.0;
+            CMPC_R(w, R_YF + bit) = keep ? yn : 0.0;
             newpm |= (nb ? 1 : 0) << bit;
-          } else {
-            CMPC_R(r, R_YF + bit) = on ? yn : yold;
+          } else if (on) {
+            CMPC_R(w, R_YF + bit) = yn;
           }
         }
       }
     }
-    if (UPD) im[32] = (pm & ~0xffff) | newpm;
+    if (PMMK && upd) imw[TL] = (pm & ~0xffff) | newpm;
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) x[i] = xn[i];
 }
 
+// commit: the lane wants the residuals of this sweep (a lane that did not ask for a check may
+// ride along in the CHECK kind when a neighbour did; its iterate update is the same arithmetic)
 template <int KIND, bool FAST>
-CMPC_FN void forward_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S, int* changes) {
-  constexpr bool CHK = KIND == FW_ADMM_CHECK, PMMK = KIND == FW_PMM || KIND == FW_PMM_UPD;
+CMPC_FN void forward_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool on, bool commit, bool upd, int* changes) {
+  constexpr bool CHK = KIND == FW_ADMM_CHECK, PMMK = KIND == FW_PMM;
   const int N = P.N;
+  KnotStream ks;
+  ks.open(T, I, SEG_B | SEG_C | SEG_E | (KIND == FW_PMM ? SEG_F : (KIND == FW_COPY ? 0 : SEG_D)), R_K, 0, N + 1, 1);
   Res R;
   R.pri = R.dua = R.npri = R.ndua = 0.0;
   int nchg = 0;
   double x[9];
-  for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
-  for (int k = 0; k <= N; ++k) {
-    double* r = rec_of(T, I, k);
-    int* im = meta_of(T, I, k);
-    fwd_state<KIND>(P, S, R, r, im, I, k, x);
-    if (k == N) break;
-    const double* gt = gt_of(T, I, k);
-    switch (T.nst[k]) {
-      case 0: fwd_knot<0, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
-      case 1: fwd_knot<1, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
-      case 2: fwd_knot<2, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
-      case 3: fwd_knot<3, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
-      default: fwd_knot<4, KIND, FAST>(P, S, R, r, im, gt, x, nchg); break;
-    }
+  if (on) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
   }
-  if (CHK || PMMK) {
+  for (int k = 0; k <= N; ++k) {
+    const double* r = ks.acquire();
+    if (on) {
+      double* w = rec_of(T, I, k);
+      fwd_state<KIND>(P, S, R, r, w, I, k, x);
+      if (k < N) {
+        int* imw = meta_of(T, I, k);
+        const double* gt = gt_of(T, I, k);
+        switch (T.ns(k)) {
+          case 0: fwd_knot<0, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
+          case 1: fwd_knot<1, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
+          case 2: fwd_knot<2, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
+          case 3: fwd_knot<3, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
+          default: fwd_knot<4, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
+        }
+      }
+    }
+    ks.release();
+  }
+  if (on && commit && (CHK || PMMK)) {
     S.pri = R.pri;
     S.npri = fmax(R.npri, S.dynrow);
     if (CHK) {
@@ -659,7 +858,7 @@ CMPC_FN void forward_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S,
       S.ndua = fmax(R.ndua, S.nq);
     }
   }
-  if (changes) *changes = nchg;
+  if (on && changes) *changes = nchg;
 }
 
 // ---------------------------------------------------------------- rho change: keep (w, y), move v
@@ -668,7 +867,7 @@ CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const 
   for (int k = 0; k <= P.N; ++k) {
     double* r = rec_of(T, I, k);
     if (k < P.N) {
-      const int nr = 4 * T.nst[k];
+      const int nr = 4 * T.ns(k);
       for (int j = 0; j < nr; ++j) {
         const double v = CMPC_R(r, R_VF + j);
         CMPC_R(r, R_VF + j) = fma(ratio, fmax(v, 0.0), fmin(v, 0.0));
@@ -686,54 +885,59 @@ CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const 
 
 // ---------------------------------------------------------------- active set of the polish
 // Friction row active iff its multiplier is positive (OSQP's rule -w < y <=> v > 0); trust-
-// region rows by the branch the prox took.  Returns 1 when some knot has trust-region rows.
+// region rows by the branch the prox took.  Sets *kap when some knot has trust-region rows.
 template <bool FAST>
-CMPC_FN int build_active_set_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S) {
+CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S, bool on, int* kap_out) {
   const int N = P.N;
   int kap = 0;
+  KnotStream ks;
+  ks.open(T, I, SEG_C | SEG_D, R_META, 0, N + 1, 1);
   for (int k = 0; k <= N; ++k) {
-    double* r = rec_of(T, I, k);
-    int* im = meta_of(T, I, k);
-    int pm = 0;
-    if (k < N) {
-      const int ns = T.nst[k];
-      const double* gt = gt_of(T, I, k);
-      for (int s = 0; s < ns; ++s) {
-        Fric<FAST> fr;
-        fr.load(P, gt, s);
-        for (int row = 0; row < 4; ++row) {
-          const double v = CMPC_R(r, R_VF + 4 * s + row);
-          const bool on = v > 0.0;
-          if (on) pm |= 1 << (4 * s + row);
-          CMPC_R(r, R_YF + 4 * s + row) = on ? S.rho * fr.e2(row) * v : 0.0;
+    const double* r = ks.acquire();
+    if (on) {
+      double* w = rec_of(T, I, k);
+      int pm = 0;
+      if (k < N) {
+        const int ns = T.ns(k);
+        const double* gt = gt_of(T, I, k);
+        for (int s = 0; s < ns; ++s) {
+          Fric<FAST> fr;
+          fr.load(P, gt, s);
+          for (int row = 0; row < 4; ++row) {
+            const double v = CMPC_R(r, R_VF + 4 * s + row);
+            const bool act = v > 0.0;
+            if (act) pm |= 1 << (4 * s + row);
+            CMPC_R(w, R_YF + 4 * s + row) = act ? S.rho * fr.e2(row) * v : 0.0;
+          }
         }
       }
-    }
-    if (k >= 1) {
-      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-      const double a3[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
-      double w[3], yk4[4] = {0.0, 0.0, 0.0, 0.0};
-      const int br = prox_trust(a3, kb, S.radius, S.weight, S.rhok, w);
-      if (br != 0) {
-        kap = 1;
-        pm |= br << 16;
-        double msum = 0.0;
-        int nz = 0;
-        for (int i = 0; i < 3; ++i) {
-          const double d = w[i] - kb[i];
-          const double yk = S.rhok * (a3[i] - w[i]);
-          const int code = d > 0.0 ? 1 : (d < 0.0 ? 2 : 0);
-          pm |= code << (18 + 2 * i);
-          if (code == 0) yk4[i] = yk;
-          else { msum += (code == 1 ? yk : -yk); ++nz; }
+      if (k >= 1) {
+        const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+        const double a3[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+        double wk[3], yk4[4] = {0.0, 0.0, 0.0, 0.0};
+        const int br = prox_trust(a3, kb, S.radius, S.weight, S.rhok, wk);
+        if (br != 0) {
+          kap = 1;
+          pm |= br << 16;
+          double msum = 0.0;
+          int nz = 0;
+          for (int i = 0; i < 3; ++i) {
+            const double d = wk[i] - kb[i];
+            const double yk = S.rhok * (a3[i] - wk[i]);
+            const int code = d > 0.0 ? 1 : (d < 0.0 ? 2 : 0);
+            pm |= code << (18 + 2 * i);
+            if (code == 0) yk4[i] = yk;
+            else { msum += (code == 1 ? yk : -yk); ++nz; }
+          }
+          if (br == 2) yk4[3] = nz ? msum / nz : 0.0;
         }
-        if (br == 2) yk4[3] = nz ? msum / nz : 0.0;
+        for (int i = 0; i < 4; ++i) CMPC_R(w, R_YK + i) = yk4[i];
       }
-      for (int i = 0; i < 4; ++i) CMPC_R(r, R_YK + i) = yk4[i];
+      meta_of(T, I, k)[TL] = pm;
     }
-    im[32] = pm;
+    ks.release();
   }
-  return kap;
+  if (on) *kap_out = kap;
 }
 
 // ---------------------------------------------------------------- trust test and accuracy ratio
@@ -841,7 +1045,7 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
     for (int j = 0; j < 4; ++j) CMPC_R(r, R_YK + j) = 0.0;
     for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = xb[6 + a];
     im[0] = L.meta;
-    im[32] = 0;
+    im[TL] = 0;
     if (k < N) {
       mc = fmax(mc, fabs(P.dtmg));
       for (int a = 0; a < 3; ++a) mc = fmax(mc, fabs(L.ck[a]));
@@ -1152,30 +1356,31 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
   }
 }
 
-// Executes one operation for one lane.
+// Executes one operation of the tile.  Every lane of the warp calls it with the same op (the
+// streamed operations are warp-collective); `on` says whether this lane takes part.
+// anycheck: some participating lane wants residuals from this ADMM sweep.
 template <bool FAST>
-CMPC_FN void execute(int op, const Params& P, const TileCtx& T, const Inst& I, const Batch& bt, Sv& S, Drv& D) {
+CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const Batch& bt, Sv& S, Drv& D, bool on, bool anycheck) {
   switch (op) {
-    case OP_FACTOR_ADMM: factor_op<MODE_ADMM, FAST>(P, T, I, S); break;
+    case OP_FACTOR_ADMM: factor_op<MODE_ADMM, FAST>(P, T, I, S, on); break;
     case OP_SWEEP_ADMM:
-      backward_op<MODE_ADMM, FAST>(P, T, I, S);
-      if (D.check) forward_op<FW_ADMM_CHECK, FAST>(P, T, I, S, nullptr);
-      else forward_op<FW_ADMM, FAST>(P, T, I, S, nullptr);
+      backward_op<MODE_ADMM, FAST>(P, T, I, S, on);
+      if (anycheck) forward_op<FW_ADMM_CHECK, FAST>(P, T, I, S, on, on && D.check, false, nullptr);
+      else forward_op<FW_ADMM, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
-    case OP_BUILD_AS: S.kap = build_active_set_op<FAST>(P, T, I, S); break;
-    case OP_FACTOR_PMM: factor_op<MODE_PMM, FAST>(P, T, I, S); break;
+    case OP_BUILD_AS: build_active_set_op<FAST>(P, T, I, S, on, &S.kap); break;
+    case OP_FACTOR_PMM: factor_op<MODE_PMM, FAST>(P, T, I, S, on); break;
     case OP_SWEEP_PMM:
-      backward_op<MODE_PMM, FAST>(P, T, I, S);
-      if (D.upd) forward_op<FW_PMM_UPD, FAST>(P, T, I, S, &D.chg);
-      else forward_op<FW_PMM, FAST>(P, T, I, S, nullptr);
+      backward_op<MODE_PMM, FAST>(P, T, I, S, on);
+      forward_op<FW_PMM, FAST>(P, T, I, S, on, true, on && D.upd, &D.chg);
       break;
-    case OP_RESCALE: rescale_op(P, T, I, S, D.rho_new, D.rhok_new); break;
+    case OP_RESCALE: if (on) rescale_op(P, T, I, S, D.rho_new, D.rhok_new); break;
     case OP_COPY_SOL:
-      backward_op<MODE_ADMM, FAST>(P, T, I, S);
-      forward_op<FW_COPY, FAST>(P, T, I, S, nullptr);
+      backward_op<MODE_ADMM, FAST>(P, T, I, S, on);
+      forward_op<FW_COPY, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
-    case OP_EVAL: evaluate_op(P, T, I, &D.snorm, &D.num, &D.den); break;
-    case OP_WRITE: write_solution_op(P, T, I, bt.X_out, bt.U_out); break;
+    case OP_EVAL: if (on) evaluate_op(P, T, I, &D.snorm, &D.num, &D.den); break;
+    case OP_WRITE: if (on) write_solution_op(P, T, I, bt.X_out, bt.U_out); break;
     default: break;
   }
 }

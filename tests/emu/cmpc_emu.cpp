@@ -40,7 +40,7 @@ static void run_tile_host(const Params& prm, const Batch& bt, int tile) {
     if (!live[l]) continue;
     drv_init(prm, S[l], D[l]);
     for (int op = advance(prm, S[l], D[l]); op != OP_DONE; op = advance(prm, S[l], D[l]))
-      execute<FAST>(op, prm, T, I[l], bt, S[l], D[l]);
+      execute<FAST>(op, prm, T, I[l], bt, S[l], D[l], true, D[l].check != 0);
     write_stats(bt, I[l], S[l], D[l]);
   }
 }
