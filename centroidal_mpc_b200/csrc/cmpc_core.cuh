@@ -17,7 +17,7 @@
 
 #if defined(__CUDACC__)   // the solver is device code in the CUDA build, host code in the test build (g++)
 #define CMPC_HD __device__ __forceinline__
-#define CMPC_FN __device__
+#define CMPC_FN __device__ __forceinline__
 #else
 #define CMPC_HD inline
 #define CMPC_FN

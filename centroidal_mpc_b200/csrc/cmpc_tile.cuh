@@ -22,6 +22,46 @@ constexpr int MODE_ADMM = 0, MODE_PMM = 1;
 constexpr int FW_ADMM = 0, FW_ADMM_CHECK = 1, FW_PMM = 2, FW_COPY = 4;
 
 #define CMPC_R(p, f) (p)[(f) * TL]
+// Staged data (what a KnotStream hands out) and per-lane scratch live in shared memory on the
+// device and are addressed by their 32-bit shared-space byte address through explicit
+// ld/st.shared (the compiler cannot see the address space through the ring bookkeeping, and
+// generic accesses cost a long-scoreboard round trip); in the host build they are plain pointers.
+// A StagedPtr addresses field BASE of the current knot for this lane (BASE = first field the
+// operation stages; a constexpr in the scope of every user of CMPC_S).
+#if defined(__CUDACC__)
+typedef unsigned StagedPtr;
+typedef unsigned ScratchPtr;
+CMPC_HD double staged_ld(StagedPtr p, int idx) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p + (unsigned)idx * 8u));
+  return v;
+}
+template <int BASE>
+CMPC_HD int staged_meta(StagedPtr p, int lane, int which) {   // which: 0 meta word, 1 active-set word
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(p - (unsigned)lane * 8u + (unsigned)((R_META - BASE) * TL * 8 + (which * TL + lane) * 4)));
+  return v;
+}
+CMPC_HD double sc_ld(ScratchPtr t, int idx) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(t + (unsigned)idx * 8u));
+  return v;
+}
+CMPC_HD void sc_st(ScratchPtr t, int idx, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(t + (unsigned)idx * 8u), "d"(v) : "memory");
+}
+#else
+typedef const double* StagedPtr;
+typedef double* ScratchPtr;
+CMPC_HD double staged_ld(StagedPtr p, int idx) { return p[idx]; }
+template <int BASE>
+CMPC_HD int staged_meta(StagedPtr p, int lane, int which) {
+  return (reinterpret_cast<const int*>(p - lane + (R_META - BASE) * TL) + lane)[which * TL];
+}
+CMPC_HD double sc_ld(ScratchPtr t, int idx) { return t[idx]; }
+CMPC_HD void sc_st(ScratchPtr t, int idx, double v) { t[idx] = v; }
+#endif
+#define CMPC_S(p, f) staged_ld(p, ((f) - BASE) * TL)
 
 struct TileCtx {
   const Params* prm;
@@ -46,19 +86,17 @@ struct Inst {
   const int* cact;
 };
 
-CMPC_HD double* rec_of(const TileCtx& T, const Inst& I, int k) { return T.ws + (long)k * (REC * TL) + I.lane; }
+CMPC_HD double* rec_of(const TileCtx& T, const Inst& I, int k) {
+  return T.ws + (long)k * (REC * TL) + I.lane;
+}
 CMPC_HD int* meta_of(const TileCtx& T, const Inst& I, int k) {
   return reinterpret_cast<int*>(T.ws + (long)k * (REC * TL) + R_META * TL) + I.lane;   // [0] meta, [TL] active set
-}
-// the same two words through a (possibly staged) record pointer r = base + lane
-CMPC_HD const int* meta_rd(const double* r, int lane) {
-  return reinterpret_cast<const int*>(r - lane + R_META * TL) + lane;
 }
 CMPC_HD double* gt_of(const TileCtx& T, const Inst& I, int k) { return T.gt ? T.gt + (long)k * (GT * TL) + I.lane : nullptr; }
 
 // ---------------------------------------------------------------- knot stream
 // Walks the knots of a tile in one direction and hands out a pointer through which the fields
-// of the requested segments of the current knot can be read (CMPC_R(r, field)).
+// of the requested segments of the current knot can be read (CMPC_S(r, field)).
 // Device: a ring of RING_DEPTH shared-memory slots filled by cp.async.bulk (one elected lane,
 // one bulk copy per segment, completion on an mbarrier), so the HBM latency of knot k+3 hides
 // behind the arithmetic of knots k..k+2 and every operand read is a shared-memory read.
@@ -76,16 +114,20 @@ CMPC_HD int seg_len(int seg, int ns) {
 CMPC_HD unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 struct KnotStream {
-  TileCtx* T;
+  // copies of the tile's ring description (kept by value so that they live in registers)
+  double* ring;
+  const double* ws;
+  const unsigned char* nst_s;
+  unsigned ring_sa, bars_sa, phases;
   int lane, segs, dir, base_f, slot_f, k_issue, n_issue, s_issue, s_wait;
 
   CMPC_HD void issue_one() {
     if (n_issue <= 0) return;
     if (lane == 0) {
-      const int ns = T->nst_s[k_issue];
-      const unsigned bar = T->bars_sa + 8u * s_issue;
-      const unsigned dst0 = T->ring_sa + (unsigned)(s_issue * slot_f - base_f) * (TL * 8);
-      const double* src0 = T->ws + (long)k_issue * (REC * TL);
+      const int ns = nst_s[k_issue];
+      const unsigned bar = bars_sa + 8u * s_issue;
+      const unsigned dst0 = ring_sa + (unsigned)(s_issue * slot_f) * (TL * 8);
+      const double* src0 = ws + (long)k_issue * (REC * TL);
       unsigned bytes = 0;
 #pragma unroll
       for (int sg = 1; sg <= SEG_F; sg <<= 1)
@@ -98,7 +140,7 @@ struct KnotStream {
         if (len == 0) continue;
         const int st = seg_start(sg);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst0 + (unsigned)st * (TL * 8)), "l"(src0 + st * TL), "r"(len), "r"(bar) : "memory");
+                     ::"r"(dst0 + (unsigned)(st - base_f) * (TL * 8)), "l"(src0 + st * TL), "r"(len), "r"(bar) : "memory");
       }
     }
     k_issue += dir;
@@ -107,7 +149,8 @@ struct KnotStream {
   }
   // knots k_first, k_first + dir, ... (count of them); fields below base_f are not staged
   CMPC_HD void open(TileCtx& Tc, const Inst& I, int segments, int base_field, int k_first, int count, int direction) {
-    T = &Tc; lane = I.lane; segs = segments; dir = direction; base_f = base_field; slot_f = R_STAGED - base_field;
+    ring = Tc.ring; ws = Tc.ws; nst_s = Tc.nst_s; ring_sa = Tc.ring_sa; bars_sa = Tc.bars_sa; phases = Tc.phases;
+    lane = I.lane; segs = segments; dir = direction; base_f = base_field; slot_f = R_STAGED - base_field;
     k_issue = k_first; n_issue = count; s_issue = s_wait = 0;
     // earlier generic-proxy writes of this warp (records written by the previous operation) must
     // be visible to the async proxy before the bulk copies read them
@@ -115,36 +158,39 @@ struct KnotStream {
     __syncwarp();
     for (int d = 0; d < RING_DEPTH; ++d) issue_one();
   }
-  CMPC_HD const double* acquire() {
-    const unsigned bar = T->bars_sa + 8u * s_wait;
-    const unsigned parity = (T->phases >> s_wait) & 1u;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "CMPC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra CMPC_DONE;\n"
-        "bra CMPC_WAIT;\n"
-        "CMPC_DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-    T->phases ^= 1u << s_wait;
-    return T->ring + (long)(s_wait * slot_f - base_f) * TL + lane;
+  CMPC_HD StagedPtr acquire() {
+    const unsigned bar = bars_sa + 8u * s_wait;
+    const unsigned parity = (phases >> s_wait) & 1u;
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      if (spins > (1u << 24)) asm volatile("trap;");   // a bulk copy that never lands: fail loudly, never hang
+    }
+    phases ^= 1u << s_wait;
+    return ring_sa + (unsigned)((s_wait * slot_f) * TL + lane) * 8u;
   }
   CMPC_HD void release() {
     __syncwarp();          // every lane is done reading the slot
     issue_one();           // refill it (s_issue == s_wait whenever something is left to issue)
     s_wait = (s_wait + 1 == RING_DEPTH) ? 0 : s_wait + 1;
   }
+  CMPC_HD void close(TileCtx& Tc) { Tc.phases = phases; }   // every issued copy has been consumed
 };
 #else
 struct KnotStream {
   const double* ws;
-  int lane, dir, k;
-  CMPC_HD void open(TileCtx& T, const Inst& I, int, int, int k_first, int, int direction) {
-    ws = T.ws; lane = I.lane; dir = direction; k = k_first;
+  int lane, dir, k, base_f;
+  CMPC_HD void open(TileCtx& T, const Inst& I, int, int base_field, int k_first, int, int direction) {
+    ws = T.ws; lane = I.lane; dir = direction; k = k_first; base_f = base_field;
   }
-  CMPC_HD const double* acquire() const { return ws + (long)k * (REC * TL) + lane; }
+  CMPC_HD StagedPtr acquire() const { return ws + (long)k * (REC * TL) + base_f * TL + lane; }
   CMPC_HD void release() { k += dir; }
+  CMPC_HD void close(TileCtx&) {}
 };
 #endif
 
@@ -194,15 +240,19 @@ template <> struct Fric<true> {
 template <> struct Fric<false> {
   double g[12], e[4];
   CMPC_HD void load(const Params&, const double* gt, int s) {
+#pragma unroll
     for (int i = 0; i < 12; ++i) g[i] = CMPC_R(gt, s * 16 + i);
+#pragma unroll
     for (int i = 0; i < 4; ++i) e[i] = CMPC_R(gt, s * 16 + 12 + i);
   }
   CMPC_HD double e2(int r) const { return e[r]; }
   CMPC_HD double G(int r, int a) const { return g[r * 3 + a]; }
   CMPC_HD void rows(const double* u, double* cf) const {
+#pragma unroll
     for (int r = 0; r < 4; ++r) cf[r] = fma(g[r * 3 + 2], u[2], fma(g[r * 3 + 1], u[1], g[r * 3] * u[0]));
   }
   CMPC_HD void trans(const double* t, double* o) const {
+#pragma unroll
     for (int a = 0; a < 3; ++a) o[a] = fma(g[9 + a], t[3], fma(g[6 + a], t[2], fma(g[3 + a], t[1], g[a] * t[0])));
   }
 };
@@ -213,11 +263,14 @@ template <> struct Fric<false> {
 CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double omega, double rho, double* w) {
   double b[3], ab[3];
   double s1 = 0.0;
+#pragma unroll
   for (int i = 0; i < 3; ++i) { b[i] = a[i] - kbar[i]; ab[i] = fabs(b[i]); s1 += ab[i]; }
   if (s1 <= r) { for (int i = 0; i < 3; ++i) w[i] = a[i]; return 0; }
   double tau = omega / rho, s2 = 0.0, d[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i) { d[i] = fmax(ab[i] - tau, 0.0); s2 += d[i]; }
   if (s2 >= r) {
+#pragma unroll
     for (int i = 0; i < 3; ++i) w[i] = kbar[i] + (b[i] < 0.0 ? -d[i] : d[i]);
     return 1;
   }
@@ -227,11 +280,13 @@ CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double ome
   if (s[0] < s[1]) { double t = s[0]; s[0] = s[1]; s[1] = t; }
   double css = 0.0;
   tau = 0.0;
+#pragma unroll
   for (int j = 0; j < 3; ++j) {
     css += s[j];
     double t = (css - r) / (double)(j + 1);
     if (s[j] - t > 0.0) tau = t;
   }
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     double di = fmax(ab[i] - tau, 0.0);
     w[i] = kbar[i] + (b[i] < 0.0 ? -di : di);
@@ -248,12 +303,15 @@ CMPC_HD void prox_kappa(const Sv& S, const double* v, const double* kbar, double
 // 2 sign -; branch (bits 16..17): 1 linear penalty, 2 surface row.
 CMPC_HD void pmm_kappa_terms(const Params& P, const Sv& S, int pm, const double* kbar, const double* yk, double* M,
                              double* kl) {
+#pragma unroll
   for (int i = 0; i < 9; ++i) M[i] = 0.0;
+#pragma unroll
   for (int i = 0; i < 3; ++i) kl[i] = 0.0;
   const int br = (pm >> 16) & 3;
   if (br == 0) return;
   const double inv = 1.0 / P.delta;
   double sg[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int code = (pm >> (18 + 2 * i)) & 3;
     sg[i] = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
@@ -263,11 +321,15 @@ CMPC_HD void pmm_kappa_terms(const Params& P, const Sv& S, int pm, const double*
     }
   }
   if (br == 1) {
+#pragma unroll
     for (int i = 0; i < 3; ++i) kl[i] += S.weight * sg[i];
   } else {             // surface: sg'(kappa - kbar) = radius
     double bb = S.radius;
+#pragma unroll
     for (int i = 0; i < 3; ++i) bb += sg[i] * kbar[i];
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
+#pragma unroll
       for (int j = 0; j < 3; ++j) M[3 * i + j] += inv * sg[i] * sg[j];
       kl[i] -= sg[i] * (inv * bb - yk[3]);
     }
@@ -277,6 +339,7 @@ CMPC_HD void pmm_kappa_terms(const Params& P, const Sv& S, int pm, const double*
 CMPC_HD void set_rho(const Params& P, double rho, double* rho_out, double* rhok_out, double* rhoe, double* rhoep) {
   const double wk = fmin(P.Wx[6], fmin(P.Wx[7], P.Wx[8]));
   double wm = 0.0;
+#pragma unroll
   for (int i = 0; i < 9; ++i) wm = fmax(wm, P.Wx[i]);
   *rho_out = rho;
   *rhok_out = rho * P.rho_k_rel * wk;
@@ -297,15 +360,15 @@ CMPC_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 CMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
 template <int NS, int MODE, bool FAST, int TS>
-CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int lane, const double* gt, int k,
-                         double* Pm, double* tb) {
+CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k,
+                         double* Pm, ScratchPtr tb) {
+  constexpr int BASE = R_META;
   constexpr int NA = 3 * NS, n = NA + 9;
   const double inv = 1.0 / P.delta;
-  const int* im = meta_rd(r, lane);
-  const int mt = im[0], nsl = mt & 7;
-  const int pm = (MODE == MODE_PMM) ? im[TL] : 0;
-  const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
-  const double ck[3] = {CMPC_R(r, R_CK), CMPC_R(r, R_CK + 1), CMPC_R(r, R_CK + 2)};
+  const int mt = staged_meta<BASE>(r, lane, 0), nsl = mt & 7;
+  const int pm = (MODE == MODE_PMM) ? staged_meta<BASE>(r, lane, 1) : 0;
+  const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
+  const double ck[3] = {CMPC_S(r, R_CK), CMPC_S(r, R_CK + 1), CMPC_S(r, R_CK + 2)};
   // Pc = P c
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
@@ -320,7 +383,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const double dts = s < nsl ? P.dt : 0.0;
-    const double ds[3] = {CMPC_R(r, R_D + 3 * s), CMPC_R(r, R_D + 3 * s + 1), CMPC_R(r, R_D + 3 * s + 2)};
+    const double ds[3] = {CMPC_S(r, R_D + 3 * s), CMPC_S(r, R_D + 3 * s + 1), CMPC_S(r, R_D + 3 * s + 2)};
     Fric<FAST> fr;
     fr.load(P, gt, s);
     double rr[4];
@@ -344,9 +407,9 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const int q1 = nxt3(q), q2 = prv3(q);
-        tb[tri(NA + q, j) * TS] = fma(P.dt, fma(wc[6 + q1], S3[q2], -(wc[6 + q2] * S3[q1])), wc[q]);
-        tb[tri(NA + 3 + q, j) * TS] = fma(P.dt_m, wc[q], wc[3 + q]);
-        tb[tri(NA + 6 + q, j) * TS] = wc[6 + q];
+        sc_st(tb, (tri(NA + q, j)) * TS, fma(P.dt, fma(wc[6 + q1], S3[q2], -(wc[6 + q2] * S3[q1])), wc[q]));
+        sc_st(tb, (tri(NA + 3 + q, j)) * TS, fma(P.dt_m, wc[q], wc[3 + q]));
+        sc_st(tb, (tri(NA + 6 + q, j)) * TS, wc[6 + q]);
       }
       // Huu[j][l], l <= j:  row (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
 #pragma unroll
@@ -359,7 +422,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int
           for (int row = 0; row < 4; ++row) radd = fma(rr[row] * fr.G(row, a), fr.G(row, b2), radd);
           v += radd;
         }
-        tb[tri(j, l) * TS] = v;
+        sc_st(tb, (tri(j, l)) * TS, v);
       }
     }
   }
@@ -368,8 +431,8 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int
     double kM[9], kl[3];
     const bool kap = MODE == MODE_PMM && S.kap && k >= 1;
     if (kap) {
-      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-      const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
+      const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
+      const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
       pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
     }
     double PA[9][9];
@@ -396,7 +459,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int
           if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
         }
         if (MODE == MODE_PMM && c >= 6 && kap) v += kM[3 * (rr2 - 6) + (c - 6)];
-        tb[tri(NA + rr2, NA + c) * TS] = v;
+        sc_st(tb, (tri(NA + rr2, NA + c)) * TS, v);
       }
     }
   }
@@ -404,59 +467,60 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, const double* r, double* w, int
   // overwritten afterwards, so that the update itself has no pv-dependent addressing.
   for (int pv = 0; pv < NA; ++pv) {
     const int tpv = pv * (pv + 1) / 2;
-    const double piv = tb[(tpv + pv) * TS];
+    const double piv = sc_ld(tb, ((tpv + pv)) * TS);
     if (!(piv > 0.0)) S.fail = 1;
     const double ip = 1.0 / piv;
     double c[n], bc[n];
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       const int idx = i < pv ? tpv + i : i * (i + 1) / 2 + pv;
-      c[i] = tb[idx * TS];
+      c[i] = sc_ld(tb, (idx) * TS);
       bc[i] = c[i] * ip;
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) {
 #pragma unroll
-      for (int j = 0; j <= i; ++j) tb[tri(i, j) * TS] = fma(-bc[i], c[j], tb[tri(i, j) * TS]);
+      for (int j = 0; j <= i; ++j) sc_st(tb, tri(i, j) * TS, fma(-bc[i], c[j], sc_ld(tb, tri(i, j) * TS)));
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       const int idx = i < pv ? tpv + i : i * (i + 1) / 2 + pv;
-      tb[idx * TS] = (i == pv) ? -ip : bc[i];
+      sc_st(tb, (idx) * TS, (i == pv) ? -ip : bc[i]);
     }
   }
   // factor record and P_k
 #pragma unroll
   for (int j = 0; j < NA; ++j) {
 #pragma unroll
-    for (int l = 0; l <= j; ++l) CMPC_R(w, R_HI + tri(j, l)) = -tb[tri(j, l) * TS];
+    for (int l = 0; l <= j; ++l) CMPC_R(w, R_HI + tri(j, l)) = -sc_ld(tb, (tri(j, l)) * TS);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) CMPC_R(w, R_K + 9 * j + i) = -tb[tri(NA + i, j) * TS];
+    for (int i = 0; i < 9; ++i) CMPC_R(w, R_K + 9 * j + i) = -sc_ld(tb, (tri(NA + i, j)) * TS);
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
 #pragma unroll
-    for (int j = 0; j <= i; ++j) Pm[tri(i, j)] = tb[tri(NA + i, NA + j) * TS];
+    for (int j = 0; j <= i; ++j) Pm[tri(i, j)] = sc_ld(tb, (tri(NA + i, NA + j)) * TS);
   }
 }
 
 template <int MODE, bool FAST>
 CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool on) {
+  constexpr int BASE = R_META;
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
   KnotStream ks;
   ks.open(T, I, SEG_C | (MODE == MODE_PMM ? SEG_F : 0), R_META, N, N + 1, -1);
 #if defined(__CUDACC__)
   constexpr int TS = TL;
-  double* tb = T.ring + RING_DEPTH * (R_STAGED - R_META) * TL + I.lane;   // behind the stream's slots
+  const ScratchPtr tb = T.ring_sa + (unsigned)(RING_DEPTH * (R_STAGED - R_META) * TL + I.lane) * 8u;   // behind the stream's slots
 #else
   constexpr int TS = 1;
   double tbl[231];
-  double* tb = tbl;
+  const ScratchPtr tb = tbl;
 #endif
   double Pm[45];
   {
-    const double* r = ks.acquire();
+    const StagedPtr r = ks.acquire();
     if (on) {
 #pragma unroll
       for (int i = 0; i < 45; ++i) Pm[i] = 0.0;
@@ -467,9 +531,9 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
         for (int i = 6; i < 9; ++i) Pm[tri(i, i)] += S.rhok;
       } else if (S.kap) {
         double kM[9], kl[3];
-        const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-        const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
-        pmm_kappa_terms(P, S, meta_rd(r, I.lane)[TL], kb, yk, kM, kl);
+        const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
+        const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
+        pmm_kappa_terms(P, S, staged_meta<BASE>(r, I.lane, 1), kb, yk, kM, kl);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -479,7 +543,7 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
     ks.release();
   }
   for (int k = N - 1; k >= 0; --k) {
-    const double* r = ks.acquire();
+    const StagedPtr r = ks.acquire();
     if (on) {
       double* w = rec_of(T, I, k);
       const double* gt = gt_of(T, I, k);
@@ -493,6 +557,7 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
     }
     ks.release();
   }
+  ks.close(T);
 }
 
 // ---------------------------------------------------------------- backward sweep (linear term)
@@ -500,16 +565,17 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
 // qx = -Wx xbar (+ kappa / terminal penalty terms), ru = friction penalty terms.
 // r: staged read pointer, w: the knot's record in global memory (writes).
 template <int MODE>
-CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, const double* r, int pm, double* p) {
-  const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
+CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, StagedPtr r, int pm, double* p) {
+  constexpr int BASE = 0;
+  const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
   if (MODE == MODE_ADMM) {
-    const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+    const double vk[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
     double w[3];
     prox_kappa(S, vk, kb, w);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p[6 + a] += -S.rhok * (w[a] + w[a] - vk[a]);
   } else if (S.kap) {
-    const double yk[4] = {CMPC_R(r, R_YK), CMPC_R(r, R_YK + 1), CMPC_R(r, R_YK + 2), CMPC_R(r, R_YK + 3)};
+    const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
     double kM[9], kl[3];
     pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
 #pragma unroll
@@ -518,28 +584,28 @@ CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, const double* r, in
 }
 
 template <int NS, int MODE, bool FAST>
-CMPC_HD void bwd_knot(const Params& P, const Sv& S, const double* r, double* w, int lane, const double* gt, int k, double* p) {
+CMPC_HD void bwd_knot(const Params& P, const Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k, double* p) {
+  constexpr int BASE = 0;
   constexpr int NA = 3 * NS;
-  const int* im = meta_rd(r, lane);
-  const int nsl = im[0] & 7;
-  const int pm = (MODE == MODE_PMM) ? im[TL] : 0;
+  const int nsl = staged_meta<BASE>(r, lane, 0) & 7;
+  const int pm = (MODE == MODE_PMM) ? staged_meta<BASE>(r, lane, 1) : 0;
   double g[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) g[i] = p[i] + CMPC_R(r, R_PC + i);
+  for (int i = 0; i < 9; ++i) g[i] = p[i] + CMPC_S(r, R_PC + i);
   double hu[NA > 0 ? NA : 1];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const double dts = s < nsl ? P.dt : 0.0;
-    const double ds[3] = {CMPC_R(r, R_D + 3 * s), CMPC_R(r, R_D + 3 * s + 1), CMPC_R(r, R_D + 3 * s + 2)};
+    const double ds[3] = {CMPC_S(r, R_D + 3 * s), CMPC_S(r, R_D + 3 * s + 1), CMPC_S(r, R_D + 3 * s + 2)};
     Fric<FAST> fr;
     fr.load(P, gt, s);
     double t[4], o[3];
 #pragma unroll
     for (int row = 0; row < 4; ++row) {
       if (MODE == MODE_ADMM) {
-        t[row] = S.rho * fr.e2(row) * fabs(CMPC_R(r, R_VF + 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
+        t[row] = S.rho * fr.e2(row) * fabs(CMPC_S(r, R_VF + 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
       } else {
-        const double y = CMPC_R(r, R_YF + 4 * s + row);
+        const double y = CMPC_S(r, R_YF + 4 * s + row);
         t[row] = ((pm >> (4 * s + row)) & 1) ? y : 0.0;
       }
     }
@@ -560,7 +626,7 @@ CMPC_HD void bwd_knot(const Params& P, const Sv& S, const double* r, double* w, 
   for (int j = 0; j < NA; ++j) {
 #pragma unroll
     for (int l = 0; l <= j; ++l) {
-      const double h = CMPC_R(r, R_HI + j * (j + 1) / 2 + l);
+      const double h = CMPC_S(r, R_HI + j * (j + 1) / 2 + l);
       acc[j] = fma(h, hu[l], acc[j]);
       if (l < j) acc[l] = fma(h, hu[j], acc[l]);
     }
@@ -570,38 +636,39 @@ CMPC_HD void bwd_knot(const Params& P, const Sv& S, const double* r, double* w, 
 #pragma unroll
   for (int j = 0; j < NA; ++j) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) kh[i] = fma(CMPC_R(r, R_K + 9 * j + i), hu[j], kh[i]);
+    for (int i = 0; i < 9; ++i) kh[i] = fma(CMPC_S(r, R_K + 9 * j + i), hu[j], kh[i]);
   }
   // p = qx + A'g + K'hu
-  const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+  const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const int a1 = nxt3(a), a2 = prv3(a);
-    p[a] = fma(P.dt, fma(g[6 + a1], S3[a2], -(g[6 + a2] * S3[a1])), g[a]) + kh[a] - P.Wx[a] * CMPC_R(r, R_XB + a);
-    p[3 + a] = fma(P.dt_m, g[a], g[3 + a]) + kh[3 + a] - P.Wx[3 + a] * CMPC_R(r, R_XB + 3 + a);
-    p[6 + a] = g[6 + a] + kh[6 + a] - P.Wx[6 + a] * CMPC_R(r, R_XB + 6 + a);
+    p[a] = fma(P.dt, fma(g[6 + a1], S3[a2], -(g[6 + a2] * S3[a1])), g[a]) + kh[a] - P.Wx[a] * CMPC_S(r, R_XB + a);
+    p[3 + a] = fma(P.dt_m, g[a], g[3 + a]) + kh[3 + a] - P.Wx[3 + a] * CMPC_S(r, R_XB + 3 + a);
+    p[6 + a] = g[6 + a] + kh[6 + a] - P.Wx[6 + a] * CMPC_S(r, R_XB + 6 + a);
   }
   if (k >= 1) kappa_linear_term<MODE>(P, S, r, pm, p);
 }
 
 template <int MODE, bool FAST>
 CMPC_FN void backward_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S, bool on) {
+  constexpr int BASE = 0;
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
   KnotStream ks;
   ks.open(T, I, SEG_A | SEG_B | SEG_C | (MODE == MODE_ADMM ? SEG_D : SEG_F), 0, N, N + 1, -1);
   double p[9];
   {
-    const double* r = ks.acquire();
+    const StagedPtr r = ks.acquire();
     if (on) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) p[i] = -(P.Wx[i] * CMPC_R(r, R_XB + i)) - (rho_e * I.xf[i] - S.ye[i]);
-      kappa_linear_term<MODE>(P, S, r, meta_rd(r, I.lane)[TL], p);
+      for (int i = 0; i < 9; ++i) p[i] = -(P.Wx[i] * CMPC_S(r, R_XB + i)) - (rho_e * I.xf[i] - S.ye[i]);
+      kappa_linear_term<MODE>(P, S, r, staged_meta<BASE>(r, I.lane, 1), p);
     }
     ks.release();
   }
   for (int k = N - 1; k >= 0; --k) {
-    const double* r = ks.acquire();
+    const StagedPtr r = ks.acquire();
     if (on) {
       double* w = rec_of(T, I, k);
       const double* gt = gt_of(T, I, k);
@@ -615,6 +682,7 @@ CMPC_FN void backward_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S
     }
     ks.release();
   }
+  ks.close(T);
 }
 
 // ---------------------------------------------------------------- forward sweep + local updates
@@ -628,7 +696,8 @@ CMPC_FN void backward_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S
 struct Res { double pri, dua, npri, ndua; };
 
 template <int KIND>
-CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, const double* r, double* w, const Inst& I, int k, const double* x) {
+CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, const Inst& I, int k, const double* x) {
+  constexpr int BASE = R_K;
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const int N = P.N;
@@ -640,8 +709,8 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, const double* r, double* 
   double rdx[3] = {0.0, 0.0, 0.0};
   if (k >= 1) {
     if (ADMM) {
-      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-      const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+      const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
+      const double vk[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
       double wk[3], vn[3];
       prox_kappa(S, vk, kb, wk);
 #pragma unroll
@@ -661,19 +730,20 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, const double* r, double* 
       }
     } else if (PMMK) {
       if (S.kap) {
-        const int pm = meta_rd(r, I.lane)[TL];
+        const int pm = staged_meta<BASE>(r, I.lane, 1);
         const int br = (pm >> 16) & 3;
         if (br != 0) {
           const double inv = 1.0 / P.delta;
           double accv = -S.radius;
+#pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int code = (pm >> (18 + 2 * i)) & 3;
             const double sgn = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
-            const double dk = x[6 + i] - CMPC_R(r, R_XB + 6 + i);
-            if (code == 0) CMPC_R(w, R_YK + i) = CMPC_R(r, R_YK + i) + inv * dk;
+            const double dk = x[6 + i] - CMPC_S(r, R_XB + 6 + i);
+            if (code == 0) CMPC_R(w, R_YK + i) = CMPC_S(r, R_YK + i) + inv * dk;
             accv += sgn * dk;
           }
-          if (br == 2) CMPC_R(w, R_YK + 3) = CMPC_R(r, R_YK + 3) + inv * accv;
+          if (br == 2) CMPC_R(w, R_YK + 3) = CMPC_S(r, R_YK + 3) + inv * accv;
         }
       }
 #pragma unroll
@@ -699,7 +769,7 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, const double* r, double* 
     for (int i = 0; i < 9; ++i) {
       const double Px = P.Wx[i] * x[i];
       const double rd = i >= 6 ? rdx[i - 6] : 0.0;
-      const double aty = rd - Px + P.Wx[i] * CMPC_R(r, R_XB + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
+      const double aty = rd - Px + P.Wx[i] * CMPC_S(r, R_XB + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
       R.dua = fmax(R.dua, fabs(rd));
       R.ndua = fmax(R.ndua, fmax(fabs(Px), fabs(aty)));
     }
@@ -707,8 +777,9 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, const double* r, double* 
 }
 
 template <int NS, int KIND, bool FAST>
-CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, double* w, int* imw, int lane,
+CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double* w, int* imw, int lane,
                       const double* gt, double* x, bool upd, int& nchg) {
+  constexpr int BASE = R_K;
   constexpr int NA = 3 * NS;
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
@@ -718,9 +789,9 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, dou
   double u[NA > 0 ? NA : 1];
 #pragma unroll
   for (int j = 0; j < NA; ++j) {
-    double t = CMPC_R(r, R_DV + j);
+    double t = CMPC_S(r, R_DV + j);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) t = fma(CMPC_R(r, R_K + 9 * j + i), x[i], t);
+    for (int i = 0; i < 9; ++i) t = fma(CMPC_S(r, R_K + 9 * j + i), x[i], t);
     u[j] = t;
   }
   if (PMMK || COPY) {
@@ -731,7 +802,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, dou
   double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    const double ds[3] = {CMPC_R(r, R_D + 3 * s), CMPC_R(r, R_D + 3 * s + 1), CMPC_R(r, R_D + 3 * s + 2)};
+    const double ds[3] = {CMPC_S(r, R_D + 3 * s), CMPC_S(r, R_D + 3 * s + 1), CMPC_S(r, R_D + 3 * s + 2)};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int a1 = nxt3(a), a2 = prv3(a);
@@ -741,20 +812,19 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, dou
   }
   double xn[9];
   {
-    const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+    const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int a1 = nxt3(a), a2 = prv3(a);
       xn[a] = fma(P.dt_m, x[3 + a], x[a]);
       xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
-      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_R(r, R_CK + a));
+      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_S(r, R_CK + a));
     }
   }
   // friction rows of the knot
   if (!COPY) {
-    const int* im = meta_rd(r, lane);
-    const int mt = im[0];
-    const int pm = PMMK ? im[TL] : 0;
+    const int mt = staged_meta<BASE>(r, lane, 0);
+    const int pm = PMMK ? staged_meta<BASE>(r, lane, 1) : 0;
     int newpm = 0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -766,7 +836,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, dou
         double dl[4];
 #pragma unroll
         for (int row = 0; row < 4; ++row) {
-          const double v = CMPC_R(r, R_VF + 4 * s + row);
+          const double v = CMPC_S(r, R_VF + 4 * s + row);
           const double w0 = fmin(v, 0.0), y0 = fmax(v, 0.0);
           const double vn = fma(al, cf[row], fma(1.0 - al, w0, y0));
           CMPC_R(w, R_VF + 4 * s + row) = vn;
@@ -793,7 +863,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, const double* r, dou
         for (int row = 0; row < 4; ++row) {
           const int bit = 4 * s + row;
           const bool on = (pm >> bit) & 1;
-          const double yn = fma(inv, cf[row], on ? CMPC_R(r, R_YF + bit) : 0.0);
+          const double yn = fma(inv, cf[row], on ? CMPC_S(r, R_YF + bit) : 0.0);
           R.pri = fmax(R.pri, on ? fabs(cf[row]) : fmax(cf[row], 0.0));
           R.npri = fmax(R.npri, fabs(cf[row]));
           if (upd) {
@@ -832,7 +902,7 @@ CMPC_FN void forward_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool 
     for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
   }
   for (int k = 0; k <= N; ++k) {
-    const double* r = ks.acquire();
+    const StagedPtr r = ks.acquire();
     if (on) {
       double* w = rec_of(T, I, k);
       fwd_state<KIND>(P, S, R, r, w, I, k, x);
@@ -850,6 +920,7 @@ CMPC_FN void forward_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool 
     }
     ks.release();
   }
+  ks.close(T);
   if (on && commit && (CHK || PMMK)) {
     S.pri = R.pri;
     S.npri = fmax(R.npri, S.dynrow);
@@ -878,6 +949,7 @@ CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const 
       const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
       double w[3];
       prox_kappa(S, vk, kb, w);
+#pragma unroll
       for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = fma(S.rhok / rhok_new, vk[a] - w[a], w[a]);
     }
   }
@@ -888,12 +960,13 @@ CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const 
 // region rows by the branch the prox took.  Sets *kap when some knot has trust-region rows.
 template <bool FAST>
 CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S, bool on, int* kap_out) {
+  constexpr int BASE = R_META;
   const int N = P.N;
   int kap = 0;
   KnotStream ks;
   ks.open(T, I, SEG_C | SEG_D, R_META, 0, N + 1, 1);
   for (int k = 0; k <= N; ++k) {
-    const double* r = ks.acquire();
+    const StagedPtr r = ks.acquire();
     if (on) {
       double* w = rec_of(T, I, k);
       int pm = 0;
@@ -903,8 +976,9 @@ CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, con
         for (int s = 0; s < ns; ++s) {
           Fric<FAST> fr;
           fr.load(P, gt, s);
+#pragma unroll
           for (int row = 0; row < 4; ++row) {
-            const double v = CMPC_R(r, R_VF + 4 * s + row);
+            const double v = CMPC_S(r, R_VF + 4 * s + row);
             const bool act = v > 0.0;
             if (act) pm |= 1 << (4 * s + row);
             CMPC_R(w, R_YF + 4 * s + row) = act ? S.rho * fr.e2(row) * v : 0.0;
@@ -912,8 +986,8 @@ CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, con
         }
       }
       if (k >= 1) {
-        const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-        const double a3[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+        const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
+        const double a3[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
         double wk[3], yk4[4] = {0.0, 0.0, 0.0, 0.0};
         const int br = prox_trust(a3, kb, S.radius, S.weight, S.rhok, wk);
         if (br != 0) {
@@ -921,6 +995,7 @@ CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, con
           pm |= br << 16;
           double msum = 0.0;
           int nz = 0;
+#pragma unroll
           for (int i = 0; i < 3; ++i) {
             const double d = wk[i] - kb[i];
             const double yk = S.rhok * (a3[i] - wk[i]);
@@ -931,12 +1006,14 @@ CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, con
           }
           if (br == 2) yk4[3] = nz ? msum / nz : 0.0;
         }
+#pragma unroll
         for (int i = 0; i < 4; ++i) CMPC_R(w, R_YK + i) = yk4[i];
       }
       meta_of(T, I, k)[TL] = pm;
     }
     ks.release();
   }
+  ks.close(T);
   if (on) *kap_out = kap;
 }
 
@@ -951,13 +1028,16 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
   for (int k = 0; k <= N; ++k) {
     const double* r = rec_of(T, I, k);
     double x[9], dx[9];
+#pragma unroll
     for (int i = 0; i < 9; ++i) { x[i] = CMPC_R(r, R_X + i); dx[i] = x[i] - I.Xr[k * 9 + i]; }
+#pragma unroll
     for (int i = 0; i < 9; ++i)
       for (int j = i; j < 9; ++j) A[i * 9 + j] = fma(dx[i], dx[j], A[i * 9 + j]);
     if (k == N) break;
     const int mt = meta_of(T, I, k)[0];
     const int ns = mt & 7;
     double u[MAXU];
+#pragma unroll
     for (int i = 0; i < MAXU; ++i) u[i] = 0.0;
     double F[3] = {0, 0, 0}, Tq[3] = {0, 0, 0};
     for (int sl = 0; sl < ns; ++sl) {
@@ -966,6 +1046,7 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
       const double us[3] = {CMPC_R(r, R_U + 3 * sl), CMPC_R(r, R_U + 3 * sl + 1), CMPC_R(r, R_U + 3 * sl + 2)};
       double t[3];
       cross3(ds, us, t);
+#pragma unroll
       for (int a = 0; a < 3; ++a) {
         u[3 * cid + a] = us[a];
         F[a] += us[a];
@@ -976,17 +1057,21 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
     const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
     double lin[9], nl[9], Sxc[3];
     cross3(S3, x, Sxc);
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
       lin[a] = x[a] + P.dt_m * x[3 + a];
       lin[3 + a] = x[3 + a] + P.dt * F[a] + (a == 2 ? P.dtmg : 0.0);
       lin[6 + a] = x[6 + a] + P.dt * Sxc[a] + P.dt * Tq[a] + CMPC_R(r, R_CK + a);
     }
     step_knot(P, x, u, I.cpos + (long)k * P.nc * 3, I.cact + (long)k * P.nc, nl);
+#pragma unroll
     for (int i = 6; i < 9; ++i) num += (nl[i] - lin[i]) * (nl[i] - lin[i]);
+#pragma unroll
     for (int i = 0; i < 9; ++i) den += lin[i] * lin[i];
   }
   *num_out = num;
   *den_out = den;
+#pragma unroll
   for (int i = 0; i < 9; ++i)
     for (int j = 0; j < i; ++j) A[i * 9 + j] = A[j * 9 + i];
   // largest eigenvalue of the Gram matrix: cyclic Jacobi
@@ -1035,46 +1120,60 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
     const double* xb = I.Xr + k * 9;
     KnotLin L;
     linearize_knot(P, xb, I.Ui + kk * P.nu, I.cpos + (long)kk * P.nc * 3, I.cact + (long)kk * P.nc, k == N, L);
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
       CMPC_R(r, R_XB + i) = xb[i];
       mq = fmax(mq, fabs(P.Wx[i] * xb[i]));
     }
+#pragma unroll
     for (int a = 0; a < 3; ++a) { CMPC_R(r, R_S + a) = L.S[a]; CMPC_R(r, R_CK + a) = L.ck[a]; }
+#pragma unroll
     for (int j = 0; j < MAXU; ++j) { CMPC_R(r, R_D + j) = L.d[j]; CMPC_R(r, R_DV + j) = 0.0; CMPC_R(r, R_U + j) = 0.0; }
+#pragma unroll
     for (int j = 0; j < 16; ++j) { CMPC_R(r, R_VF + j) = 0.0; CMPC_R(r, R_YF + j) = 0.0; }
+#pragma unroll
     for (int j = 0; j < 4; ++j) CMPC_R(r, R_YK + j) = 0.0;
+#pragma unroll
     for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = xb[6 + a];
     im[0] = L.meta;
     im[TL] = 0;
     if (k < N) {
       mc = fmax(mc, fabs(P.dtmg));
+#pragma unroll
       for (int a = 0; a < 3; ++a) mc = fmax(mc, fabs(L.ck[a]));
       const int ns = L.meta & 7;
       double* gt = gt_of(T, I, k);
+#pragma unroll
       for (int sl = 0; sl < MAXC; ++sl) {
         const int cid = sl < ns ? ((L.meta >> (4 + 2 * sl)) & 3) : 0;
         double G[12];
+#pragma unroll
         for (int row = 0; row < 4; ++row) {
           double mx = 0.0;
+#pragma unroll
           for (int a = 0; a < 3; ++a) {
             double g = pyr4(P, row, a);
             if (sl < ns && I.cR) {
               const double* Rm = I.cR + ((long)k * P.nc + cid) * 9;
               g = 0.0;
+#pragma unroll
               for (int b2 = 0; b2 < 3; ++b2) g += pyr4(P, row, b2) * Rm[a * 3 + b2];
             }
             G[row * 3 + a] = g;
             mx = fmax(mx, fabs(g) / sqrt(P.Wu[3 * cid + a]));
           }
           if (gt) {
+#pragma unroll
             for (int a = 0; a < 3; ++a) CMPC_R(gt, sl * 16 + row * 3 + a) = G[row * 3 + a];
             CMPC_R(gt, sl * 16 + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
           }
         }
         if (sl < ns) {
           const double* ub = I.Ui + k * P.nu + 3 * cid;
+#pragma unroll
           for (int row = 0; row < 4; ++row) {
             double cf = 0.0;
+#pragma unroll
             for (int a = 0; a < 3; ++a) cf += G[row * 3 + a] * ub[a];
             CMPC_R(r, R_VF + 4 * sl + row) = fmin(cf, 0.0);
           }
@@ -1084,8 +1183,10 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
   }
   S.nq = mq;
   double mi = 0.0;
+#pragma unroll
   for (int i = 0; i < 9; ++i) mi = fmax(mi, fabs(I.xi[i]));
   S.dynrow = fmax(mc, mi);
+#pragma unroll
   for (int i = 0; i < 9; ++i) S.ye[i] = 0.0;
   S.kap = 0;
   S.fail = 0;
@@ -1099,6 +1200,7 @@ CMPC_FN void write_solution_op(const Params& P, const TileCtx& T, const Inst& I,
   double* Uo = U_out + (long)I.b * N * P.nu;
   for (int k = 0; k <= N; ++k) {
     const double* r = rec_of(T, I, k);
+#pragma unroll
     for (int i = 0; i < 9; ++i) Xo[k * 9 + i] = CMPC_R(r, R_X + i);
     if (k == N) break;
     const int mt = meta_of(T, I, k)[0];
@@ -1106,6 +1208,7 @@ CMPC_FN void write_solution_op(const Params& P, const TileCtx& T, const Inst& I,
     for (int j = 0; j < P.nu; ++j) Uo[k * P.nu + j] = 0.0;
     for (int sl = 0; sl < ns; ++sl) {
       const int cid = (mt >> (4 + 2 * sl)) & 3;
+#pragma unroll
       for (int a = 0; a < 3; ++a) Uo[k * P.nu + 3 * cid + a] = CMPC_R(r, R_U + 3 * sl + a);
     }
   }
@@ -1155,6 +1258,7 @@ CMPC_HD void drv_init(const Params& P, Sv& S, Drv& D) {
   D.pri0 = D.dua0 = D.npri0 = D.ndua0 = 0.0;
   D.round = D.sw = D.chg = D.certified = D.upd = 0;
   D.prev_chg = 1 << 30;
+#pragma unroll
   for (int i = 0; i < 9; ++i) D.ye_keep[i] = 0.0;
   D.rho_new = D.rhok_new = 0.0;
   set_rho(P, P.rho0, &S.rho, &S.rhok, &S.rhoe, &S.rhoep);
@@ -1197,6 +1301,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         if (D.term || D.it == D.next_as) {
           D.pri0 = S.pri; D.dua0 = S.dua; D.npri0 = S.npri; D.ndua0 = S.ndua;
           if (P.polish) {
+#pragma unroll
             for (int i = 0; i < 9; ++i) D.ye_keep[i] = S.ye[i];
             D.pc = PC_AFTER_BUILD;
             return OP_BUILD_AS;
@@ -1260,6 +1365,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         break;
       case PC_POLISH_END: {
         S.kap = 0;
+#pragma unroll
         for (int i = 0; i < 9; ++i) S.ye[i] = D.ye_keep[i];   // the ADMM multiplier comes back
         // OSQP's rule for an uncertified polish after normal termination: keep it if it improves
         const double m0 = fmax(D.pri0 / (P.eps_abs + P.eps_rel * D.npri0), D.dua0 / (P.eps_abs + P.eps_rel * D.ndua0));
