@@ -1358,7 +1358,6 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
           D.pc = PC_POLISH_END;
           break;
         }
-        if (D.chg > D.prev_chg) { D.pc = PC_POLISH_END; break; }   // the active set is not settling: back to ADMM
         D.prev_chg = D.chg;
         ++D.round;
         D.pc = D.round > P.as_rounds ? PC_POLISH_END : PC_ROUND_TOP;

@@ -315,7 +315,7 @@ class RiccatiADMM:
           sign'(kappa-kappa_bar) = radius, zero components pinned.
         After each round the friction active set is corrected (rows that came out violated by
         more than tol join, rows whose multiplier came out negative leave) and the round is
-        repeated, at most 1 + rounds times or until the number of changes stops decreasing.
+        repeated, at most 1 + rounds times.
 
         Returns (certified, pri, npri).  certified: no row wants to change and the primal
         residual is <= tol; stationarity is exact by construction, so the polished point
@@ -398,8 +398,6 @@ class RiccatiADMM:
             ypol = self.yf.copy()
             if chg == 0:
                 certified = pri <= tol
-                break
-            if chg > prev_chg:
                 break
             prev_chg = chg
         self.Mk = None
