@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcmpc_b200.so")
+# CMPC_B200_LIB: another build of the same library (kernel experiments); never a different backend
+LIB_PATH = os.environ.get("CMPC_B200_LIB") or os.path.join(_HERE, "csrc", "libcmpc_b200.so")
 
 
 class cmpc_dims(C.Structure):

@@ -68,7 +68,10 @@ constexpr int R_STAGED = 274;  // fields [0, R_STAGED) can be staged by the swee
 constexpr int SEG_A = 1, SEG_B = 2, SEG_C = 4, SEG_D = 8, SEG_E = 16, SEG_F = 32;
 constexpr int GT = 64;       // general friction table per knot: per slot G (12, row-major 4x3) + e2 (4)
 constexpr int INFO = 12;     // per-instance statistics (cmpc_get_stats)
-constexpr int RING_DEPTH = 3;  // knots in flight per tile
+#ifndef CMPC_RING_DEPTH
+#define CMPC_RING_DEPTH 2
+#endif
+constexpr int RING_DEPTH = CMPC_RING_DEPTH;  // knots in flight per tile
 
 enum Status { ST_OK = 0, ST_QP_MAXITER = 1, ST_QP_NUMERIC = 2 };
 
