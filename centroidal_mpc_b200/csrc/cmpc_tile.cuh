@@ -1145,6 +1145,7 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
       double* gt = gt_of(T, I, k);
 #pragma unroll
       for (int sl = 0; sl < MAXC; ++sl) {
+        if (sl >= ns && !gt) continue;   // padded slot on the fast path: nothing to write
         const int cid = sl < ns ? ((L.meta >> (4 + 2 * sl)) & 3) : 0;
         double G[12];
 #pragma unroll
@@ -1160,7 +1161,7 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
               for (int b2 = 0; b2 < 3; ++b2) g += pyr4(P, row, b2) * Rm[a * 3 + b2];
             }
             G[row * 3 + a] = g;
-            mx = fmax(mx, fabs(g) / sqrt(P.Wu[3 * cid + a]));
+            if (gt) mx = fmax(mx, fabs(g) / sqrt(P.Wu[3 * cid + a]));
           }
           if (gt) {
 #pragma unroll
