@@ -80,7 +80,7 @@ def run_reference_arm(args):
         return
     cores = host_cores()
     workers = max(1, min(cores, 64))
-    per_step = workers * 8
+    per_step = workers * 16
     for _ in range(args.warmup and 1):
         cpu_oracle_throughput(workers, workers)
     vals, times = [], []
@@ -151,28 +151,34 @@ class ClockSampler:
 
 def algorithmic_work(batch, stats):
     """HBM bytes and FP64 flops the algorithm must move / execute for one launch (DESIGN.md
-    "roofline"): per sweep pair the per-knot records both sweeps read and write, per
-    factorisation the stage record read and the factor record written, plus compulsory I/O.
-    Counts come from the solver's own statistics (ADMM iterations, multiplier-method sweeps,
-    factorisations per instance)."""
+    "roofline").  Bytes: per knot exactly the record fields each operation stages (the bulk-copy
+    segments of csrc/cmpc_core.cuh) plus the fields it writes, 8 bytes each, times the
+    operations each INSTANCE asked for (ADMM iterations, multiplier-method sweeps,
+    factorisations: the solver's own statistics), plus compulsory I/O.  Work a tile repeats
+    because a neighbouring lane needs another polish round is not algorithmic and is not counted."""
     import numpy as np
     ns = batch.contact_active[0].sum(axis=1).astype(float)   # active contacts per knot (shared plan)
     na = 3 * ns
     N = batch.N
-    # backward: Pc 9, xbar 9, S 3, d na, v/y rows 4ns, kappa copy 3, Hinv na^2, K 9na; writes d na
-    bwd = 9 + 9 + 3 + na + 4 * ns + 3 + na * na + 9 * na + na
-    # forward: d na, Kt 9na, stage (xbar 9, S 3, ck 3, d na), rows 4ns read + written, kappa copy 3 + 3
-    fwd = na + 9 * na + 9 + 3 + 3 + na + 8 * ns + 6
-    sweep_bytes = 8.0 * float(bwd.sum() + fwd.sum() + 2 * (9 + 9 + 3))                # + terminal knot
-    pmm_extra = 8.0 * float((9 + na).sum())                                           # solution record
-    factor_bytes = 8.0 * float((28 + na * na + 18 * na + 9).sum())
+    tri = na * (na + 1) / 2
+    segA, segB, segC, segD, segE, segF = 9 + tri, 9 * na, 16 + na, 3 + 4 * ns, na, 4 + 4 * ns
+    term = 16 + 3                                             # terminal knot: stage data + kappa copy
+    bwd_admm = (segA + segB + segC + segD + na).sum() + term            # + writes d_k
+    fwd_admm = (segB + segC + segD + segE + 3 + 4 * ns).sum() + term + 3   # + writes vk, vf
+    bwd_pmm = (segA + segB + segC + segF + na).sum() + 16 + 4
+    fwd_pmm = (segB + segC + segE + segF + 9 + na + 4 * ns).sum() + 16 + 4 + 9   # + writes x, u, yf
+    fac = (segC + 9 + tri + 9 * na).sum() + 16                             # reads stage, writes Pc, Hinv, K
+    sweep_bytes = 8.0 * float(bwd_admm + fwd_admm)
+    pmm_bytes = 8.0 * float(bwd_pmm + fwd_pmm)
+    factor_bytes = 8.0 * float(fac)
     sweep_flops = 2.0 * float((na * na + 9 * na + 9 * na + 14 * ns + 60).sum())
-    factor_flops = 2.0 * float((na ** 3 + 9 * na * na + 81 * na + 6 * (na + 9) * na / 3 + 400).sum())
+    factor_flops = 2.0 * float((na * (na + 9) * (na + 10) / 2 + 27 * na + 6 * na * (na + 1) / 2 + 350).sum())
     admm = float(stats["qp_iters"].sum())
     pmm = float(stats["info"][:, 8].sum())
     nfac = float(stats["n_factor"].sum())
     io = batch.input_bytes() / batch.B + ((N + 1) * 9 + N * batch.nu) * 8 + 12
-    total_bytes = sweep_bytes * (admm + pmm) + pmm_extra * pmm + factor_bytes * nfac + io * batch.B
+    setup = 8.0 * float((segC + segD + segF + 12).sum())                   # records initialised once per solve
+    total_bytes = sweep_bytes * admm + pmm_bytes * pmm + factor_bytes * nfac + (io + setup) * batch.B
     total_flops = sweep_flops * (admm + pmm) + factor_flops * nfac
     return float(total_bytes), float(total_flops), sweep_bytes
 
@@ -284,7 +290,7 @@ def run_gpu_arm(args):
 
     cores = host_cores()
     workers = max(1, min(cores, 64))
-    cpu_v, cpu_dt = cpu_oracle_throughput(workers * 8, workers) if not args.no_cpu_baseline else (None, None)
+    cpu_v, cpu_dt = cpu_oracle_throughput(workers * 48, workers) if not args.no_cpu_baseline else (None, None)
 
     srt = sorted(step_ms)
     line = {
@@ -306,7 +312,7 @@ def run_gpu_arm(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "kernel": "cmpc_scp_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_sweep_pair_per_solve": per_iter_bytes,
-                     "note": "latency/issue-bound recursion at 28 warps per SM: neither HBM nor the FP64 pipe binds (DESIGN.md)",
+                     "note": "one tile (32 instances) per SM: the dependent chain of a knot step, not HBM or the FP64 pipe, sets the time (DESIGN.md section 6)",
                      "fp64": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "measured_peak_tflops": tf.value,
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / max(tf.value, 1e-9)}},
         "solver_stats": {"admm_iters_mean": float(stats["qp_iters"].mean()), "admm_iters_max": int(stats["qp_iters"].max()),
@@ -317,7 +323,7 @@ def run_gpu_arm(args):
                          "accepted": int((res["n_accepted"] > 0).sum()), "polished_frac": float(stats["info"][:, 7].mean())},
         "cpu_baseline": None if cpu_v is None else {
             "value": cpu_v, "unit": "solves/s", "cores": workers, "kind": "port",
-            "sample": "%d instances of the same workload, one single-threaded oracle solve per process, %.1f s" % (workers * 8, cpu_dt)},
+            "sample": "%d instances of the same workload, one single-threaded oracle solve per process, %.1f s" % (workers * 48, cpu_dt)},
     }
     print(json.dumps(line))
     if world > 1:

@@ -15,7 +15,7 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
   s->delta = 1e-6;              // OSQP polish regularisation
   s->adaptive_rho_tolerance = 5.0;
   s->max_iter = 4000;           // OSQP default
-  s->check_termination = 5;     // residuals are knot-local by-products of the forward sweep
+  s->check_termination = 25;    // OSQP default; residuals are knot-local by-products of the forward sweep
   s->polish = 1;                // scp_solver.py:63
   s->polish_refine_iter = 3;    // OSQP default
   s->adaptive_rho = 1;

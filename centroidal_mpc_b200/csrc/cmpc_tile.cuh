@@ -1330,12 +1330,13 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         ++D.nfact;
         if (S.fail) { D.pc = PC_POLISH_END; break; }
         D.chg = 0;
-        D.upd = 0;
+        D.upd = 1;   // the first multiplier sweep already corrects the active set
         D.pc = PC_AFTER_PMM0;
         return OP_SWEEP_PMM;
       case PC_AFTER_PMM0:
         ++S.n_pmm;
         D.sw = 0;
+        if (D.chg) { D.pc = PC_ROUND_CHECK; break; }   // rows changed: refactor right away
         D.pc = PC_SW_TOP;
         break;
       case PC_SW_TOP:

@@ -12,7 +12,7 @@ import numpy as np
 from . import dynamics
 
 ALPHA = 1.6
-CHECK = 5            # termination test every CHECK iterations (knot-local residuals, see iterate())
+CHECK = 25           # termination test every CHECK iterations (OSQP default) (knot-local residuals, see iterate())
 PER_ROW_FRICTION = True
 RHO0 = 2.0
 ADAPT_START = 200    # early residuals are transient; adapting on them hurts
@@ -383,18 +383,24 @@ class RiccatiADMM:
             self.yf = ypol * af
             self.wf = np.zeros_like(self.wf)
             self.factor()
-            sweep()
-            chg = 0
-            for sw in range(1 + refine):
-                cf, pri, npri = sweep()
+
+            def correct(cf):
+                nonlocal af
                 keep_r = af & ~(self.yf < 0.0)
                 join = (~af) & st.act[:, :, None] & (cf > tol)
                 new_af = keep_r | join
-                chg = int((new_af != af).sum())
+                n = int((new_af != af).sum())
                 self.yf = np.where(keep_r, self.yf, 0.0)
                 af = new_af
-                if chg or pri <= tol:
-                    break
+                return n
+            cf, pri, npri = sweep()
+            chg = correct(cf)          # the first multiplier sweep already corrects the active set
+            if chg == 0:
+                for sw in range(1 + refine):
+                    cf, pri, npri = sweep()
+                    chg = correct(cf)
+                    if chg or pri <= tol:
+                        break
             ypol = self.yf.copy()
             if chg == 0:
                 certified = pri <= tol
