@@ -35,7 +35,7 @@ int fail(int code, const std::string& msg) {
 // the later operations (evaluate, write) and the tile does those together.  Warps never
 // synchronise with each other.
 // ------------------------------------------------------------------------------------------
-constexpr int THREADS = 32;                      // one warp (one tile at a time) per block
+constexpr int THREADS = 64;   // solver warp (one tile at a time) + producer / helper warp
 constexpr long RING_BYTES = (long)RING_DEPTH * R_STAGED * TL * 8;
 inline long scp_smem_bytes(int N) { return RING_BYTES + 64 + ((N + 1 + 15) & ~15); }
 
@@ -88,12 +88,16 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
   T.phases = 0;
   unsigned char* nst_s = smem_raw + RING_BYTES + 64;
   T.nst_s = nst_s;
-  if (lane == 0) {
-    for (int d = 0; d < RING_DEPTH; ++d)
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < 2 * RING_DEPTH; ++d)   // "full" barriers (bulk-copy completion), then "empty" ones
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(T.bars_sa + 8u * d) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  __syncthreads();
+  if (threadIdx.x >= 32) {   // bulk-copy producer and factorisation helper
+    producer_warp(T.ring_sa, T.bars_sa, nst_s);
+    return;
+  }
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = atomicAdd(queue, 1);
@@ -103,6 +107,8 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
     else run_tile<false>(prm, bt, tile, T, nst_s);
     __syncwarp();
   }
+  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(T.bars_sa + 32u + 16u + 12u), "r"(-1) : "memory");   // count < 0: exit
+  asm volatile("bar.arrive 1, 64;" ::: "memory");
 }
 
 // compute_trajectory_data / integrate_dynamics_trajectory (one thread per instance and knot)

@@ -112,75 +112,106 @@ CMPC_HD int seg_len(int seg, int ns) {
 
 #if defined(__CUDACC__)
 CMPC_HD unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// bounded wait on an mbarrier phase: a bulk copy that never lands traps instead of hanging
+CMPC_HD void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1u << 24)) asm volatile("trap;");
+  }
+}
 
 struct KnotStream {
   // copies of the tile's ring description (kept by value so that they live in registers)
-  double* ring;
-  const double* ws;
-  const unsigned char* nst_s;
   unsigned ring_sa, bars_sa, phases;
-  int lane, segs, dir, base_f, slot_f, k_issue, n_issue, s_issue, s_wait;
+  int lane, slot_f, s_wait;
 
-  CMPC_HD void issue_one() {
-    if (n_issue <= 0) return;
-    if (lane == 0) {
-      const int ns = nst_s[k_issue];
-      const unsigned bar = bars_sa + 8u * s_issue;
-      const unsigned dst0 = ring_sa + (unsigned)(s_issue * slot_f) * (TL * 8);
-      const double* src0 = ws + (long)k_issue * (REC * TL);
-      unsigned bytes = 0;
-#pragma unroll
-      for (int sg = 1; sg <= SEG_F; sg <<= 1)
-        if (segs & sg) bytes += (unsigned)seg_len(sg, ns) * (TL * 8);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-#pragma unroll
-      for (int sg = 1; sg <= SEG_F; sg <<= 1) {
-        if (!(segs & sg)) continue;
-        const unsigned len = (unsigned)seg_len(sg, ns) * (TL * 8);
-        if (len == 0) continue;
-        const int st = seg_start(sg);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst0 + (unsigned)(st - base_f) * (TL * 8)), "l"(src0 + st * TL), "r"(len), "r"(bar) : "memory");
-      }
-    }
-    k_issue += dir;
-    --n_issue;
-    s_issue = (s_issue + 1 == RING_DEPTH) ? 0 : s_issue + 1;
-  }
-  // knots k_first, k_first + dir, ... (count of them); fields below base_f are not staged
+  // knots k_first, k_first + dir, ... (count of them); fields below base_field are not staged.
+  // The stream is handed to the CTA's producer warp: descriptor in shared memory, named barrier 1.
   CMPC_HD void open(TileCtx& Tc, const Inst& I, int segments, int base_field, int k_first, int count, int direction) {
-    ring = Tc.ring; ws = Tc.ws; nst_s = Tc.nst_s; ring_sa = Tc.ring_sa; bars_sa = Tc.bars_sa; phases = Tc.phases;
-    lane = I.lane; segs = segments; dir = direction; base_f = base_field; slot_f = R_STAGED - base_field;
-    k_issue = k_first; n_issue = count; s_issue = s_wait = 0;
+    ring_sa = Tc.ring_sa; bars_sa = Tc.bars_sa; phases = Tc.phases;
+    lane = I.lane; slot_f = R_STAGED - base_field; s_wait = 0;
     // earlier generic-proxy writes of this warp (records written by the previous operation) must
     // be visible to the async proxy before the bulk copies read them
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
-    for (int d = 0; d < RING_DEPTH; ++d) issue_one();
+    if (lane == 0) {
+      const unsigned c = bars_sa + 32u;
+      asm volatile("st.shared.u64 [%0], %1;" ::"r"(c), "l"(Tc.ws) : "memory");
+      asm volatile("st.shared.s32 [%0], %1;" ::"r"(c + 8u), "r"(direction) : "memory");
+      asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(c + 16u), "r"(segments), "r"(base_field), "r"(k_first), "r"(count) : "memory");
+    }
+    asm volatile("bar.arrive 1, 64;" ::: "memory");
   }
   CMPC_HD StagedPtr acquire() {
     const unsigned bar = bars_sa + 8u * s_wait;
-    const unsigned parity = (phases >> s_wait) & 1u;
-    unsigned done = 0;
-    for (unsigned spins = 0; !done; ++spins) {
-      asm volatile(
-          "{\n"
-          ".reg .pred p;\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-          "selp.u32 %0, 1, 0, p;\n"
-          "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-      if (spins > (1u << 24)) asm volatile("trap;");   // a bulk copy that never lands: fail loudly, never hang
-    }
+    mbar_wait(bar, (phases >> s_wait) & 1u);
     phases ^= 1u << s_wait;
     return ring_sa + (unsigned)((s_wait * slot_f) * TL + lane) * 8u;
   }
   CMPC_HD void release() {
     __syncwarp();          // every lane is done reading the slot
-    issue_one();           // refill it (s_issue == s_wait whenever something is left to issue)
+    if (lane == 0)         // tell the producer warp that the slot is free
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_sa + 8u * (RING_DEPTH + s_wait)) : "memory");
     s_wait = (s_wait + 1 == RING_DEPTH) ? 0 : s_wait + 1;
   }
   CMPC_HD void close(TileCtx& Tc) { Tc.phases = phases; }   // every issued copy has been consumed
 };
+
+// The producer warp of a CTA: waits for a stream descriptor (named barrier 1), then issues the
+// bulk copies of the stream's knots as ring slots fall free ("empty" mbarriers, one arrival per
+// release of the solver warp), and goes back to waiting.  count < 0 ends it.
+CMPC_HD void producer_warp(unsigned ring_sa, unsigned bars_sa, const unsigned char* nst_s) {
+  const int lane = (int)(threadIdx.x & 31u);
+  unsigned eph = 0xffffffffu;   // parity to wait for per "empty" barrier: a fresh barrier passes parity 1
+  for (;;) {
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    const unsigned c = bars_sa + 32u;
+    const double* ws;
+    int segs, base_f, k0, count, dir;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ws) : "r"(c) : "memory");
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dir) : "r"(c + 8u) : "memory");
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(segs), "=r"(base_f), "=r"(k0), "=r"(count) : "r"(c + 16u) : "memory");
+    if (count < 0) break;
+    const int slot_f = R_STAGED - base_f;
+    auto issue = [&](int i, int s) {   // knot number i of the stream into slot s
+      mbar_wait(bars_sa + 8u * (RING_DEPTH + s), (eph >> s) & 1u);
+      eph ^= 1u << s;
+      if (lane == 0) {
+        const int k = k0 + i * dir;
+        const int ns = nst_s[k];
+        const unsigned bar = bars_sa + 8u * s;
+        const unsigned dst0 = ring_sa + (unsigned)(s * slot_f) * (TL * 8);
+        const double* src0 = ws + (long)k * (REC * TL);
+        unsigned bytes = 0;
+#pragma unroll
+        for (int sg = 1; sg <= SEG_F; sg <<= 1)
+          if (segs & sg) bytes += (unsigned)seg_len(sg, ns) * (TL * 8);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+        for (int sg = 1; sg <= SEG_F; sg <<= 1) {
+          if (!(segs & sg)) continue;
+          const unsigned len = (unsigned)seg_len(sg, ns) * (TL * 8);
+          if (len == 0) continue;
+          const int st = seg_start(sg);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst0 + (unsigned)(st - base_f) * (TL * 8)), "l"(src0 + st * TL), "r"(len), "r"(bar) : "memory");
+        }
+      }
+    };
+    for (int i = 0; i < RING_DEPTH && i < count; ++i) issue(i, i);
+    int s = 0;
+    for (int i = 0; i < count; ++i) {
+      if (i + RING_DEPTH < count) issue(i + RING_DEPTH, s);
+      s = (s + 1 == RING_DEPTH) ? 0 : s + 1;
+    }
+  }
+}
 #else
 struct KnotStream {
   const double* ws;
@@ -361,7 +392,7 @@ CMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i);
 
 template <int NS, int MODE, bool FAST, int TS>
 CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k,
-                         double* Pm, ScratchPtr tb) {
+                         double* Pm, ScratchPtr tb, bool on) {
   constexpr int BASE = R_META;
   constexpr int NA = 3 * NS, n = NA + 9;
   const double inv = 1.0 / P.delta;
@@ -376,7 +407,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
     pc = fma(Pm[trs(i, 6)], ck[0], pc);
     pc = fma(Pm[trs(i, 7)], ck[1], pc);
     pc = fma(Pm[trs(i, 8)], ck[2], pc);
-    CMPC_R(w, R_PC + i) = pc;
+    if (on) CMPC_R(w, R_PC + i) = pc;
   }
   // control part of the tableau, one slot at a time:  W = P B (rows 3..8 kept), Hux = W'A, Huu = R + B'W
   double Wm[6][NA > 0 ? NA : 1];   // rows 3..8 of P B
@@ -468,7 +499,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
   for (int pv = 0; pv < NA; ++pv) {
     const int tpv = pv * (pv + 1) / 2;
     const double piv = sc_ld(tb, ((tpv + pv)) * TS);
-    if (!(piv > 0.0)) S.fail = 1;
+    if (!(piv > 0.0) && on) S.fail = 1;
     const double ip = 1.0 / piv;
     double c[n], bc[n];
 #pragma unroll
@@ -492,9 +523,9 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
 #pragma unroll
   for (int j = 0; j < NA; ++j) {
 #pragma unroll
-    for (int l = 0; l <= j; ++l) CMPC_R(w, R_HI + tri(j, l)) = -sc_ld(tb, (tri(j, l)) * TS);
+    for (int l = 0; l <= j; ++l) { const double v = -sc_ld(tb, (tri(j, l)) * TS); if (on) CMPC_R(w, R_HI + tri(j, l)) = v; }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) CMPC_R(w, R_K + 9 * j + i) = -sc_ld(tb, (tri(NA + i, j)) * TS);
+    for (int i = 0; i < 9; ++i) { const double v = -sc_ld(tb, (tri(NA + i, j)) * TS); if (on) CMPC_R(w, R_K + 9 * j + i) = v; }
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
@@ -548,11 +579,11 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
       double* w = rec_of(T, I, k);
       const double* gt = gt_of(T, I, k);
       switch (T.ns(k)) {
-        case 0: factor_knot<0, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
-        case 1: factor_knot<1, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
-        case 2: factor_knot<2, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
-        case 3: factor_knot<3, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
-        default: factor_knot<4, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb); break;
+        case 0: factor_knot<0, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
+        case 1: factor_knot<1, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
+        case 2: factor_knot<2, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
+        case 3: factor_knot<3, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
+        default: factor_knot<4, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
       }
     }
     ks.release();
