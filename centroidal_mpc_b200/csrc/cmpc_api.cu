@@ -50,9 +50,17 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
   Drv D;
   I.lane = lane & (TL - 1);
   D.check = D.upd = 0;
-  if (live) {
-    bind_instance(I, prm, bt, b);
-    setup_op(prm, T, I, S);
+  if (live) bind_instance(I, prm, bt, b);
+  {   // even knots here, odd knots on the producer warp
+    helper_fork(T, CMD_SETUP, __ballot_sync(0xffffffffu, live));
+    double mq = 0.0, mc = 0.0;
+    if (live) setup_knots(prm, T, I, 0, 2, &mq, &mc);
+    helper_join();
+    if (live) {
+      mq = fmax(mq, sc_ld(T.ring_sa + (unsigned)lane * 8u, 0));
+      mc = fmax(mc, sc_ld(T.ring_sa + (unsigned)lane * 8u, TL));
+      setup_finish(I, S, mq, mc);
+    }
   }
   for (int k = 0; k <= prm.N; ++k) {   // slots per knot of the tile
     const int ns = live ? (meta_of(T, I, k)[0] & 7) : 0;
@@ -95,7 +103,7 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
   }
   __syncthreads();
   if (threadIdx.x >= 32) {   // bulk-copy producer and factorisation helper
-    producer_warp(T.ring_sa, T.bars_sa, nst_s);
+    producer_warp(prm, bt, T.ring_sa, T.bars_sa, nst_s);
     return;
   }
   for (;;) {
@@ -107,7 +115,7 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
     else run_tile<false>(prm, bt, tile, T, nst_s);
     __syncwarp();
   }
-  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(T.bars_sa + 32u + 16u + 12u), "r"(-1) : "memory");   // count < 0: exit
+  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(T.bars_sa + 32u + 16u + 12u), "r"(CMD_EXIT) : "memory");
   asm volatile("bar.arrive 1, 64;" ::: "memory");
 }
 

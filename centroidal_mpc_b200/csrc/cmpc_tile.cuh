@@ -73,6 +73,7 @@ struct TileCtx {
   // shared copy of nst; all warp-uniform
   double* ring;
   unsigned ring_sa, bars_sa, phases;
+  int tile;
   const unsigned char* nst_s;
   CMPC_HD int ns(int k) const { return nst_s[k]; }
 #else
@@ -112,6 +113,8 @@ CMPC_HD int seg_len(int seg, int ns) {
 
 #if defined(__CUDACC__)
 CMPC_HD unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// commands to the producer warp other than a stream (the descriptor's count field)
+constexpr int CMD_EXIT = -1, CMD_SETUP = -2, CMD_WRITE = -3;
 // bounded wait on an mbarrier phase: a bulk copy that never lands traps instead of hanging
 CMPC_HD void mbar_wait(unsigned bar, unsigned parity) {
   unsigned done = 0;
@@ -125,6 +128,11 @@ CMPC_HD void mbar_wait(unsigned bar, unsigned parity) {
     if (spins > (1u << 24)) asm volatile("trap;");
   }
 }
+
+// solver warp: hand the producer warp the odd knots of a per-knot operation of this tile (mask:
+// the lanes that take part), and wait for it to finish
+CMPC_HD void helper_fork(const TileCtx& T, int cmd, unsigned mask);
+CMPC_HD void helper_join() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
 
 struct KnotStream {
   // copies of the tile's ring description (kept by value so that they live in registers)
@@ -166,7 +174,12 @@ struct KnotStream {
 // The producer warp of a CTA: waits for a stream descriptor (named barrier 1), then issues the
 // bulk copies of the stream's knots as ring slots fall free ("empty" mbarriers, one arrival per
 // release of the solver warp), and goes back to waiting.  count < 0 ends it.
-CMPC_HD void producer_warp(unsigned ring_sa, unsigned bars_sa, const unsigned char* nst_s) {
+CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k0, int kstep, double* mq_out, double* mc_out);
+CMPC_FN void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out, int k0, int kstep);
+CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b);
+CMPC_HD void bind_tile(TileCtx& T, const Params& P, const Batch& bt, int tile);
+
+CMPC_HD void producer_warp(const Params& P, const Batch& bt, unsigned ring_sa, unsigned bars_sa, const unsigned char* nst_s) {
   const int lane = (int)(threadIdx.x & 31u);
   unsigned eph = 0xffffffffu;   // parity to wait for per "empty" barrier: a fresh barrier passes parity 1
   for (;;) {
@@ -177,7 +190,28 @@ CMPC_HD void producer_warp(unsigned ring_sa, unsigned bars_sa, const unsigned ch
     asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ws) : "r"(c) : "memory");
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dir) : "r"(c + 8u) : "memory");
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(segs), "=r"(base_f), "=r"(k0), "=r"(count) : "r"(c + 16u) : "memory");
-    if (count < 0) break;
+    if (count == CMD_EXIT) break;
+    if (count == CMD_SETUP || count == CMD_WRITE) {   // half of a per-knot operation: the odd knots
+      const int tile = segs;
+      const unsigned mask = (unsigned)base_f;
+      TileCtx T;
+      bind_tile(T, P, bt, tile);
+      Inst I;
+      I.lane = lane;
+      if ((mask >> lane) & 1u) {
+        bind_instance(I, P, bt, tile * TL + lane);
+        if (count == CMD_SETUP) {
+          double mq, mc;
+          setup_knots(P, T, I, 1, 2, &mq, &mc);
+          sc_st(ring_sa + (unsigned)lane * 8u, 0, mq);      // the ring is idle during setup
+          sc_st(ring_sa + (unsigned)lane * 8u, TL, mc);
+        } else {
+          write_solution_knots(P, T, I, bt.X_out, bt.U_out, 1, 2);
+        }
+      }
+      asm volatile("bar.sync 2, 64;" ::: "memory");         // join
+      continue;
+    }
     const int slot_f = R_STAGED - base_f;
     auto issue = [&](int i, int s) {   // knot number i of the stream into slot s
       mbar_wait(bars_sa + 8u * (RING_DEPTH + s), (eph >> s) & 1u);
@@ -1141,10 +1175,12 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
 // ---------------------------------------------------------------- per-instance setup
 // K1 for every knot, friction table when not on the fast path, start of the iterate at the
 // linearisation point, constant parts of the residual norms.
-CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
+// setup_knots handles the knots k0, k0 + kstep, ... and returns the partial maxima through mq / mc
+// (device: the solver warp takes the even knots, the producer warp the odd ones).
+CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k0, int kstep, double* mq_out, double* mc_out) {
   const int N = P.N;
   double mq = 0.0, mc = 0.0;
-  for (int k = 0; k <= N; ++k) {
+  for (int k = k0; k <= N; k += kstep) {
     double* r = rec_of(T, I, k);
     int* im = meta_of(T, I, k);
     const int kk = k < N ? k : N - 1;
@@ -1213,6 +1249,10 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
       }
     }
   }
+  *mq_out = mq;
+  *mc_out = mc;
+}
+CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc) {
   S.nq = mq;
   double mi = 0.0;
 #pragma unroll
@@ -1226,11 +1266,12 @@ CMPC_FN void setup_op(const Params& P, const TileCtx& T, const Inst& I, Sv& S) {
   S.pri = S.dua = S.npri = S.ndua = 0.0;
 }
 
-CMPC_FN void write_solution_op(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out) {
+// knots k0, k0 + kstep, ... (device: even knots on the solver warp, odd ones on the producer warp)
+CMPC_FN void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out, int k0, int kstep) {
   const int N = P.N;
   double* Xo = X_out + (long)I.b * (N + 1) * 9;
   double* Uo = U_out + (long)I.b * N * P.nu;
-  for (int k = 0; k <= N; ++k) {
+  for (int k = k0; k <= N; k += kstep) {
     const double* r = rec_of(T, I, k);
 #pragma unroll
     for (int i = 0; i < 9; ++i) Xo[k * 9 + i] = CMPC_R(r, R_X + i);
@@ -1518,7 +1559,15 @@ CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const B
       forward_op<FW_COPY, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
     case OP_EVAL: if (on) evaluate_op(P, T, I, &D.snorm, &D.num, &D.den); break;
-    case OP_WRITE: if (on) write_solution_op(P, T, I, bt.X_out, bt.U_out); break;
+    case OP_WRITE:
+#if defined(__CUDACC__)
+      helper_fork(T, CMD_WRITE, __ballot_sync(0xffffffffu, on));
+      if (on) write_solution_knots(P, T, I, bt.X_out, bt.U_out, 0, 2);
+      helper_join();
+#else
+      if (on) write_solution_knots(P, T, I, bt.X_out, bt.U_out, 0, 1);
+#endif
+      break;
     default: break;
   }
 }
@@ -1549,8 +1598,20 @@ CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b) {
   I.xi = bt.x_init + (long)b * 9;
   I.xf = bt.x_final + (long)b * 9;
 }
+#if defined(__CUDACC__)
+CMPC_HD void helper_fork(const TileCtx& T, int cmd, unsigned mask) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  if ((threadIdx.x & 31u) == 0)
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(T.bars_sa + 48u), "r"(T.tile), "r"((int)mask), "r"(0), "r"(cmd) : "memory");
+  asm volatile("bar.arrive 1, 64;" ::: "memory");
+}
+#endif
 CMPC_HD void bind_tile(TileCtx& T, const Params& P, const Batch& bt, int tile) {
   T.prm = &P;
+#if defined(__CUDACC__)
+  T.tile = tile;
+#endif
   T.ws = bt.ws + (long)tile * (P.N + 1) * (REC * TL);
   T.gt = bt.gtab ? bt.gtab + (long)tile * P.N * (GT * TL) : nullptr;
   T.nst = bt.nst + (long)tile * (P.N + 1);

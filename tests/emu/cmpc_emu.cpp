@@ -30,7 +30,9 @@ static void run_tile_host(const Params& prm, const Batch& bt, int tile) {
     live[l] = b < bt.B;
     if (!live[l]) continue;
     bind_instance(I[l], prm, bt, b);
-    setup_op(prm, T, I[l], S[l]);
+    double mq = 0.0, mc = 0.0;
+    setup_knots(prm, T, I[l], 0, 1, &mq, &mc);
+    setup_finish(I[l], S[l], mq, mc);
     for (int k = 0; k <= prm.N; ++k) {
       const int ns = meta_of(T, I[l], k)[0] & 7;
       if (ns > T.nst[k]) T.nst[k] = ns;
