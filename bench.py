@@ -284,6 +284,11 @@ def run_gpu_arm(args):
     except OSError:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None   # DRAM bytes of one launch from the committed ncu --set full capture of this kernel
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except (OSError, ValueError):
+        pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     tf, ms = __import__("ctypes").c_double(), __import__("ctypes").c_double()
     lib.cmpc_fp64_peak(__import__("ctypes").byref(tf), __import__("ctypes").byref(ms))
@@ -308,7 +313,9 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None,
+                     "frac": achieved / peak_gbs,
+                     "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                     "traffic_source": None if traffic is None else traffic.get("source"),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "kernel": "cmpc_scp_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_sweep_pair_per_solve": per_iter_bytes,
