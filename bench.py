@@ -20,6 +20,8 @@ nothing on the solve path and one gather collects the solutions).
 in the cpu_baseline leg, as the thing compared against, never as the product path).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -346,10 +348,21 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+    # stdout carries exactly one JSON line: library chatter (NCCL banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_gpu_arm(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
