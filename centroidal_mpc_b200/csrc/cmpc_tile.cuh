@@ -850,6 +850,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const double al = ADMM ? P.alpha : 1.0;
   const double inv = 1.0 / P.delta;
+  const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
   // controls u~ = K x + d
   double u[NA > 0 ? NA : 1];
 #pragma unroll
@@ -933,7 +934,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
           R.npri = fmax(R.npri, fabs(cf[row]));
           if (upd) {
             const bool keep = on && !(yn < 0.0);
-            const bool join = !on && (cf[row] > P.as_tol);
+            const bool join = !on && (cf[row] > tolc);
             const bool nb = keep || join;
             nchg += (nb != on) ? 1 : 0;
             CMPC_R(w, R_YF + bit) = keep ? yn : 0.0;
@@ -1421,14 +1422,14 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         D.pc = PC_ROUND_CHECK;
         break;
       case PC_AFTER_PMM1:
-        if (D.chg || S.pri <= P.as_tol) { D.pc = PC_ROUND_CHECK; break; }
+        if (D.chg || S.pri <= P.as_tol * (1.0 + S.npri)) { D.pc = PC_ROUND_CHECK; break; }
         ++D.sw;
         D.pc = PC_SW_TOP;
         break;
       case PC_ROUND_CHECK:
         if (!(S.pri == S.pri)) { D.pc = PC_POLISH_END; break; }   // NaN
         if (D.chg == 0) {
-          D.certified = S.pri <= P.as_tol;
+          D.certified = S.pri <= P.as_tol * (1.0 + S.npri);   // absolute + relative, the form of OSQP's test
           D.pc = PC_POLISH_END;
           break;
         }

@@ -278,7 +278,7 @@ class RiccatiADMM:
             term = pri <= eps_abs + eps_rel * npri and dua <= eps_abs + eps_rel * ndua
             if term or it == next_as:
                 if polish:
-                    cert, ppri, pnpri = self.polish(rounds=as_rounds, refine=refine, tol=as_tol)
+                    cert, ppri, pnpri = self.polish(rounds=as_rounds, refine=refine, tol=as_tol, npri0=npri)
                     m0 = max(pri / (eps_abs + eps_rel * npri), dua / (eps_abs + eps_rel * ndua))
                     m1 = ppri / (eps_abs + eps_rel * pnpri)
                     if cert or (term and m1 < m0):
@@ -303,7 +303,7 @@ class RiccatiADMM:
         return status, it
 
     # ---------------------------------------------------------------- polish
-    def polish(self, delta=1e-6, refine=3, rounds=AS_ROUNDS, tol=AS_TOL):
+    def polish(self, delta=1e-6, refine=3, rounds=AS_ROUNDS, tol=AS_TOL, npri0=0.0):
         """OSQP-style polish (guess the active set, solve the equality-constrained QP) done as a
         method of multipliers with penalty 1/delta on the active rows — algebraically OSQP's
         regularised KKT solve + iterative refinement — reusing factor / x_update.
@@ -357,7 +357,8 @@ class RiccatiADMM:
                 self.Mk[k] += inv * np.outer(a, a)
         lin_keep = self.lin_k.copy()
         certified, prev_chg = False, 1 << 30
-        pri = npri = np.inf
+        pri = np.inf
+        npri = npri0      # thresholds are tol * (1 + npri of the previous sweep): absolute + relative
 
         def sweep():
             self.wk = np.zeros((N + 1, 3)); self.yk = np.zeros((N + 1, 3))
@@ -384,26 +385,28 @@ class RiccatiADMM:
             self.wf = np.zeros_like(self.wf)
             self.factor()
 
-            def correct(cf):
+            def correct(cf, npri_prev):
                 nonlocal af
                 keep_r = af & ~(self.yf < 0.0)
-                join = (~af) & st.act[:, :, None] & (cf > tol)
+                join = (~af) & st.act[:, :, None] & (cf > tol * (1.0 + npri_prev))
                 new_af = keep_r | join
                 n = int((new_af != af).sum())
                 self.yf = np.where(keep_r, self.yf, 0.0)
                 af = new_af
                 return n
+            npri_prev = npri
             cf, pri, npri = sweep()
-            chg = correct(cf)          # the first multiplier sweep already corrects the active set
+            chg = correct(cf, npri_prev)   # the first multiplier sweep already corrects the active set
             if chg == 0:
                 for sw in range(1 + refine):
+                    npri_prev = npri
                     cf, pri, npri = sweep()
-                    chg = correct(cf)
-                    if chg or pri <= tol:
+                    chg = correct(cf, npri_prev)
+                    if chg or pri <= tol * (1.0 + npri):
                         break
             ypol = self.yf.copy()
             if chg == 0:
-                certified = pri <= tol
+                certified = pri <= tol * (1.0 + npri)
                 break
             prev_chg = chg
         self.Mk = None

@@ -155,3 +155,61 @@ def test_linearize_and_rollout_kernels(gpu, cases):
                                      m._contact_data["contacts_position"][3], m._contact_data["contacts_logic"][3],
                                      m._contact_data["contacts_orient"][3])
     np.testing.assert_allclose(one, ref["dynamics"][:, 3], atol=1e-13)
+
+
+def test_general_friction_path_and_ragged_plans_on_device(gpu, cases):
+    """Rotated contact frames (per-knot friction table instead of the constant pyramid) and a
+    batch whose instances have different contact plans (padded slots): device == host build."""
+    import emu_binding as E
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.batch import ProblemBatch
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    from centroidal_mpc_b200.src.scp_solver import solve_scp_batched
+    conf = synthetic.load_conf("solo12_trot", N=20)
+    models = []
+    for b in range(3):
+        m = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b))
+        c, s = np.cos(0.1 * (b + 1)), np.sin(0.1 * (b + 1))
+        Rx = np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+        R = m._contact_data["contacts_orient"]
+        for k in range(conf.N):
+            for i in range(4):
+                if m._contact_data["contacts_logic"][k, i]:
+                    R[k, i] = Rx
+        models.append(m)
+    batch = ProblemBatch(models, shared_plan=False)
+    assert not batch.identity_R
+    out = solve_scp_batched(batch, conf.scp_params, return_stats=True)
+    emu = E.solve_scp(batch, conf.scp_params)
+    np.testing.assert_array_equal(out["status"], emu["status"])
+    np.testing.assert_array_equal(out["qp_iters"], emu["qp_iters"])
+    for b in range(3):
+        assert relerr(out["X"][b], emu["X"][b]) < 1e-7 and relerr(out["U"][b], emu["U"][b]) < 1e-7
+    # different gaits in one tile: trot and bound plans side by side
+    conf_t, mt = cases["solo12_trot"]
+    _, mb = cases["solo12_bound"]
+    mixed = ProblemBatch([mt[0], mb[0], mt[1], mb[1]], shared_plan=False)
+    out = solve_scp_batched(mixed, conf_t.scp_params, return_stats=True)
+    emu = E.solve_scp(mixed, conf_t.scp_params)
+    np.testing.assert_array_equal(out["qp_iters"], emu["qp_iters"])
+    for b in range(4):
+        assert relerr(out["X"][b], emu["X"][b]) < 1e-7 and relerr(out["U"][b], emu["U"][b]) < 1e-7
+
+
+def test_shipped_horizon_on_device(gpu):
+    """N = 165 / 107 are the horizons of the shipped trot and pace gait tables.
+    (At N = 165 the oracle's OSQP restatement stops at max_iter = 4000 with 'solved inaccurate',
+    i.e. the reference would return False; the device solver certifies a KKT point.)"""
+    import emu_binding as E
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.src.scp_solver import solve_scp_batched
+    for name, N, B in (("solo12_trot", 165, 40), ("solo12_pace", 107, 35)):
+        conf = synthetic.load_conf(name, N=N)
+        batch = synthetic.make_batch(conf, B)
+        out = solve_scp_batched(batch, conf.scp_params, return_stats=True)
+        emu = E.solve_scp(batch, conf.scp_params)
+        assert (out["status"] == 0).all()
+        np.testing.assert_array_equal(out["scp_iters"], emu["scp_iters"])
+        np.testing.assert_array_equal(out["qp_iters"], emu["qp_iters"])
+        for b in range(B):
+            assert relerr(out["X"][b], emu["X"][b]) < 1e-7 and relerr(out["U"][b], emu["U"][b]) < 1e-7
