@@ -150,3 +150,32 @@ def check_properties(batch, out, tol=1e-6):
             lin = td["dynamics"][:, k] + td["f_x"][k] @ (X[k] - batch.X_ref[b, k]) + \
                 td["f_u"][k] @ (out["U"][b, k] - batch.U_init[b, k])
             assert np.abs(X[k + 1] - lin).max() < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_problem_parameters_match_oracle(seed):
+    """Randomised problem data (gait, horizon, weights, friction coefficient, reference velocity
+    and noise): the kernel source against the oracle (OSQP restatement), 1e-6 norm-wise."""
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    rng = np.random.default_rng(seed)
+    name = ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"][seed % 4]
+    conf = synthetic.load_conf(name, N=int(rng.integers(12, 36)))
+    conf.mu = float(rng.uniform(0.3, 0.9))
+    conf.state_cost_weights = np.diag(np.diag(conf.state_cost_weights) * rng.uniform(0.3, 3.0, size=9))
+    conf.control_cost_weights = np.diag(np.diag(conf.control_cost_weights) * rng.uniform(0.3, 3.0))
+    X = synthetic.reference_trajectory(conf, 50 + seed, v=float(rng.uniform(0.0, 0.3)))
+    X[:, 6:9] += rng.normal(0.0, 5e-3, size=X[:, 6:9].shape)
+    model = Centroidal_model(conf, centroidal_traj=X)
+    # the oracle solved tightly (as the golden fixtures' X_tight): OSQP's default settings leave
+    # up to 4e-6 of their own error on some draws, or stop at max_iter = 4000
+    ref = scp.solve_scp(model.problem_arrays(), conf.scp_params,
+                        osqp_settings=dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=40000, polish_refine_iter=30))
+    out = E.solve_scp(ProblemBatch([model]), conf.scp_params)
+    if ref is False:
+        # a draw whose QP is infeasible (OSQP: 'primal infeasible'): the reference returns False
+        # (scp_solver.py:65-68,146-148) and the device reports the QP failure in status[]
+        assert out["status"][0] != 0
+        return
+    assert out["status"][0] == 0
+    assert out["scp_iters"][0] == ref["iterations"] and out["n_accepted"][0] == len(ref["state"])
+    assert relerr(out["X"][0].T, ref["state"][-1]) < TOL and relerr(out["U"][0].T, ref["control"][-1]) < TOL
