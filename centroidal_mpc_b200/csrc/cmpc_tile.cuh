@@ -148,7 +148,7 @@ struct KnotStream {
     // be visible to the async proxy before the bulk copies read them
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
-    if (lane == 0) {
+    if ((threadIdx.x & 31u) == 0) {   // (lane is the instance's lane, which wraps for tiles narrower than a warp)
       const unsigned c = bars_sa + 32u;
       asm volatile("st.shared.u64 [%0], %1;" ::"r"(c), "l"(Tc.ws) : "memory");
       asm volatile("st.shared.s32 [%0], %1;" ::"r"(c + 8u), "r"(direction) : "memory");
@@ -164,7 +164,7 @@ struct KnotStream {
   }
   CMPC_HD void release() {
     __syncwarp();          // every lane is done reading the slot
-    if (lane == 0)         // tell the producer warp that the slot is free
+    if ((threadIdx.x & 31u) == 0)   // tell the producer warp that the slot is free
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_sa + 8u * (RING_DEPTH + s_wait)) : "memory");
     s_wait = (s_wait + 1 == RING_DEPTH) ? 0 : s_wait + 1;
   }

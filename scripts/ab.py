@@ -10,7 +10,8 @@ import torch
 from centroidal_mpc_b200 import synthetic
 from centroidal_mpc_b200.device import BatchSolver
 conf = synthetic.load_conf("solo12_trot", N=100)
-solver = BatchSolver(synthetic.make_batch(conf, 4096))
+B = int(os.environ.get("AB_BATCH", "4096"))
+solver = BatchSolver(synthetic.make_batch(conf, B))
 for _ in range(3): solver.solve(conf.scp_params)
 torch.cuda.synchronize()
 ts = []
@@ -19,7 +20,7 @@ for _ in range(5):
     e0.record(); solver.solve(conf.scp_params); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 r = solver.results()
-print("%%-40s ms %%s  min %%.2f  failed %%d" %% (os.environ.get("CMPC_B200_LIB", "default")[-40:], " ".join("%%.2f" %% t for t in ts), min(ts), int((r["status"] != 0).sum())))
+print("%%-34s B %%6d ms %%s  min %%.2f  %%.0f solves/s  failed %%d" %% (os.environ.get("CMPC_B200_LIB", "default")[-34:], B, " ".join("%%.2f" %% t for t in ts), min(ts), B / min(ts) * 1e3, int((r["status"] != 0).sum())))
 ''' % root
 for lib in sys.argv[1:] or [""]:
     env = dict(os.environ)
