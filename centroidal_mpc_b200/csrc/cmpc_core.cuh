@@ -81,7 +81,7 @@ struct Params {
   double Wx[NX], Wu[MAXU];
   double e2[4];                       // fast path: friction-row equilibration factors e^2 per pyramid row
   // QP solver settings (OSQP's where they have the same meaning; scp_solver.py:61-63)
-  double alpha, rho0, eps_abs, eps_rel, delta, adapt_tol, rho_e_rel, rho_k_rel, rho_e_pol_rel, as_tol;
+  double alpha, rho0, eps_abs, eps_rel, delta, inv_delta, adapt_tol, rho_e_rel, rho_k_rel, rho_e_pol_rel, as_tol;
   int max_iter, check_every, polish, refine, adaptive_rho, adapt_start;
   int as_start, as_step, as_rounds;   // early active-set polish: first attempt, retry interval, rounds
   // SCP parameters (scp_solver.py:120-128)

@@ -54,7 +54,7 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
     p->e2[row] = 1.0 / (mx * mx);
   }
   p->alpha = qp->alpha; p->rho0 = qp->rho; p->eps_abs = qp->eps_abs;
-  p->eps_rel = qp->eps_rel; p->delta = qp->delta; p->adapt_tol = qp->adaptive_rho_tolerance;
+  p->eps_rel = qp->eps_rel; p->delta = qp->delta; p->inv_delta = 1.0 / qp->delta; p->adapt_tol = qp->adaptive_rho_tolerance;
   p->rho_e_rel = 100.0; p->rho_k_rel = 1.0;
   p->rho_e_pol_rel = 1e4;   // terminal-equality penalty while polishing (x max W_x), DESIGN.md
   p->max_iter = qp->max_iter; p->check_every = qp->check_termination > 0 ? qp->check_termination : 5;

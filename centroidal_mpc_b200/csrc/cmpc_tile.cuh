@@ -262,6 +262,7 @@ struct KnotStream {
 // Solver scalars of one lane.
 struct Sv {
   double rho, rhok, rhoe, rhoep, radius, weight;
+  double tau;                      // weight / rhok: threshold of the trust-region prox
   double pri, dua, npri, ndua;     // last residuals
   double nq, dynrow;               // constant parts of the residual norms
   int kap;                         // multiplier method: some knot has trust-region rows
@@ -325,13 +326,15 @@ template <> struct Fric<false> {
 // ---------------------------------------------------------------- trust-region prox
 // argmin_v omega*max(0, |v - kbar|_1 - r) + rho/2 |v - a|^2  (oracle/device_model.py prox_trust)
 // branch 0: inside the L1 ball; 1: outside after soft-thresholding; 2: on the surface.
-CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double omega, double rho, double* w) {
+// tau = omega / rho is passed in (no division on the device in the per-knot path: a double
+// division is a subroutine call in SASS and spills every live register around it)
+CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double tau_in, double* w) {
   double b[3], ab[3];
   double s1 = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { b[i] = a[i] - kbar[i]; ab[i] = fabs(b[i]); s1 += ab[i]; }
   if (s1 <= r) { for (int i = 0; i < 3; ++i) w[i] = a[i]; return 0; }
-  double tau = omega / rho, s2 = 0.0, d[3];
+  double tau = tau_in, s2 = 0.0, d[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { d[i] = fmax(ab[i] - tau, 0.0); s2 += d[i]; }
   if (s2 >= r) {
@@ -348,7 +351,7 @@ CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double ome
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     css += s[j];
-    double t = (css - r) / (double)(j + 1);
+    double t = (css - r) * (j == 0 ? 1.0 : (j == 1 ? 0.5 : 1.0 / 3.0));
     if (s[j] - t > 0.0) tau = t;
   }
 #pragma unroll
@@ -359,7 +362,7 @@ CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double ome
   return 2;
 }
 CMPC_HD void prox_kappa(const Sv& S, const double* v, const double* kbar, double* w) {
-  prox_trust(v, kbar, S.radius, S.weight, S.rhok, w);
+  prox_trust(v, kbar, S.radius, S.tau, w);
 }
 
 // ---------------------------------------------------------------- multiplier-method kappa rows
@@ -374,7 +377,7 @@ CMPC_HD void pmm_kappa_terms(const Params& P, const Sv& S, int pm, const double*
   for (int i = 0; i < 3; ++i) kl[i] = 0.0;
   const int br = (pm >> 16) & 3;
   if (br == 0) return;
-  const double inv = 1.0 / P.delta;
+  const double inv = P.inv_delta;
   double sg[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -424,12 +427,34 @@ CMPC_HD void set_rho(const Params& P, double rho, double* rho_out, double* rhok_
 CMPC_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 CMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
+// (P A)[i][c] and (A' P A)[q][c] straight from P (packed lower triangle) and the structure of A
+CMPC_HD double pa_of(const Params& P, const double* Pm, const double* S3, int i, int c) {
+  if (c < 3) {
+    const int c1 = nxt3(c), c2 = prv3(c);
+    return fma(P.dt, fma(Pm[trs(i, 6 + c1)], S3[c2], -(Pm[trs(i, 6 + c2)] * S3[c1])), Pm[trs(i, c)]);
+  }
+  if (c < 6) return fma(P.dt_m, Pm[trs(i, c - 3)], Pm[trs(i, c)]);
+  return Pm[trs(i, c)];
+}
+CMPC_HD double apa_of(const Params& P, const double* Pm, const double* S3, int q, int c) {
+  double v = pa_of(P, Pm, S3, q, c);
+  if (q < 3) {
+    const int q1 = nxt3(q), q2 = prv3(q);
+    v = fma(P.dt, fma(pa_of(P, Pm, S3, 6 + q1, c), S3[q2], -(pa_of(P, Pm, S3, 6 + q2, c) * S3[q1])), v);
+  } else if (q < 6) {
+    v = fma(P.dt_m, pa_of(P, Pm, S3, q - 3, c), v);
+  }
+  return v;
+}
+constexpr int TB_W = 231;   // scratch behind the tableau: rows 3..8 of W = P B, W[i*12 + l]  (72)
+constexpr int TB_SIZE = 231 + 72;
+
 template <int NS, int MODE, bool FAST, int TS>
 CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k,
                          double* Pm, ScratchPtr tb, bool on) {
   constexpr int BASE = R_META;
   constexpr int NA = 3 * NS, n = NA + 9;
-  const double inv = 1.0 / P.delta;
+  const double inv = P.inv_delta;
   const int mt = staged_meta<BASE>(r, lane, 0), nsl = mt & 7;
   const int pm = (MODE == MODE_PMM) ? staged_meta<BASE>(r, lane, 1) : 0;
   const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
@@ -444,7 +469,14 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
     if (on) CMPC_R(w, R_PC + i) = pc;
   }
   // control part of the tableau, one slot at a time:  W = P B (rows 3..8 kept), Hux = W'A, Huu = R + B'W
+#if defined(CMPC_FACTOR_V3)   // rows 3..8 of P B in the scratch, no P A temporary: nothing but P in registers
+#define CMPC_WM(i, l) sc_ld(tb, (TB_W + (i) * 12 + (l)) * TS)
+#define CMPC_WM_ST(i, l, v) sc_st(tb, (TB_W + (i) * 12 + (l)) * TS, v)
+#else
   double Wm[6][NA > 0 ? NA : 1];   // rows 3..8 of P B
+#define CMPC_WM(i, l) Wm[i][l]
+#define CMPC_WM_ST(i, l, v) Wm[i][l] = (v)
+#endif
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const double dts = s < nsl ? P.dt : 0.0;
@@ -467,7 +499,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       for (int i = 0; i < 9; ++i)
         wc[i] = dts * fma(Pm[trs(i, 6 + a1)], ds[a2], fma(-Pm[trs(i, 6 + a2)], ds[a1], Pm[trs(i, 3 + a)]));
 #pragma unroll
-      for (int i = 0; i < 6; ++i) Wm[i][j] = wc[3 + i];
+      for (int i = 0; i < 6; ++i) CMPC_WM_ST(i, j, wc[3 + i]);
       // Hux[j][q] = (W'A)[j][q]
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -479,7 +511,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       // Huu[j][l], l <= j:  row (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
 #pragma unroll
       for (int l = 0; l <= j; ++l) {
-        double v = dts * fma(Wm[3 + a1][l], ds[a2], fma(-Wm[3 + a2][l], ds[a1], Wm[a][l]));
+        double v = dts * fma(CMPC_WM(3 + a1, l), ds[a2], fma(-CMPC_WM(3 + a2, l), ds[a1], CMPC_WM(a, l)));
         if (l >= 3 * s) {   // R block of the slot: W_u + G' diag(rr) G
           const int b2 = l - 3 * s;
           double radd = (b2 == a) ? (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) : 0.0;
@@ -500,6 +532,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
       pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
     }
+#if !defined(CMPC_FACTOR_V3)
     double PA[9][9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -511,14 +544,20 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
         PA[i][6 + q] = Pm[trs(i, 6 + q)];
       }
     }
+#endif
 #pragma unroll
     for (int rr2 = 0; rr2 < 9; ++rr2) {
       const int g3 = rr2 / 3, a = rr2 - 3 * g3, a1 = nxt3(a), a2 = prv3(a);
 #pragma unroll
       for (int c = 0; c <= rr2; ++c) {
+#if defined(CMPC_FACTOR_V3)
+        double v = apa_of(P, Pm, S3, rr2, c);
+        (void)g3; (void)a1; (void)a2;
+#else
         double v = PA[rr2][c];
         if (g3 == 0) v = fma(P.dt, fma(PA[6 + a1][c], S3[a2], -(PA[6 + a2][c] * S3[a1])), v);
         else if (g3 == 1) v = fma(P.dt_m, PA[a][c], v);
+#endif
         if (c == rr2) {
           v += P.Wx[rr2];
           if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
@@ -569,7 +608,12 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
 }
 
 template <int MODE, bool FAST>
-CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool on) {
+CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on) {
+  // local copies: the reference arguments live in the caller's frame, which every generic store
+  // of the operation could alias (the compiler would reload them after each one)
+  const Params P = P_in;
+  const Inst I = I_in;
+  Sv S = S_in;
   constexpr int BASE = R_META;
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
@@ -580,7 +624,7 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
   const ScratchPtr tb = T.ring_sa + (unsigned)(RING_DEPTH * (R_STAGED - R_META) * TL + I.lane) * 8u;   // behind the stream's slots
 #else
   constexpr int TS = 1;
-  double tbl[231];
+  double tbl[TB_SIZE];
   const ScratchPtr tb = tbl;
 #endif
   double Pm[45];
@@ -623,6 +667,7 @@ CMPC_FN void factor_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool o
     ks.release();
   }
   ks.close(T);
+  if (S.fail) S_in.fail = 1;
 }
 
 // ---------------------------------------------------------------- backward sweep (linear term)
@@ -716,7 +761,10 @@ CMPC_HD void bwd_knot(const Params& P, const Sv& S, StagedPtr r, double* w, int 
 }
 
 template <int MODE, bool FAST>
-CMPC_FN void backward_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S, bool on) {
+CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, const Sv& S_in, bool on) {
+  const Params P = P_in;
+  const Inst I = I_in;
+  const Sv S = S_in;
   constexpr int BASE = 0;
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
@@ -798,7 +846,7 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
         const int pm = staged_meta<BASE>(r, I.lane, 1);
         const int br = (pm >> 16) & 3;
         if (br != 0) {
-          const double inv = 1.0 / P.delta;
+          const double inv = P.inv_delta;
           double accv = -S.radius;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -849,7 +897,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const double al = ADMM ? P.alpha : 1.0;
-  const double inv = 1.0 / P.delta;
+  const double inv = P.inv_delta;
   const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
   // controls u~ = K x + d
   double u[NA > 0 ? NA : 1];
@@ -954,7 +1002,10 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
 // commit: the lane wants the residuals of this sweep (a lane that did not ask for a check may
 // ride along in the CHECK kind when a neighbour did; its iterate update is the same arithmetic)
 template <int KIND, bool FAST>
-CMPC_FN void forward_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool on, bool commit, bool upd, int* changes) {
+CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on, bool commit, bool upd, int* changes) {
+  const Params P = P_in;
+  const Inst I = I_in;
+  Sv S = S_in;
   constexpr bool CHK = KIND == FW_ADMM_CHECK, PMMK = KIND == FW_PMM;
   const int N = P.N;
   KnotStream ks;
@@ -996,6 +1047,7 @@ CMPC_FN void forward_op(const Params& P, TileCtx& T, const Inst& I, Sv& S, bool 
     }
   }
   if (on && changes) *changes = nchg;
+  if (on) S_in = S;
 }
 
 // ---------------------------------------------------------------- rho change: keep (w, y), move v
@@ -1025,7 +1077,10 @@ CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const 
 // Friction row active iff its multiplier is positive (OSQP's rule -w < y <=> v > 0); trust-
 // region rows by the branch the prox took.  Sets *kap when some knot has trust-region rows.
 template <bool FAST>
-CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, const Sv& S, bool on, int* kap_out) {
+CMPC_FN void build_active_set_op(const Params& P_in, TileCtx& T, const Inst& I_in, const Sv& S_in, bool on, int* kap_out) {
+  const Params P = P_in;
+  const Inst I = I_in;
+  const Sv S = S_in;
   constexpr int BASE = R_META;
   const int N = P.N;
   int kap = 0;
@@ -1055,7 +1110,7 @@ CMPC_FN void build_active_set_op(const Params& P, TileCtx& T, const Inst& I, con
         const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
         const double a3[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
         double wk[3], yk4[4] = {0.0, 0.0, 0.0, 0.0};
-        const int br = prox_trust(a3, kb, S.radius, S.weight, S.rhok, wk);
+        const int br = prox_trust(a3, kb, S.radius, S.tau, wk);
         if (br != 0) {
           kap = 1;
           pm |= br << 16;
@@ -1338,6 +1393,7 @@ CMPC_HD void drv_init(const Params& P, Sv& S, Drv& D) {
   set_rho(P, P.rho0, &S.rho, &S.rhok, &S.rhoe, &S.rhoep);
   S.radius = D.radius;
   S.weight = D.weight;
+  S.tau = S.weight / S.rhok;
 }
 
 CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
@@ -1351,6 +1407,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         D.success = 0;
         S.radius = D.radius;
         S.weight = D.weight;
+        S.tau = S.weight / S.rhok;
         D.nfact = 0; D.solved = 0; D.polished = 0; D.it = 0;
         S.fail = 0;
         D.pc = PC_AFTER_FACTOR0;
@@ -1483,6 +1540,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
       case PC_AFTER_RESCALE:
         S.rho = D.rho_new;
         S.rhok = D.rhok_new;
+        S.tau = S.weight / S.rhok;
         D.pc = PC_AFTER_ADAPT_FACTOR;
         return OP_FACTOR_ADMM;
       case PC_AFTER_ADAPT_FACTOR:
