@@ -223,6 +223,8 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   h->smem_max = smem_optin;
   if (scp_smem_bytes(N) > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
   CUDA_TRY(cudaFuncSetAttribute(cmpc_scp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scp_smem_bytes(N)));
+  h->bt.B = B;
+  h->bt.plan_stride = dims->shared_plan ? 0 : 1;
   *out = h;
   return 0;
 }
