@@ -85,7 +85,7 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
   if (live) write_stats(bt, I, S, D);
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 1)
 cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31u;
