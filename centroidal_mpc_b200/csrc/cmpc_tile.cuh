@@ -651,21 +651,24 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
     }
     ks.release();
   }
-  for (int k = N - 1; k >= 0; --k) {
-    const StagedPtr r = ks.acquire();
-    if (on) {
-      double* w = rec_of(T, I, k);
-      const double* gt = gt_of(T, I, k);
-      switch (T.ns(k)) {
-        case 0: factor_knot<0, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
-        case 1: factor_knot<1, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
-        case 2: factor_knot<2, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
-        case 3: factor_knot<3, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
-        default: factor_knot<4, MODE, FAST, TS>(P, S, r, w, I.lane, gt, k, Pm, tb, on); break;
-      }
+  // runs of equal slot count: one specialisation of the knot step per inner loop, P in registers
+#define CMPC_FAC_RUN(NS_)                                                             \
+  do {                                                                                \
+    const StagedPtr r = ks.acquire();                                                 \
+    if (on) factor_knot<NS_, MODE, FAST, TS>(P, S, r, rec_of(T, I, k), I.lane, gt_of(T, I, k), k, Pm, tb, on); \
+    ks.release();                                                                     \
+    --k;                                                                              \
+  } while (k >= 0 && T.ns(k) == NS_)
+  for (int k = N - 1; k >= 0;) {
+    switch (T.ns(k)) {
+      case 0: CMPC_FAC_RUN(0); break;
+      case 1: CMPC_FAC_RUN(1); break;
+      case 2: CMPC_FAC_RUN(2); break;
+      case 3: CMPC_FAC_RUN(3); break;
+      default: CMPC_FAC_RUN(4); break;
     }
-    ks.release();
   }
+#undef CMPC_FAC_RUN
   ks.close(T);
   if (S.fail) S_in.fail = 1;
 }
@@ -780,21 +783,25 @@ CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, const
     }
     ks.release();
   }
-  for (int k = N - 1; k >= 0; --k) {
-    const StagedPtr r = ks.acquire();
-    if (on) {
-      double* w = rec_of(T, I, k);
-      const double* gt = gt_of(T, I, k);
-      switch (T.ns(k)) {
-        case 0: bwd_knot<0, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
-        case 1: bwd_knot<1, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
-        case 2: bwd_knot<2, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
-        case 3: bwd_knot<3, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
-        default: bwd_knot<4, MODE, FAST>(P, S, r, w, I.lane, gt, k, p); break;
-      }
+  // the knots are walked in runs of equal slot count, so that the inner loop is one
+  // specialisation of the knot step and the carried vector p stays in registers
+#define CMPC_BWD_RUN(NS_)                                                             \
+  do {                                                                                \
+    const StagedPtr r = ks.acquire();                                                 \
+    if (on) bwd_knot<NS_, MODE, FAST>(P, S, r, rec_of(T, I, k), I.lane, gt_of(T, I, k), k, p); \
+    ks.release();                                                                     \
+    --k;                                                                              \
+  } while (k >= 0 && T.ns(k) == NS_)
+  for (int k = N - 1; k >= 0;) {
+    switch (T.ns(k)) {
+      case 0: CMPC_BWD_RUN(0); break;
+      case 1: CMPC_BWD_RUN(1); break;
+      case 2: CMPC_BWD_RUN(2); break;
+      case 3: CMPC_BWD_RUN(3); break;
+      default: CMPC_BWD_RUN(4); break;
     }
-    ks.release();
   }
+#undef CMPC_BWD_RUN
   ks.close(T);
 }
 
@@ -1018,23 +1025,31 @@ CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
 #pragma unroll
     for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
   }
-  for (int k = 0; k <= N; ++k) {
-    const StagedPtr r = ks.acquire();
-    if (on) {
-      double* w = rec_of(T, I, k);
-      fwd_state<KIND>(P, S, R, r, w, I, k, x);
-      if (k < N) {
-        int* imw = meta_of(T, I, k);
-        const double* gt = gt_of(T, I, k);
-        switch (T.ns(k)) {
-          case 0: fwd_knot<0, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
-          case 1: fwd_knot<1, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
-          case 2: fwd_knot<2, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
-          case 3: fwd_knot<3, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
-          default: fwd_knot<4, KIND, FAST>(P, S, R, r, w, imw, I.lane, gt, x, upd, nchg); break;
-        }
-      }
+  // runs of equal slot count: one specialisation of the knot step per inner loop, x in registers
+#define CMPC_FWD_RUN(NS_)                                                             \
+  do {                                                                                \
+    const StagedPtr r = ks.acquire();                                                 \
+    if (on) {                                                                         \
+      double* w = rec_of(T, I, k);                                                    \
+      fwd_state<KIND>(P, S, R, r, w, I, k, x);                                        \
+      fwd_knot<NS_, KIND, FAST>(P, S, R, r, w, meta_of(T, I, k), I.lane, gt_of(T, I, k), x, upd, nchg); \
+    }                                                                                 \
+    ks.release();                                                                     \
+    ++k;                                                                              \
+  } while (k < N && T.ns(k) == NS_)
+  for (int k = 0; k < N;) {
+    switch (T.ns(k)) {
+      case 0: CMPC_FWD_RUN(0); break;
+      case 1: CMPC_FWD_RUN(1); break;
+      case 2: CMPC_FWD_RUN(2); break;
+      case 3: CMPC_FWD_RUN(3); break;
+      default: CMPC_FWD_RUN(4); break;
     }
+  }
+#undef CMPC_FWD_RUN
+  {   // terminal knot
+    const StagedPtr r = ks.acquire();
+    if (on) fwd_state<KIND>(P, S, R, r, rec_of(T, I, N), I, N, x);
     ks.release();
   }
   ks.close(T);
