@@ -427,28 +427,6 @@ CMPC_HD void set_rho(const Params& P, double rho, double* rho_out, double* rhok_
 CMPC_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 CMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
-// (P A)[i][c] and (A' P A)[q][c] straight from P (packed lower triangle) and the structure of A
-CMPC_HD double pa_of(const Params& P, const double* Pm, const double* S3, int i, int c) {
-  if (c < 3) {
-    const int c1 = nxt3(c), c2 = prv3(c);
-    return fma(P.dt, fma(Pm[trs(i, 6 + c1)], S3[c2], -(Pm[trs(i, 6 + c2)] * S3[c1])), Pm[trs(i, c)]);
-  }
-  if (c < 6) return fma(P.dt_m, Pm[trs(i, c - 3)], Pm[trs(i, c)]);
-  return Pm[trs(i, c)];
-}
-CMPC_HD double apa_of(const Params& P, const double* Pm, const double* S3, int q, int c) {
-  double v = pa_of(P, Pm, S3, q, c);
-  if (q < 3) {
-    const int q1 = nxt3(q), q2 = prv3(q);
-    v = fma(P.dt, fma(pa_of(P, Pm, S3, 6 + q1, c), S3[q2], -(pa_of(P, Pm, S3, 6 + q2, c) * S3[q1])), v);
-  } else if (q < 6) {
-    v = fma(P.dt_m, pa_of(P, Pm, S3, q - 3, c), v);
-  }
-  return v;
-}
-constexpr int TB_W = 231;   // scratch behind the tableau: rows 3..8 of W = P B, W[i*12 + l]  (72)
-constexpr int TB_SIZE = 231 + 72;
-
 template <int NS, int MODE, bool FAST, int TS>
 CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k,
                          double* Pm, ScratchPtr tb, bool on) {
@@ -469,14 +447,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
     if (on) CMPC_R(w, R_PC + i) = pc;
   }
   // control part of the tableau, one slot at a time:  W = P B (rows 3..8 kept), Hux = W'A, Huu = R + B'W
-#if defined(CMPC_FACTOR_V3)   // rows 3..8 of P B in the scratch, no P A temporary: nothing but P in registers
-#define CMPC_WM(i, l) sc_ld(tb, (TB_W + (i) * 12 + (l)) * TS)
-#define CMPC_WM_ST(i, l, v) sc_st(tb, (TB_W + (i) * 12 + (l)) * TS, v)
-#else
   double Wm[6][NA > 0 ? NA : 1];   // rows 3..8 of P B
-#define CMPC_WM(i, l) Wm[i][l]
-#define CMPC_WM_ST(i, l, v) Wm[i][l] = (v)
-#endif
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     const double dts = s < nsl ? P.dt : 0.0;
@@ -499,7 +470,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       for (int i = 0; i < 9; ++i)
         wc[i] = dts * fma(Pm[trs(i, 6 + a1)], ds[a2], fma(-Pm[trs(i, 6 + a2)], ds[a1], Pm[trs(i, 3 + a)]));
 #pragma unroll
-      for (int i = 0; i < 6; ++i) CMPC_WM_ST(i, j, wc[3 + i]);
+      for (int i = 0; i < 6; ++i) Wm[i][j] = wc[3 + i];
       // Hux[j][q] = (W'A)[j][q]
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -511,7 +482,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       // Huu[j][l], l <= j:  row (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
 #pragma unroll
       for (int l = 0; l <= j; ++l) {
-        double v = dts * fma(CMPC_WM(3 + a1, l), ds[a2], fma(-CMPC_WM(3 + a2, l), ds[a1], CMPC_WM(a, l)));
+        double v = dts * fma(Wm[3 + a1][l], ds[a2], fma(-Wm[3 + a2][l], ds[a1], Wm[a][l]));
         if (l >= 3 * s) {   // R block of the slot: W_u + G' diag(rr) G
           const int b2 = l - 3 * s;
           double radd = (b2 == a) ? (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) : 0.0;
@@ -532,7 +503,6 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
       pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
     }
-#if !defined(CMPC_FACTOR_V3)
     double PA[9][9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -544,20 +514,14 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
         PA[i][6 + q] = Pm[trs(i, 6 + q)];
       }
     }
-#endif
 #pragma unroll
     for (int rr2 = 0; rr2 < 9; ++rr2) {
       const int g3 = rr2 / 3, a = rr2 - 3 * g3, a1 = nxt3(a), a2 = prv3(a);
 #pragma unroll
       for (int c = 0; c <= rr2; ++c) {
-#if defined(CMPC_FACTOR_V3)
-        double v = apa_of(P, Pm, S3, rr2, c);
-        (void)g3; (void)a1; (void)a2;
-#else
         double v = PA[rr2][c];
         if (g3 == 0) v = fma(P.dt, fma(PA[6 + a1][c], S3[a2], -(PA[6 + a2][c] * S3[a1])), v);
         else if (g3 == 1) v = fma(P.dt_m, PA[a][c], v);
-#endif
         if (c == rr2) {
           v += P.Wx[rr2];
           if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
@@ -624,7 +588,7 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
   const ScratchPtr tb = T.ring_sa + (unsigned)(RING_DEPTH * (R_STAGED - R_META) * TL + I.lane) * 8u;   // behind the stream's slots
 #else
   constexpr int TS = 1;
-  double tbl[TB_SIZE];
+  double tbl[231];
   const ScratchPtr tb = tbl;
 #endif
   double Pm[45];
