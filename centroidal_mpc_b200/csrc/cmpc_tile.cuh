@@ -494,7 +494,9 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
       }
     }
   }
-  // Q + A'(PA), lower triangle
+  // Q + A'(PA), lower triangle.  This state block of the tableau (the future P_k) never goes to
+  // the scratch: it is built, swept and handed on in registers.
+  double Pn[45];
   {
     double kM[9], kl[3];
     const bool kap = MODE == MODE_PMM && S.kap && k >= 1;
@@ -527,7 +529,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
           if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
         }
         if (MODE == MODE_PMM && c >= 6 && kap) v += kM[3 * (rr2 - 6) + (c - 6)];
-        sc_st(tb, (tri(NA + rr2, NA + c)) * TS, v);
+        Pn[tri(rr2, c)] = v;
       }
     }
   }
@@ -548,7 +550,10 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
 #pragma unroll
     for (int i = 0; i < n; ++i) {
 #pragma unroll
-      for (int j = 0; j <= i; ++j) sc_st(tb, tri(i, j) * TS, fma(-bc[i], c[j], sc_ld(tb, tri(i, j) * TS)));
+      for (int j = 0; j <= i; ++j) {
+        if (j >= NA) Pn[tri(i - NA, j - NA)] = fma(-bc[i], c[j], Pn[tri(i - NA, j - NA)]);   // state block: registers
+        else sc_st(tb, tri(i, j) * TS, fma(-bc[i], c[j], sc_ld(tb, tri(i, j) * TS)));
+      }
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) {
@@ -567,7 +572,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lan
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
 #pragma unroll
-    for (int j = 0; j <= i; ++j) Pm[tri(i, j)] = sc_ld(tb, (tri(NA + i, NA + j)) * TS);
+    for (int j = 0; j <= i; ++j) Pm[tri(i, j)] = Pn[tri(i, j)];
   }
 }
 
