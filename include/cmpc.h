@@ -61,12 +61,14 @@ typedef struct {
   double sigma;                  /* accepted for OSQP compatibility, unused: W_x, W_u > 0 make the
                                     x-update strictly convex without a proximal term */
   double alpha, rho, delta, adaptive_rho_tolerance;
-  int32_t max_iter, check_termination, polish, polish_refine_iter, adaptive_rho;
+  int32_t max_iter, check_termination /* default 25 as in OSQP; every polish attempt checks too */, polish,
+      polish_refine_iter, adaptive_rho;
   int32_t adaptive_rho_start;    /* first ADMM iteration at which rho may be adapted */
   int32_t polish_active_set_rounds; /* extra polish rounds with a corrected active set (0 = OSQP) */
   int32_t active_set_start;      /* ADMM iteration of the first early polish (0 = only after termination) */
   int32_t active_set_step;       /* ADMM iterations between early polishes */
-  double active_set_tol;         /* certificate: primal residual / row-violation tolerance */
+  double active_set_tol;         /* certificate: primal residual / row violation <= tol * (1 + norm), the form of
+                                    OSQP's test (default 1e-9: 100x tighter than the reference's eps = 1e-7) */
 } cmpc_qp_settings;
 
 /* status[] values */
