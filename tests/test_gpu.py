@@ -213,3 +213,20 @@ def test_shipped_horizon_on_device(gpu):
         np.testing.assert_array_equal(out["qp_iters"], emu["qp_iters"])
         for b in range(B):
             assert relerr(out["X"][b], emu["X"][b]) < 1e-7 and relerr(out["U"][b], emu["U"][b]) < 1e-7
+
+
+def test_bitwise_equal_to_host_build(gpu):
+    """The GPU and the host build of the same source agree BIT FOR BIT (FMA contraction is explicit
+    in both, no lane depends on its neighbours): 512 instances of the headline workload.
+    scripts/full_batch_check.py does the same for all 4096."""
+    import emu_binding as E
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.src.scp_solver import solve_scp_batched
+    conf = synthetic.load_conf("solo12_trot", N=100)
+    batch = synthetic.make_batch(conf, 512, first=1024)
+    out = solve_scp_batched(batch, conf.scp_params, return_stats=True)
+    emu = E.solve_scp(batch, conf.scp_params)
+    for k in ("status", "scp_iters", "n_accepted", "qp_iters", "n_factor"):
+        np.testing.assert_array_equal(out[k], emu[k])
+    np.testing.assert_array_equal(out["X"], emu["X"])
+    np.testing.assert_array_equal(out["U"], emu["U"])
