@@ -179,3 +179,17 @@ def test_random_problem_parameters_match_oracle(seed):
     assert out["status"][0] == 0
     assert out["scp_iters"][0] == ref["iterations"] and out["n_accepted"][0] == len(ref["state"])
     assert relerr(out["X"][0].T, ref["state"][-1]) < TOL and relerr(out["U"][0].T, ref["control"][-1]) < TOL
+
+
+def test_headline_horizon_matches_oracle():
+    """The benchmark's horizon (N = 100) on the host build: 12 instances against the oracle."""
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    conf = synthetic.load_conf("solo12_trot", N=100)
+    ids = [0, 1, 7, 38, 500, 1000, 1500, 2000, 2500, 3000, 3500, 4095]   # 7 and 38 need four polish rounds
+    models = [Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b)) for b in ids]
+    out = E.solve_scp(ProblemBatch(models), conf.scp_params)
+    for j, m in enumerate(models):
+        ref = scp.solve_scp(m.problem_arrays(), conf.scp_params)
+        assert ref is not False and out["status"][j] == 0
+        assert out["scp_iters"][j] == ref["iterations"]
+        assert relerr(out["X"][j].T, ref["state"][-1]) < TOL and relerr(out["U"][j].T, ref["control"][-1]) < TOL

@@ -230,3 +230,23 @@ def test_bitwise_equal_to_host_build(gpu):
         np.testing.assert_array_equal(out[k], emu[k])
     np.testing.assert_array_equal(out["X"], emu["X"])
     np.testing.assert_array_equal(out["U"], emu["U"])
+
+
+def test_headline_size_oracle_parity(gpu):
+    """48 instances of the headline workload (solo12 trot, N = 100, instance ids spread over the
+    4096 of the benchmark batch) against the oracle: equal SCP iteration counts, 1e-6 norm-wise."""
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    from centroidal_mpc_b200.src.scp_solver import solve_scp_batched
+    from oracle import scp
+    conf = synthetic.load_conf("solo12_trot", N=100)
+    ids = [int(i) for i in np.linspace(0, 4095, 48)]
+    models = [Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b)) for b in ids]
+    out = solve_scp_batched(models, conf.scp_params)
+    worst = 0.0
+    for j, m in enumerate(models):
+        ref = scp.solve_scp(m.problem_arrays(), conf.scp_params)
+        assert ref is not False and out["status"][j] == 0
+        assert out["scp_iters"][j] == ref["iterations"] and out["n_accepted"][j] == len(ref["state"])
+        worst = max(worst, relerr(out["X"][j].T, ref["state"][-1]), relerr(out["U"][j].T, ref["control"][-1]))
+    assert worst < TOL, worst
