@@ -125,9 +125,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken in [t0, t1] (host clock); when the
+        timed region is shorter than the sampling period, the samples next to it."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -137,7 +139,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.05)]
+        if not rows and self.rows and t0 is not None:
+            near = sorted(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[:3]
+            rows = [r for _, r in near]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -232,14 +238,15 @@ def run_gpu_arm(args):
         if world > 1:   # the single end-of-batch collective
             parallel.gather_solutions(dict(X=solver.X, U=solver.U, ints=solver.ints[:3]), B * world, dist, dst=0)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                    # nvidia-smi needs ~100 ms to deliver its first sample
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     launches0 = lib.cmpc_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_host0 = time.time()
     t_all0 = torch.cuda.Event(enable_timing=True)
     t_all1 = torch.cuda.Event(enable_timing=True)
     t_all0.record()
@@ -249,7 +256,7 @@ def run_gpu_arm(args):
         e1.record()
     t_all1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_host0, time.time())
     launches = lib.cmpc_launch_count() - launches0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     total_ms = t_all0.elapsed_time(t_all1)
