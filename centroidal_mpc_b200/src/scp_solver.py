@@ -63,12 +63,45 @@ def get_QP_solution(model, z):
 
 
 def interpolate_SCP_solution(solution):
-    """Linear x10 up-sampling of the last accepted (X, U) (scp_solver.py:95-111), vectorised."""
+    """Linear x10 up-sampling of the last accepted (X, U) (scp_solver.py:95-111), vectorised with
+    the reference's arithmetic (``M[:, i] + j * ((M[:, i+1] - M[:, i]) / 10)``) so the result is
+    bit-identical to its double loop."""
     N_inner = 10
     X, U = solution["state"][-1], solution["control"][-1]
-    frac = np.arange(N_inner) / float(N_inner)
+    j = np.arange(N_inner, dtype=float)
 
     def up(M):
-        seg = M[:, :-1, None] + (M[:, 1:, None] - M[:, :-1, None]) * frac[None, None, :]
+        d = (M[:, 1:] - M[:, :-1]) / float(N_inner)
+        seg = M[:, :-1, None] + j[None, None, :] * d[:, :, None]
         return seg.reshape(M.shape[0], -1)
     return dict(X=up(X), U=up(U))
+
+
+# File names and keys of the hand-off between the reference's pipeline stages
+# (build/lib/demos/run_motion.py:30,41-43; read back by src/whole_body_control.py:41-44 and
+# src/centroidal_model.py:87,174).
+WHOLEBODY_TO_CENTROIDAL = "wholeBody_to_centroidal_traj.npz"   # X [N+1, 9]: DDP -> SCP warm start
+CENTROIDAL_TO_WHOLEBODY = "centroidal_to_wholeBody_traj.npz"   # X (9, N+1), U (n_u, N): SCP -> DDP
+SCP_INTERPOLATED = "scp_sol_interpol_nom.npz"                  # X (9, 10 N), U (n_u, 10 (N-1))
+
+
+def save_scp_handoff(solution, directory="."):
+    """Write the two files the reference's whole-body stage consumes after ``solve_scp``
+    (run_motion.py:41-43): the x10 interpolated solution and the last accepted (X, U), with the
+    reference's file names, keys and array layouts.  Returns the two paths."""
+    import os
+    if solution is False or not solution["state"]:
+        raise ValueError("no accepted SCP iterate to hand off")
+    ip = interpolate_SCP_solution(solution)
+    p1 = os.path.join(directory, SCP_INTERPOLATED)
+    p2 = os.path.join(directory, CENTROIDAL_TO_WHOLEBODY)
+    np.savez(p1, X=ip["X"], U=ip["U"])
+    np.savez(p2, X=solution["state"][-1], U=solution["control"][-1])
+    return p1, p2
+
+
+def load_scp_handoff(directory="."):
+    """Read ``centroidal_to_wholeBody_traj.npz`` the way whole_body_control.py:41-44 does."""
+    import os
+    f = np.load(os.path.join(directory, CENTROIDAL_TO_WHOLEBODY))
+    return f["X"], f["U"]

@@ -92,8 +92,30 @@ def test_interpolation_matches_naive_loops():
             for j in range(10):
                 R[:, i * 10 + j] = M[:, i] + j * d
         return R
-    np.testing.assert_allclose(out["X"], naive(X), atol=1e-15)
-    np.testing.assert_allclose(out["U"], naive(U), atol=1e-15)
+    np.testing.assert_array_equal(out["X"], naive(X))     # same arithmetic as the reference's loops
+    np.testing.assert_array_equal(out["U"], naive(U))
+
+
+def test_npz_handoff_files_have_the_reference_names_keys_and_layouts(tmp_path):
+    from centroidal_mpc_b200.src.scp_solver import load_scp_handoff, save_scp_handoff
+    rng = np.random.default_rng(4)
+    N = 7
+    X, U = rng.normal(size=(9, N + 1)), rng.normal(size=(12, N))
+    sol = dict(state=[X * 0, X], control=[U * 0, U], gains=[None, None], covs=[None, None])
+    p1, p2 = save_scp_handoff(sol, tmp_path)
+    assert p1.endswith("scp_sol_interpol_nom.npz") and p2.endswith("centroidal_to_wholeBody_traj.npz")
+    f1, f2 = np.load(p1), np.load(p2)
+    assert sorted(f1.files) == ["U", "X"] and sorted(f2.files) == ["U", "X"]
+    assert f1["X"].shape == (9, 10 * N) and f1["U"].shape == (12, 10 * (N - 1))
+    np.testing.assert_array_equal(f2["X"], X)             # the LAST accepted iterate
+    np.testing.assert_array_equal(f2["U"], U)
+    Xr, Ur = load_scp_handoff(tmp_path)
+    np.testing.assert_array_equal(Xr, X)
+    np.testing.assert_array_equal(Ur, U)
+    with pytest.raises(ValueError):
+        save_scp_handoff(dict(state=[], control=[]), tmp_path)
+    with pytest.raises(ValueError):
+        save_scp_handoff(False, tmp_path)
 
 
 def test_get_qp_solution_layout():
