@@ -36,9 +36,17 @@ class cmpc_qp_settings(C.Structure):
                 ("active_set_tol", C.c_double)]
 
 
+class cmpc_lqr_weights(C.Structure):
+    _fields_ = [("Q", C.c_double * 81), ("R", C.c_double * 144), ("cov_w", C.c_double * 144),
+                ("cov_eta", C.c_double * 81)]
+
+
+LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
+
+
 EXPORTS = ["cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
            "cmpc_set_problem", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
-           "cmpc_linearize", "cmpc_rollout", "cmpc_fp64_peak", "cmpc_launch_count",
+           "cmpc_linearize", "cmpc_rollout", "cmpc_lqr_covs", "cmpc_fp64_peak", "cmpc_launch_count",
            "cmpc_last_error", "cmpc_version"]
 
 _lib = None
@@ -63,6 +71,21 @@ def make_model_struct(prob):
     for i in range(12):
         m.control_cost_weights[i] = wu[i] if i < len(wu) else 1.0
     return m
+
+
+def make_lqr_struct(Q, R, cov_w, cov_eta, nu):
+    """conf.Q, conf.R, conf.cov_w, conf.cov_white_noise -> cmpc_lqr_weights (dense, row-major)."""
+    import numpy as np
+    w = cmpc_lqr_weights()
+    for name, a, n in (("Q", Q, 9), ("R", R, nu), ("cov_w", cov_w, nu), ("cov_eta", cov_eta, 9)):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if a.shape != (n, n):
+            raise CmpcError("%s must be %d x %d, got %r" % (name, n, n, a.shape))
+        dst = getattr(w, name)
+        flat = a.ravel()
+        for i in range(n * n):
+            dst[i] = flat[i]
+    return w
 
 
 def make_scp_struct(scp_params):
@@ -120,6 +143,8 @@ def load():
     lib.cmpc_get_stats.argtypes = [C.c_void_p, ip, ip, dp]
     lib.cmpc_linearize.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, dp, dp, vp]
     lib.cmpc_rollout.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, vp]
+    lib.cmpc_lqr_covs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.POINTER(cmpc_lqr_weights),
+                                  dp, dp, dp, ip, dp, dp, vp, vp]
     lib.cmpc_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.cmpc_launch_count.restype = C.c_int64
     lib.cmpc_last_error.restype = C.c_char_p

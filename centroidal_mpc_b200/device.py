@@ -140,11 +140,53 @@ def _lin_call(model, X, U, want_jac):
     return f[0].cpu().numpy()
 
 
+def lqr_gains_covs_batched(batch, X, U, Q, R, cov_w, cov_eta, want_covs=True):
+    """cmpc_lqr_covs for a ProblemBatch along the trajectories X [B,N+1,9], U [B,N,nu] (numpy or
+    CUDA tensors): gains [B,N,nu,9] and covs [B,N+1,9,9] as CUDA tensors
+    (centroidal_model.py:215-227,233-238,284-285 of the reference)."""
+    torch = _torch_cuda()
+    lib = L.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, N, nc, nu = batch.B, batch.N, batch.nc, batch.nu
+    if batch.proto["robot"] == "TALOS":
+        raise NotImplementedError("TALOS contact model: SURVEY.md section 8 row f4 (next)")
+
+    def dv(a, dt):
+        t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=dev, dtype=dt).contiguous()
+    Xd, Ud = dv(X, torch.float64), dv(U, torch.float64)
+    if tuple(Xd.shape) != (B, N + 1, 9) or tuple(Ud.shape) != (B, N, nu):
+        raise L.CmpcError("X must be [B,N+1,9] and U [B,N,nu]")
+    cp, ca = dv(batch.contact_pos, torch.float64), dv(batch.contact_active, torch.int32)
+    dims = L.cmpc_dims(B, N, nc, 1 if batch.shared_plan else 0)
+    mdl = L.make_model_struct(batch.proto)
+    w = L.make_lqr_struct(Q, R, cov_w, cov_eta, nu)
+    gains = torch.empty((B, N, nu, 9), dtype=torch.float64, device=dev)
+    covs = torch.empty((B, N + 1, 9, 9), dtype=torch.float64, device=dev) if want_covs else None
+    scratch = torch.empty(L.LQR_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    L.check(lib.cmpc_lqr_covs(C.byref(dims), C.byref(mdl), C.byref(w), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca),
+                              _ptr(gains), _ptr(covs), _ptr(scratch), C.c_void_p(st.cuda_stream)), lib)
+    st.synchronize()   # `w` (host) and `scratch` must outlive the asynchronous copy
+    return gains, covs
+
+
+def lqr_gains_covs(model, traj_tuple):
+    """LQR_gains (N,nu,9) and Covs (N+1,9,9) of one model along traj_tuple, as numpy arrays."""
+    X = np.asarray(traj_tuple["state"], dtype=np.float64).T[None]
+    U = np.asarray(traj_tuple["control"], dtype=np.float64).T[None]
+    g, c = lqr_gains_covs_batched(ProblemBatch([model]), X, U, model._Q, model._R, model._Cov_w, model._Cov_eta)
+    return g[0].cpu().numpy(), c[0].cpu().numpy()
+
+
 def compute_trajectory_data(model, traj_tuple):
-    """dict(dynamics (9,N), gradients{f_x (N,9,9), f_u (N,9,nu)}) like the reference's
-    compute_trajectory_data; LQR gains / covariances are SURVEY.md section 8 row f1 (next)."""
+    """dict(dynamics (9,N), gradients{f_x (N,9,9), f_u (N,9,nu)}, LQR_gains (N,nu,9),
+    Covs (N+1,9,9)) like the reference's compute_trajectory_data (centroidal_model.py:257-291);
+    the covariance-gradient tensors, identically zero in the reference,
+    are not produced."""
     f, fx, fu = _lin_call(model, traj_tuple["state"], traj_tuple["control"], True)
-    return dict(dynamics=f.T.copy(), gradients={"f_x": fx, "f_u": fu}, LQR_gains=None, Covs=None)
+    gains, covs = lqr_gains_covs(model, traj_tuple)
+    return dict(dynamics=f.T.copy(), gradients={"f_x": fx, "f_u": fu}, LQR_gains=gains, Covs=covs)
 
 
 def integrate_dynamics_trajectory(model, traj_tuple):

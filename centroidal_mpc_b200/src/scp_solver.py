@@ -44,13 +44,19 @@ def solve_scp(model, scp_params):
         warn("[solve_OSQP]: Problem unfeasible.")
         return False
     all_solution = dict(state=[], control=[], gains=[], covs=[])
+    gains = covs = None
+    if int(out["n_accepted"][0]) > 0:
+        # traj_data is computed once, at the warm start (scp_solver.py:129-130), so every accepted
+        # iterate carries the same LQR_gains / Covs (scp_solver.py:165-166)
+        from ..device import lqr_gains_covs
+        gains, covs = lqr_gains_covs(model, model._init_trajectories)
     # the linearisation point never moves (scp_solver.py:129-130), so every accepted iterate
     # solves the same QP; the last accepted one is what the kernel returns
     for _ in range(int(out["n_accepted"][0])):
         all_solution["state"].append(out["X"][0].T.copy())
         all_solution["control"].append(out["U"][0].T.copy())
-        all_solution["gains"].append(None)     # LQR gains / covariances: SURVEY.md section 8 f1 (next)
-        all_solution["covs"].append(None)
+        all_solution["gains"].append(gains)
+        all_solution["covs"].append(covs)
     return all_solution
 
 

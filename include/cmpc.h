@@ -122,6 +122,23 @@ int cmpc_linearize(const cmpc_dims* dims, const cmpc_model* model, const double*
 int cmpc_rollout(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,
                  const double* contact_pos, const int32_t* contact_active, double* f, void* stream);
 
+/* conf.Q, conf.R, conf.cov_w, conf.cov_white_noise (src/centroidal_model.py:34-35,41-42): dense,
+ * row-major; R and cov_w are nu x nu with leading dimension nu (the first nu*nu entries are read). */
+typedef struct {
+  double Q[81], R[144], cov_w[144], cov_eta[81];
+} cmpc_lqr_weights;
+#define CMPC_LQR_SCRATCH_BYTES 4096
+
+/* LQR feedback gains and state covariances along (X,U): the `LQR_gains` and `Covs` entries of
+ * compute_trajectory_data (src/centroidal_model.py:215-227,233-238,284-285) that solve_scp hands
+ * back as all_solution['gains'] / ['covs'] (src/scp_solver.py:165-166).
+ * gains [B][N][nu][9]; covs [B][N+1][9][9] with covs[b][0] = 0 (nullable: gains only).
+ * `w` is a HOST pointer; `scratch` is CMPC_LQR_SCRATCH_BYTES of caller-owned DEVICE memory.
+ * A knot whose R + B'PB is not positive definite gets NaN gains. */
+int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X,
+                  const double* U, const double* contact_pos, const int32_t* contact_active, double* gains,
+                  double* covs, void* scratch, void* stream);
+
 /* DFMA micro-benchmark on the current device: achieved FP64 TFLOP/s and the SM clock (MHz) seen. */
 int cmpc_fp64_peak(double* tflops, double* ms);
 

@@ -112,3 +112,35 @@ def trajectory_data(X, U, prob, emulate_jax_fp32=False):
     if emulate_jax_fp32:
         F, Ax, Bu, Cw = [v.astype(np.float32).astype(np.float64) for v in (F, Ax, Bu, Cw)]
     return dict(dynamics=F, f_x=Ax, f_u=Bu, f_w=Cw)
+
+
+def lqr_feedback_gain(A, B, Q, R, niter=2):
+    """compute_lqr_feedback_gains, centroidal_model.py:215-227: P = Q, `niter` Riccati steps,
+    K = -(R + B'PB)^-1 B'PA."""
+    P = Q
+    for _ in range(niter):
+        AtP = A.T @ P
+        AtPB = AtP @ B
+        P = (Q + AtP @ A) - AtPB @ np.linalg.solve(R + B.T @ P @ B, AtPB.T)
+    return -np.linalg.solve(R + B.T @ P @ B, B.T @ P @ A)
+
+
+def lqr_gains_covs(X, U, prob, Q, R, cov_w, cov_eta):
+    """LQR_gains (N,nu,9) and Covs (N+1,9,9) of compute_trajectory_data
+    (centroidal_model.py:233-238,284-285): Covs[0] = 0,
+    Covs[k+1] = [A B] [[S, SK'],[KS, KSK']] [A B]' + C cov_w C' + cov_eta."""
+    N = U.shape[1]
+    nu = U.shape[0]
+    gains = np.zeros((N, nu, 9))
+    covs = np.zeros((N + 1, 9, 9))
+    for k in range(N):
+        A, B, C = jacobians(X[:, k], U[:, k], prob["contact_pos"][k], prob["contact_active"][k],
+                            prob["contact_R"][k], prob["m"], prob["g"], prob["dt"], prob["robot"])
+        K = lqr_feedback_gain(A, B, Q, R)
+        S = covs[k]
+        SKt = S @ K.T
+        AB = np.hstack([A, B])
+        Sxu = np.vstack([np.hstack([S, SKt]), np.hstack([SKt.T, K @ SKt])])
+        gains[k] = K
+        covs[k + 1] = AB @ Sxu @ AB.T + C @ cov_w @ C.T + cov_eta
+    return gains, covs

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "emu", "cmpc_emu.cpp")
 _SO = os.path.join(_HERE, "emu", "libcmpc_emu.so")
 _DEPS = [os.path.join(_HERE, "..", "centroidal_mpc_b200", "csrc", f)
-         for f in ("cmpc_core.cuh", "cmpc_tile.cuh", "cmpc_params.h")] + [_SRC]
+         for f in ("cmpc_core.cuh", "cmpc_tile.cuh", "cmpc_lqr.cuh", "cmpc_params.h")] + [_SRC]
 _lib = None
 
 
@@ -54,3 +54,20 @@ def solve_scp(batch, scp_params, qp_overrides=None):
     if rc != 0:
         raise RuntimeError("cmpc_emu_solve_scp returned %d" % rc)
     return out
+
+
+def lqr_covs(batch, X, U, Q, R, cov_w, cov_eta):
+    """Host build of csrc/cmpc_lqr.cuh: gains [B,N,nu,9], covs [B,N+1,9,9]."""
+    lib = load()
+    B, N, nu = batch.B, batch.N, batch.nu
+    dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0)
+    model = L.make_model_struct(batch.proto)
+    w = L.make_lqr_struct(Q, R, cov_w, cov_eta, nu)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    gains, covs = np.zeros((B, N, nu, 9)), np.zeros((B, N + 1, 9, 9))
+    rc = lib.cmpc_emu_lqr_covs(C.byref(dims), C.byref(model), C.byref(w), _p(X), _p(U), _p(batch.contact_pos),
+                               _p(batch.contact_active), _p(gains), _p(covs))
+    if rc != 0:
+        raise RuntimeError("cmpc_emu_lqr_covs returned %d" % rc)
+    return gains, covs

@@ -193,3 +193,49 @@ def test_headline_horizon_matches_oracle():
         assert ref is not False and out["status"][j] == 0
         assert out["scp_iters"][j] == ref["iterations"]
         assert relerr(out["X"][j].T, ref["state"][-1]) < TOL and relerr(out["U"][j].T, ref["control"][-1]) < TOL
+
+
+# ---- LQR gains / covariance propagation (csrc/cmpc_lqr.cuh) ----
+def lqr_case(conf, models, seed=0):
+    """Perturbed nominal trajectories of a few models: X [B,N+1,9], U [B,N,nu]."""
+    rng = np.random.default_rng(seed)
+    X = np.stack([m._init_trajectories["state"].T for m in models])
+    U = np.stack([m._init_trajectories["control"].T for m in models])
+    return X + 0.01 * rng.normal(size=X.shape), U + 0.5 * rng.normal(size=U.shape) * (U != 0)
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
+def test_lqr_gains_and_covs_match_oracle(cases, name):
+    from oracle import dynamics
+    conf, models = cases[name]
+    m0 = models[0]
+    X, U = lqr_case(conf, models)
+    gains, covs = E.lqr_covs(ProblemBatch(models), X, U, m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+    for b, m in enumerate(models):
+        g, c = dynamics.lqr_gains_covs(X[b].T, U[b].T, m.problem_arrays(), m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+        assert relerr(gains[b], g) < 1e-12 and relerr(covs[b], c) < 1e-12
+        # inactive contacts: zero feedback rows (B columns are zero); Covs symmetric PSD, Covs[0] = 0
+        act = np.repeat(m.problem_arrays()["contact_active"].astype(bool), 3, axis=1)
+        assert np.all(gains[b][~act] == 0.0)
+        assert np.all(covs[b][0] == 0.0)
+        assert np.abs(covs[b] - covs[b].transpose(0, 2, 1)).max() < 1e-12
+        assert np.linalg.eigvalsh(covs[b][-1]).min() > 0.0
+
+
+def test_lqr_gain_is_the_two_step_riccati_minimiser(cases):
+    """K of a knot minimises u'Ru + (Ax+Bu)'P(Ax+Bu) with P the twice-iterated Riccati matrix:
+    (R + B'PB) K + B'PA = 0, checked from the definition with dense numpy algebra."""
+    from oracle import dynamics
+    conf, models = cases["solo12_trot"]
+    m0 = models[0]
+    X, U = lqr_case(conf, models[:1], seed=3)
+    gains, _ = E.lqr_covs(ProblemBatch(models[:1]), X, U, m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+    prob = m0.problem_arrays()
+    for k in (0, 7, conf.N - 1):
+        A, B, _ = dynamics.jacobians(X[0, k], U[0, k], prob["contact_pos"][k], prob["contact_active"][k],
+                                     prob["contact_R"][k], prob["m"], prob["g"], prob["dt"], prob["robot"])
+        P = m0._Q
+        for _ in range(2):
+            P = m0._Q + A.T @ P @ A - A.T @ P @ B @ np.linalg.solve(m0._R + B.T @ P @ B, B.T @ P @ A)
+        res = (m0._R + B.T @ P @ B) @ gains[0, k] + B.T @ P @ A
+        assert np.abs(res).max() < 1e-9 * np.abs(B.T @ P @ A).max()

@@ -128,6 +128,13 @@ def test_drop_in_solve_scp(gpu, cases):
     sol = solve_scp(models[0], conf.scp_params)
     assert set(sol) == {"state", "control", "gains", "covs"} and len(sol["state"]) == 1
     assert sol["state"][-1].shape == (9, conf.N + 1) and sol["control"][-1].shape == (12, conf.N)
+    # gains / covs along the warm start (scp_solver.py:165-166), against the oracle
+    from oracle import dynamics
+    m = models[0]
+    g, c = dynamics.lqr_gains_covs(m._init_trajectories["state"], m._init_trajectories["control"],
+                                   m.problem_arrays(), m._Q, m._R, m._Cov_w, m._Cov_eta)
+    assert sol["gains"][-1].shape == (conf.N, 12, 9) and sol["covs"][-1].shape == (conf.N + 1, 9, 9)
+    assert relerr(sol["gains"][-1], g) < 1e-12 and relerr(sol["covs"][-1], c) < 1e-12
     ip = interpolate_SCP_solution(sol)
     assert ip["X"].shape == (9, conf.N * 10) and ip["U"].shape == (12, (conf.N - 1) * 10)
     empty = solve_scp(models[0], dict(conf.scp_params, trust_region_radius0=1.0, max_iterations=2))
@@ -250,3 +257,54 @@ def test_headline_size_oracle_parity(gpu):
         assert out["scp_iters"][j] == ref["iterations"] and out["n_accepted"][j] == len(ref["state"])
         worst = max(worst, relerr(out["X"][j].T, ref["state"][-1]), relerr(out["U"][j].T, ref["control"][-1]))
     assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
+def test_lqr_gains_and_covs_through_cabi(gpu, cases, name):
+    """cmpc_lqr_covs against the oracle (1e-12 relative) and bitwise against the host build of
+    csrc/cmpc_lqr.cuh; unshared plans, perturbed trajectories."""
+    import emu_binding as E
+    from centroidal_mpc_b200.batch import ProblemBatch
+    from centroidal_mpc_b200.device import lqr_gains_covs_batched
+    from oracle import dynamics
+    from test_emu_parity import lqr_case
+    conf, models = cases[name]
+    m0 = models[0]
+    X, U = lqr_case(conf, models)
+    batch = ProblemBatch(models)
+    w = (m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+    gains, covs = lqr_gains_covs_batched(batch, X, U, *w)
+    gains, covs = gains.cpu().numpy(), covs.cpu().numpy()
+    ge, ce = E.lqr_covs(batch, X, U, *w)
+    assert np.array_equal(gains, ge) and np.array_equal(covs, ce)
+    for b, m in enumerate(models):
+        g, c = dynamics.lqr_gains_covs(X[b].T, U[b].T, m.problem_arrays(), *w)
+        assert relerr(gains[b], g) < 1e-12 and relerr(covs[b], c) < 1e-12
+    td = m0.compute_trajectory_data(dict(state=X[0].T, control=U[0].T))
+    assert np.array_equal(td["LQR_gains"], gains[0]) and np.array_equal(td["Covs"], covs[0])
+
+
+def test_lqr_covs_full_batch_properties(gpu):
+    """Headline shape (4096 x N=100): every instance's covariances are symmetric and grow from 0;
+    gains of inactive contacts are exactly zero; a sample of instances against the oracle."""
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.device import lqr_gains_covs_batched
+    from oracle import dynamics
+    conf = synthetic.load_conf("solo12_trot", N=100)
+    batch = synthetic.make_batch(conf, 4096)
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    m0 = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 0))
+    w = (m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+    gains, covs = lqr_gains_covs_batched(batch, batch.X_ref, batch.U_init, *w)
+    assert bool(gains.isfinite().all()) and bool(covs.isfinite().all())
+    assert float((covs - covs.transpose(2, 3)).abs().max()) < 1e-12
+    assert float(covs[:, 0].abs().max()) == 0.0
+    tr = covs.diagonal(dim1=2, dim2=3).sum(-1)
+    assert bool((tr[:, 1:] > 0).all())
+    act = np.repeat(batch.contact_active.astype(bool), 3, axis=-1)
+    act = np.broadcast_to(act, (4096,) + act.shape[1:]) if act.shape[0] == 1 else act
+    assert float(gains.cpu().numpy()[~act].__abs__().max()) == 0.0
+    for b in (0, 4095):
+        m = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b))
+        g, c = dynamics.lqr_gains_covs(batch.X_ref[b].T, batch.U_init[b].T, m.problem_arrays(), *w)
+        assert relerr(gains[b].cpu().numpy(), g) < 1e-12 and relerr(covs[b].cpu().numpy(), c) < 1e-12
