@@ -46,7 +46,7 @@ LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
 
 EXPORTS = ["cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
            "cmpc_set_problem", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
-           "cmpc_linearize", "cmpc_rollout", "cmpc_lqr_covs", "cmpc_fp64_peak", "cmpc_launch_count",
+           "cmpc_linearize", "cmpc_rollout", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
            "cmpc_last_error", "cmpc_version"]
 
 _lib = None
@@ -145,6 +145,8 @@ def load():
     lib.cmpc_rollout.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, vp]
     lib.cmpc_lqr_covs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.POINTER(cmpc_lqr_weights),
                                   dp, dp, dp, ip, dp, dp, vp, vp]
+    lib.cmpc_friction_backoffs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.c_double,
+                                           dp, dp, dp, ip, dp, vp]
     lib.cmpc_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.cmpc_launch_count.restype = C.c_int64
     lib.cmpc_last_error.restype = C.c_char_p

@@ -192,6 +192,22 @@ __global__ void cmpc_covs_kernel(const __grid_constant__ Params prm, const LqrWe
   }
 }
 
+// friction-row upper bounds in stochastic mode (one thread per instance and knot): ub [B][N][nc][4]
+__global__ void cmpc_backoff_kernel(const __grid_constant__ Params prm, double xi, int B, int shared_plan,
+                                    const double* __restrict__ gains, const double* __restrict__ covs,
+                                    const double* __restrict__ cR, const int* __restrict__ cact,
+                                    double* __restrict__ ub) {
+  const int N = prm.N, nu = prm.nu, nc = prm.nc;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * N) return;
+  int b = (int)(t / N), k = (int)(t % N);
+  const long plan = shared_plan ? 0 : b;
+  double o[4 * MAXC];
+  friction_backoff_knot(prm, xi, k, gains + t * nu * 9, covs + ((long)b * (N + 1) + k) * 81,
+                        cR ? cR + (plan * N + k) * nc * 9 : nullptr, cact + (plan * N + k) * nc, o);
+  for (int i = 0; i < 4 * nc; ++i) ub[t * 4 * nc + i] = o[i];
+}
+
 // DFMA micro-benchmark: 8 independent FMA chains per thread
 __global__ void cmpc_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -433,6 +449,21 @@ int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
   }
+  return 0;
+}
+
+int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, double xi, const double* gains,
+                           const double* covs, const double* contact_R, const int32_t* contact_active,
+                           double* friction_ub, void* stream) {
+  if (!dims || !model || !gains || !covs || !contact_active || !friction_ub) return fail(-1, "null argument");
+  Params prm;
+  int rc = fill_params(&prm, dims, model, nullptr, nullptr, contact_R == nullptr);
+  if (rc) return fail(rc, "bad dims or weights");
+  long total = (long)dims->batch * dims->N;
+  cmpc_backoff_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      prm, xi, dims->batch, dims->shared_plan, gains, covs, contact_R, (const int*)contact_active, friction_ub);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -8,6 +8,7 @@
 //   src/centroidal_model.py:234-238   Sigma_next = [A B] Sigma_xu [A B]' + C Cov_w C' + Cov_eta,
 //                                     Sigma_xu = [[S, SK'],[KS, KSK']]  ==  (A+BK) S (A+BK)'
 //   src/centroidal_model.py:284-285   LQR_gains[k] = K, Covs[k+1] = Sigma_next (Covs[0] = 0)
+//   src/constraints.py:157-163,187-214 chance-constraint back-offs of the friction rows (stochastic mode)
 #pragma once
 #include "cmpc_core.cuh"
 
@@ -170,6 +171,40 @@ CMPC_HD void cov_step_knot(const double* A, const double* Bm, const double* Ct, 
       for (int l = 0; l < nu; ++l) s = fma(CW[i * nu + l], Ct[j * nu + l], s);
       Sn[(6 + i) * 9 + 6 + j] += s;
     }
+}
+
+// Friction-row upper bounds of one knot in stochastic mode (constraints.py:187-214 with the
+// identically-zero covariance-gradient terms dropped):
+//   ub[c][j] = - sum_u xi 2 G_ju sqrt((K_c Sigma_k K_c')_uu)   over G_ju > 1e-6, sqrt(.) > 1e-6,
+// G = pyramid R_c' (utils.py:9-16), K_c = rows 3c..3c+2 of K_k; zero at k = 0 and for inactive contacts.
+CMPC_HD void friction_backoff_knot(const Params& P, double xi, int k, const double* K, const double* Sg,
+                                   const double* cR, const int* cact, double* ub) {
+  for (int c = 0; c < P.nc; ++c) {
+    for (int j = 0; j < 4; ++j) ub[4 * c + j] = 0.0;
+    if (k == 0 || !cact[c]) continue;
+    double sq[3];
+    for (int u = 0; u < 3; ++u) {
+      const double* Ku = K + (3 * c + u) * 9;
+      double q = 0.0;
+      for (int i = 0; i < 9; ++i) {
+        double t = 0.0;
+        for (int l = 0; l < 9; ++l) t = fma(Ku[l], Sg[l * 9 + i], t);
+        q = fma(t, Ku[i], q);
+      }
+      sq[u] = sqrt(q);
+    }
+    for (int j = 0; j < 4; ++j) {
+      // pyramid row j: (+-1, 0, -kf) for j < 2, (0, +-1, -kf) for j >= 2
+      const double sgn = (j & 1) ? -1.0 : 1.0;
+      const int ax = j >> 1;
+      for (int u = 0; u < 3; ++u) {
+        double G;
+        if (cR) G = sgn * cR[9 * c + 3 * u + ax] - P.kf * cR[9 * c + 3 * u + 2];   // (pyr R')_ju = sum_a pyr_ja R_ua
+        else G = (u == ax ? sgn : 0.0) - (u == 2 ? P.kf : 0.0);
+        if (G > 1e-6 && sq[u] > 1e-6) ub[4 * c + j] -= xi * (2.0 * G * sq[u]);
+      }
+    }
+  }
 }
 
 }  // namespace cmpc

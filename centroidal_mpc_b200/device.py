@@ -179,6 +179,45 @@ def lqr_gains_covs(model, traj_tuple):
     return g[0].cpu().numpy(), c[0].cpu().numpy()
 
 
+def chance_constraint_xi(beta_u):
+    """xi of construct_friction_pyramid_constraints (constraints.py:157): the pyramid matrix has
+    5 rows (utils.py:9-16), xi = Phi^-1(1 - beta_u / 5 * 3)."""
+    from scipy.stats import norm
+    return float(norm.ppf(1 - (beta_u / 5 * 3)))
+
+
+def friction_backoffs_batched(batch, gains, covs, beta_u):
+    """cmpc_friction_backoffs: friction-row upper bounds of the stochastic mode [B,N,nc,4] (CUDA
+    tensor) from the CUDA tensors of lqr_gains_covs_batched (constraints.py:157-163,187-214)."""
+    torch = _torch_cuda()
+    lib = L.load()
+    dev = gains.device
+    B, N, nc = batch.B, batch.N, batch.nc
+    ca = torch.from_numpy(batch.contact_active).to(dev)
+    cR = None if batch.contact_R is None else torch.from_numpy(batch.contact_R).to(dev)
+    dims = L.cmpc_dims(B, N, nc, 1 if batch.shared_plan else 0)
+    mdl = L.make_model_struct(batch.proto)
+    ub = torch.empty((B, N, nc, 4), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream()
+        L.check(lib.cmpc_friction_backoffs(C.byref(dims), C.byref(mdl), chance_constraint_xi(beta_u),
+                                           _ptr(gains.contiguous()), _ptr(covs.contiguous()), _ptr(cR), _ptr(ca),
+                                           _ptr(ub), C.c_void_p(st.cuda_stream)), lib)
+        st.synchronize()
+    return ub
+
+
+def friction_backoffs(model, traj_tuple=None):
+    """Upper bounds (N, nc, 4) of one model's friction rows in stochastic mode, along traj_tuple
+    (default: the warm start, as solve_scp linearises there)."""
+    traj_tuple = model._init_trajectories if traj_tuple is None else traj_tuple
+    batch = ProblemBatch([model])
+    X = np.asarray(traj_tuple["state"], dtype=np.float64).T[None]
+    U = np.asarray(traj_tuple["control"], dtype=np.float64).T[None]
+    g, c = lqr_gains_covs_batched(batch, X, U, model._Q, model._R, model._Cov_w, model._Cov_eta)
+    return friction_backoffs_batched(batch, g, c, model._beta_u)[0].cpu().numpy()
+
+
 def compute_trajectory_data(model, traj_tuple):
     """dict(dynamics (9,N), gradients{f_x (N,9,9), f_u (N,9,nu)}, LQR_gains (N,nu,9),
     Covs (N+1,9,9)) like the reference's compute_trajectory_data (centroidal_model.py:257-291);

@@ -139,6 +139,16 @@ int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr
                   const double* U, const double* contact_pos, const int32_t* contact_active, double* gains,
                   double* covs, void* scratch, void* stream);
 
+/* Stochastic mode (Centroidal_model(conf, STOCHASTIC_OCP=True)): upper bounds of the friction-pyramid
+ * rows with the chance-constraint back-offs of construct_friction_pyramid_constraints
+ * (src/constraints.py:157-163,187-214): friction_ub [B][N][nc][4] =
+ * - sum_u xi 2 G_ju sqrt((K_c Sigma_k K_c')_uu) over the entries with G_ju > 1e-6 and sqrt(.) > 1e-6, zero at
+ * k = 0 and for inactive contacts.  xi = Phi^-1(1 - beta_u/5*3) is computed by the caller (:157);
+ * gains / covs are the outputs of cmpc_lqr_covs; contact_R as in cmpc_set_problem (NULL = identity). */
+int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, double xi, const double* gains,
+                           const double* covs, const double* contact_R, const int32_t* contact_active,
+                           double* friction_ub, void* stream);
+
 /* DFMA micro-benchmark on the current device: achieved FP64 TFLOP/s and the SM clock (MHz) seen. */
 int cmpc_fp64_peak(double* tflops, double* ms);
 

@@ -155,7 +155,11 @@ def build_constraints(prob, traj_data, radius, weight, emulate_jax_fp32=False):
                 for j in range(4):                      # range(4): 5th row never written
                     for a in range(3):
                         add(r0 + 5 * k + j, idx_u(prob, k, npc * c + f_off + a), G[j, a])
-        lo += [-np.inf] * (5 * N); up += [0.0] * (5 * N)
+        ubc = [0.0] * (5 * N)
+        if prob.get("friction_ub") is not None:       # stochastic mode: chance-constraint back-offs
+            for k in range(N):
+                ubc[5 * k:5 * k + 4] = list(prob["friction_ub"][k, c])
+        lo += [-np.inf] * (5 * N); up += ubc
         r0 += 5 * N
     # 5. L1 trust region on angular momentum (constraints.py:260-293)
     blocks["trust"] = r0
@@ -184,3 +188,30 @@ def unpack(prob, z):
     X = np.reshape(z[:nx * (N + 1)], (nx, N + 1), order="F")
     U = np.reshape(z[nx * (N + 1):nx * (N + 1) + nu * N], (nu, N), order="F")
     return X, U
+
+
+def friction_backoffs(prob, gains, covs, beta_u):
+    """Upper bounds of the friction rows in stochastic mode, constraints.py:157-163,187-214:
+    ub[k,c,j] = -sum_u xi 2 G_ju sqrt((K_c Sigma_k K_c')_uu) over the entries with G_ju > 1e-6 and
+    sqrt(.) > 1e-6, for k > 0 and active contacts; xi = Phi^-1(1 - beta_u / 5 * 3).  The
+    covariance-gradient terms of the reference are identically zero.
+    Returns (ub [N, nc, 4], xi)."""
+    from scipy.stats import norm
+    N, nc = prob["N"], prob["contact_active"].shape[1]
+    pyr = friction_pyramid(prob["mu"])
+    xi = norm.ppf(1 - (beta_u / pyr.shape[0] * 3))
+    ub = np.zeros((N, nc, 4))
+    for c in range(nc):
+        for k in range(1, N):
+            if not prob["contact_active"][k, c]:
+                continue
+            G = pyr @ prob["contact_R"][k, c].T
+            K = gains[k, 3 * c:3 * c + 3, :]
+            KSK = K @ covs[k] @ K.T
+            for j in range(4):
+                for u in range(3):
+                    with np.errstate(invalid="ignore"):
+                        sq = np.sqrt(KSK[u, u])
+                    if G[j, u] > 1e-6 and sq > 1e-6:
+                        ub[k, c, j] -= xi * (2 * G[j, u] * sq)
+    return ub, xi

@@ -109,3 +109,20 @@ extern "C" int cmpc_emu_lqr_covs(const cmpc_dims* dims, const cmpc_model* model,
   }
   return 0;
 }
+
+extern "C" int cmpc_emu_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, double xi,
+                                          const double* gains, const double* covs, const double* contact_R,
+                                          const int32_t* contact_active, double* friction_ub) {
+  Params prm;
+  int rc = fill_params(&prm, dims, model, nullptr, nullptr, contact_R == nullptr);
+  if (rc) return rc;
+  const int B = dims->batch, N = prm.N, nu = prm.nu, nc = prm.nc;
+  for (long t = 0; t < (long)B * N; ++t) {
+    const int b = (int)(t / N), k = (int)(t % N);
+    const long plan = dims->shared_plan ? 0 : b;
+    friction_backoff_knot(prm, xi, k, gains + t * nu * 9, covs + ((long)b * (N + 1) + k) * 81,
+                          contact_R ? contact_R + (plan * N + k) * nc * 9 : nullptr,
+                          (const int*)contact_active + (plan * N + k) * nc, friction_ub + t * 4 * nc);
+  }
+  return 0;
+}

@@ -71,3 +71,19 @@ def lqr_covs(batch, X, U, Q, R, cov_w, cov_eta):
     if rc != 0:
         raise RuntimeError("cmpc_emu_lqr_covs returned %d" % rc)
     return gains, covs
+
+
+def friction_backoffs(batch, xi, gains, covs):
+    """Host build of friction_backoff_knot: ub [B,N,nc,4]."""
+    lib = load()
+    lib.cmpc_emu_friction_backoffs.argtypes = [C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 5
+    B, N, nc = batch.B, batch.N, batch.nc
+    dims = L.cmpc_dims(B, N, nc, 1 if batch.shared_plan else 0)
+    model = L.make_model_struct(batch.proto)
+    ub = np.zeros((B, N, nc, 4))
+    rc = lib.cmpc_emu_friction_backoffs(C.byref(dims), C.byref(model), float(xi), _p(np.ascontiguousarray(gains)),
+                                        _p(np.ascontiguousarray(covs)), _p(batch.contact_R),
+                                        _p(batch.contact_active), _p(ub))
+    if rc != 0:
+        raise RuntimeError("cmpc_emu_friction_backoffs returned %d" % rc)
+    return ub

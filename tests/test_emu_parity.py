@@ -239,3 +239,48 @@ def test_lqr_gain_is_the_two_step_riccati_minimiser(cases):
             P = m0._Q + A.T @ P @ A - A.T @ P @ B @ np.linalg.solve(m0._R + B.T @ P @ B, B.T @ P @ A)
         res = (m0._R + B.T @ P @ B) @ gains[0, k] + B.T @ P @ A
         assert np.abs(res).max() < 1e-9 * np.abs(B.T @ P @ A).max()
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_bound", "bolt"])
+def test_friction_backoffs_match_oracle(cases, name):
+    """Stochastic-mode friction upper bounds (constraints.py:187-214) from the host build."""
+    from oracle import dynamics, qp_build
+    conf, models = cases[name]
+    m0 = models[0]
+    X, U = lqr_case(conf, models, seed=2)
+    batch = ProblemBatch(models)
+    gains, covs = E.lqr_covs(batch, X, U, m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+    xi = qp_build.friction_backoffs(m0.problem_arrays(), gains[0], covs[0], m0._beta_u)[1]
+    ub = E.friction_backoffs(batch, xi, gains, covs)
+    for b, m in enumerate(models):
+        ref, _ = qp_build.friction_backoffs(m.problem_arrays(), gains[b], covs[b], m0._beta_u)
+        assert np.abs(ub[b] - ref).max() <= 1e-12 * np.abs(ref).max()
+        act = m.problem_arrays()["contact_active"].astype(bool)
+        assert np.all(ub[b][0] == 0.0) and np.all(ub[b][~act] == 0.0)
+        # only the rows with a positive tangential coefficient (+fx, +fy) are backed off
+        assert np.all(ub[b][..., 1] == 0.0) and np.all(ub[b][..., 3] == 0.0)
+        assert np.all(ub[b][1:][act[1:]][:, 0] < 0.0) and np.all(ub[b][1:][act[1:]][:, 2] < 0.0)
+
+
+def test_friction_backoffs_with_rotated_contacts():
+    from oracle import qp_build
+    conf = synthetic.load_conf("solo12_trot", N=12)
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    m = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 0))
+    rng = np.random.default_rng(11)
+    R = m._contact_data["contacts_orient"]
+    for k in range(R.shape[0]):
+        for c in range(R.shape[1]):
+            if m._contact_data["contacts_logic"][k, c]:
+                a = 0.3 * rng.normal(size=3)
+                th = np.linalg.norm(a)
+                Kx = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]]) / th
+                R[k, c] = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    batch = ProblemBatch([m])
+    assert batch.contact_R is not None
+    X, U = lqr_case(conf, [m], seed=4)
+    gains, covs = E.lqr_covs(batch, X, U, m._Q, m._R, m._Cov_w, m._Cov_eta)
+    ref, xi = qp_build.friction_backoffs(m.problem_arrays(), gains[0], covs[0], m._beta_u)
+    ub = E.friction_backoffs(batch, xi, gains, covs)
+    assert np.abs(ub[0] - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.count_nonzero(ub[0]) > np.count_nonzero(ub[0][..., [0, 2]]) - 1   # rotated rows gain back-offs

@@ -308,3 +308,29 @@ def test_lqr_covs_full_batch_properties(gpu):
         m = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b))
         g, c = dynamics.lqr_gains_covs(batch.X_ref[b].T, batch.U_init[b].T, m.problem_arrays(), *w)
         assert relerr(gains[b].cpu().numpy(), g) < 1e-12 and relerr(covs[b].cpu().numpy(), c) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_bound", "bolt"])
+def test_friction_backoffs_through_cabi(gpu, cases, name):
+    """cmpc_friction_backoffs (stochastic-mode friction upper bounds) against the oracle and
+    bitwise against the host build."""
+    import emu_binding as E
+    from centroidal_mpc_b200.batch import ProblemBatch
+    from centroidal_mpc_b200.device import (chance_constraint_xi, friction_backoffs, friction_backoffs_batched,
+                                            lqr_gains_covs_batched)
+    from oracle import qp_build
+    from test_emu_parity import lqr_case
+    conf, models = cases[name]
+    m0 = models[0]
+    X, U = lqr_case(conf, models, seed=2)
+    batch = ProblemBatch(models)
+    gains, covs = lqr_gains_covs_batched(batch, X, U, m0._Q, m0._R, m0._Cov_w, m0._Cov_eta)
+    ub = friction_backoffs_batched(batch, gains, covs, m0._beta_u).cpu().numpy()
+    gh, ch = gains.cpu().numpy(), covs.cpu().numpy()
+    assert np.array_equal(ub, E.friction_backoffs(batch, chance_constraint_xi(m0._beta_u), gh, ch))
+    for b, m in enumerate(models):
+        ref, xi = qp_build.friction_backoffs(m.problem_arrays(), gh[b], ch[b], m0._beta_u)
+        assert xi == chance_constraint_xi(m0._beta_u)
+        assert np.abs(ub[b] - ref).max() <= 1e-12 * np.abs(ref).max()
+    one = friction_backoffs(m0)
+    assert one.shape == (conf.N, batch.nc, 4) and np.all(one <= 0.0) and np.any(one < 0.0)

@@ -162,3 +162,26 @@ def test_oracle_reproduces_golden(path):
     assert [e.get("verdict", "qp_failed") for e in log] == [str(v) for v in g["verdicts"]]
     if int(g["n_accepted"]):
         assert relerr(sol["state"][-1], g["X"]) < 1e-9 and relerr(sol["control"][-1], g["U"]) < 1e-9
+
+
+def test_oracle_stochastic_mode_tightens_the_friction_rows(cases):
+    """Stochastic mode of the oracle (constraints.py:157-163,187-214): the friction rows get the
+    back-offs as upper bounds; the solve stays feasible, honours them, and moves the forces."""
+    from oracle import dynamics, qp_build, scp
+    conf, models = cases["solo12_trot"]
+    m = models[0]
+    prob = m.problem_arrays()
+    g, c = dynamics.lqr_gains_covs(prob["X_ref"], prob["U_init"], prob, m._Q, m._R, m._Cov_w, m._Cov_eta)
+    ub, xi = qp_build.friction_backoffs(prob, g, c, m._beta_u)
+    assert abs(xi - 2.5121443279304616) < 1e-12          # Phi^-1(1 - 0.01/5*3)
+    assert ub.shape == (conf.N, 4, 4) and ub.min() < -0.1 and ub.max() == 0.0
+    nom = scp.solve_scp(prob, conf.scp_params)
+    sto = scp.solve_scp(dict(prob, friction_ub=ub), conf.scp_params)
+    assert sto is not False and len(sto["state"]) == 1
+    U, Un = sto["control"][-1], nom["control"][-1]
+    pyr = qp_build.friction_pyramid(prob["mu"])[:4]
+    for k in range(conf.N):
+        for cc in range(4):
+            if prob["contact_active"][k, cc]:
+                assert (pyr @ U[3 * cc:3 * cc + 3, k] - ub[k, cc]).max() < 1e-7
+    assert np.linalg.norm(U - Un) / np.linalg.norm(Un) > 1e-3
