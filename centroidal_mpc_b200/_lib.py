@@ -45,7 +45,7 @@ LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
 
 
 EXPORTS = ["cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
-           "cmpc_set_problem", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
+           "cmpc_set_problem", "cmpc_set_friction_ub", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
            "cmpc_linearize", "cmpc_rollout", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
            "cmpc_last_error", "cmpc_version"]
 
@@ -136,6 +136,7 @@ def load():
     lib.cmpc_workspace_bytes.argtypes = [C.c_void_p]
     lib.cmpc_workspace_bytes.restype = C.c_int64
     lib.cmpc_set_problem.argtypes = [C.c_void_p, C.POINTER(cmpc_model)] + [dp] * 7
+    lib.cmpc_set_friction_ub.argtypes = [C.c_void_p, dp]
     lib.cmpc_solve_scp.argtypes = [C.c_void_p, C.POINTER(cmpc_scp_params), C.POINTER(cmpc_qp_settings),
                                    dp, dp, ip, ip, ip, vp]
     lib.cmpc_solve_scp_host.argtypes = [C.c_void_p, C.POINTER(cmpc_model), C.POINTER(cmpc_scp_params),

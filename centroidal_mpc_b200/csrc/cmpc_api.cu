@@ -306,6 +306,12 @@ int cmpc_set_problem(cmpc_handle h, const cmpc_model* model, const double* x_ini
   return 0;
 }
 
+int cmpc_set_friction_ub(cmpc_handle h, const double* friction_ub) {
+  if (!h) return fail(-1, "null argument");
+  h->bt.fub = friction_ub;
+  return 0;
+}
+
 int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
                    double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, void* stream) {
   if (!h || !scp || !X_out || !U_out || !scp_iters || !status) return fail(-1, "null argument");
@@ -315,6 +321,7 @@ int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_sett
   if (rc) return fail(rc, rc == -2 ? "cost weights must be positive" : "bad dims");
   cudaStream_t st = (cudaStream_t)stream;
   Batch bt = h->bt;
+  if (bt.fub) prm.fast = 0;   // upper bounds live in the general friction table
   bt.gtab = prm.fast ? nullptr : h->gtab;
   bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = (int*)scp_iters; bt.status = (int*)status;
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;

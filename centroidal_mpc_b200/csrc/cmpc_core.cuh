@@ -66,7 +66,8 @@ constexpr int R_U = 283;     // solution u[12] (compact)
 constexpr int REC = 296;     // 2368 bytes per instance and knot
 constexpr int R_STAGED = 274;  // fields [0, R_STAGED) can be staged by the sweeps
 constexpr int SEG_A = 1, SEG_B = 2, SEG_C = 4, SEG_D = 8, SEG_E = 16, SEG_F = 32;
-constexpr int GT = 64;       // general friction table per knot: per slot G (12, row-major 4x3) + e2 (4)
+constexpr int GS = 20;       // general friction table, per slot: G (12, row-major 4x3), e2 (4), upper bound (4)
+constexpr int GT = 4 * GS;   // ... per knot
 constexpr int INFO = 12;     // per-instance statistics (cmpc_get_stats)
 #ifndef CMPC_RING_DEPTH
 #define CMPC_RING_DEPTH 2
@@ -100,6 +101,7 @@ struct Batch {
   const double* cR;       // [Bp][N][nc][9] or null (identity)
   const int* cact;        // [Bp][N][nc]
   long plan_stride;       // 0 (shared plan) or 1
+  const double* fub;      // [B][N][nc][4] friction-row upper bounds (stochastic mode) or null (all zero)
   // workspace
   double* ws;             // [tiles][N+1][REC][32]
   double* gtab;           // [tiles][N][GT][32]   general friction rows; null on the fast path

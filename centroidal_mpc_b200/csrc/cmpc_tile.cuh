@@ -83,7 +83,7 @@ struct TileCtx {
 
 struct Inst {
   int b, lane;
-  const double *Xr, *Ui, *xi, *xf, *cpos, *cR;
+  const double *Xr, *Ui, *xi, *xf, *cpos, *cR, *fub;
   const int* cact;
 };
 
@@ -286,6 +286,7 @@ template <> struct Fric<true> {
   double kf, ea, eb;
   CMPC_HD void load(const Params& P, const double*, int) { kf = P.kf; ea = P.e2[0]; eb = P.e2[2]; }
   CMPC_HD double e2(int r) const { return r < 2 ? ea : eb; }
+  CMPC_HD double ub(int) const { return 0.0; }
   CMPC_HD double G(int r, int a) const {
     if (a == 2) return -kf;
     if (a == 0) return r == 0 ? 1.0 : (r == 1 ? -1.0 : 0.0);
@@ -304,18 +305,22 @@ template <> struct Fric<true> {
   }
 };
 template <> struct Fric<false> {
-  double g[12], e[4];
+  double g[12], e[4], b[4];
   CMPC_HD void load(const Params&, const double* gt, int s) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) g[i] = CMPC_R(gt, s * 16 + i);
+    for (int i = 0; i < 12; ++i) g[i] = CMPC_R(gt, s * GS + i);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) e[i] = CMPC_R(gt, s * 16 + 12 + i);
+    for (int i = 0; i < 4; ++i) { e[i] = CMPC_R(gt, s * GS + 12 + i); b[i] = CMPC_R(gt, s * GS + 16 + i); }
   }
   CMPC_HD double e2(int r) const { return e[r]; }
+  CMPC_HD double ub(int r) const { return b[r]; }
   CMPC_HD double G(int r, int a) const { return g[r * 3 + a]; }
+  // cf = G u - ub: the rows are carried SHIFTED by their upper bound (stochastic mode: the
+  // chance-constraint back-offs, constraints.py:187-214; zero otherwise), so that w = min(v, 0),
+  // y ~ max(v, 0), "active <=> cf = 0" and "violated <=> cf > 0" hold unchanged for the shifted values
   CMPC_HD void rows(const double* u, double* cf) const {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) cf[r] = fma(g[r * 3 + 2], u[2], fma(g[r * 3 + 1], u[1], g[r * 3] * u[0]));
+    for (int r = 0; r < 4; ++r) cf[r] = fma(g[r * 3 + 2], u[2], fma(g[r * 3 + 1], u[1], g[r * 3] * u[0])) - b[r];
   }
   CMPC_HD void trans(const double* t, double* o) const {
 #pragma unroll
@@ -686,9 +691,10 @@ CMPC_HD void bwd_knot(const Params& P, const Sv& S, StagedPtr r, double* w, int 
     for (int row = 0; row < 4; ++row) {
       if (MODE == MODE_ADMM) {
         t[row] = S.rho * fr.e2(row) * fabs(CMPC_S(r, R_VF + 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
+        if (!FAST) t[row] = fma(-S.rho * fr.e2(row), fr.ub(row), t[row]);     // unshifted w = min(v, 0) + ub
       } else {
         const double y = CMPC_S(r, R_YF + 4 * s + row);
-        t[row] = ((pm >> (4 * s + row)) & 1) ? y : 0.0;
+        t[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? y : fma(-P.inv_delta, fr.ub(row), y)) : 0.0;
       }
     }
     fr.trans(t, o);
@@ -933,7 +939,8 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
           if (CHK) {
             const double wn = fmin(vn, 0.0);
             R.pri = fmax(R.pri, fabs(cf[row] - wn));
-            R.npri = fmax(R.npri, fmax(fabs(cf[row]), fabs(wn)));
+            R.npri = fmax(R.npri, FAST ? fmax(fabs(cf[row]), fabs(wn))
+                                       : fmax(fabs(cf[row] + fr.ub(row)), fabs(wn + fr.ub(row))));
             dl[row] = S.rho * fr.e2(row) * (fmax(vn, 0.0) - y0 - cf[row] + w0);
           }
         }
@@ -955,7 +962,7 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
           const bool on = (pm >> bit) & 1;
           const double yn = fma(inv, cf[row], on ? CMPC_S(r, R_YF + bit) : 0.0);
           R.pri = fmax(R.pri, on ? fabs(cf[row]) : fmax(cf[row], 0.0));
-          R.npri = fmax(R.npri, fabs(cf[row]));
+          R.npri = fmax(R.npri, FAST ? fabs(cf[row]) : fabs(cf[row] + fr.ub(row)));
           if (upd) {
             const bool keep = on && !(yn < 0.0);
             const bool join = !on && (cf[row] > tolc);
@@ -1272,8 +1279,9 @@ CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k
           }
           if (gt) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) CMPC_R(gt, sl * 16 + row * 3 + a) = G[row * 3 + a];
-            CMPC_R(gt, sl * 16 + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
+            for (int a = 0; a < 3; ++a) CMPC_R(gt, sl * GS + row * 3 + a) = G[row * 3 + a];
+            CMPC_R(gt, sl * GS + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
+            CMPC_R(gt, sl * GS + 16 + row) = (sl < ns && I.fub) ? I.fub[((long)k * P.nc + cid) * 4 + row] : 0.0;
           }
         }
         if (sl < ns) {
@@ -1283,6 +1291,7 @@ CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k
             double cf = 0.0;
 #pragma unroll
             for (int a = 0; a < 3; ++a) cf += G[row * 3 + a] * ub[a];
+            if (I.fub) cf -= I.fub[((long)k * P.nc + cid) * 4 + row];
             CMPC_R(r, R_VF + 4 * sl + row) = fmin(cf, 0.0);
           }
         }
@@ -1635,6 +1644,7 @@ CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b) {
   I.lane = b & (TL - 1);
   I.cpos = bt.cpos + plan * N * P.nc * 3;
   I.cR = bt.cR ? bt.cR + plan * N * P.nc * 9 : nullptr;
+  I.fub = bt.fub ? bt.fub + (long)b * N * P.nc * 4 : nullptr;
   I.cact = bt.cact + plan * N * P.nc;
   I.Xr = bt.X_ref + (long)b * (N + 1) * 9;
   I.Ui = bt.U_init + (long)b * N * P.nu;

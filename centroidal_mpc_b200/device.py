@@ -41,6 +41,7 @@ class BatchSolver:
         self.ints = torch.zeros((5, B), dtype=torch.int32, device=self.device)
         self.info = torch.zeros((B, 12), dtype=f64, device=self.device)
         self.d = {}
+        self.friction_ub = None
         self.upload(batch)
 
     def upload(self, batch):
@@ -53,6 +54,16 @@ class BatchSolver:
         L.check(self.lib.cmpc_set_problem(self.handle, C.byref(self.model), _ptr(d["x_init"]), _ptr(d["x_final"]),
                                           _ptr(d["X_ref"]), _ptr(d["U_init"]), _ptr(d["contact_pos"]),
                                           _ptr(d["contact_R"]), _ptr(d["contact_active"])), self.lib)
+        # Centroidal_model(conf, STOCHASTIC_OCP=True): friction rows G f <= ub with the chance-constraint
+        # back-offs along the warm start (constraints.py:157-163,187-214), computed on the device
+        sto = batch.proto.get("stochastic")
+        self.friction_ub = None
+        if sto is not None:
+            with torch.cuda.device(self.device):
+                gains, covs = lqr_gains_covs_batched(batch, d["X_ref"], d["U_init"], sto["Q"], sto["R"],
+                                                     sto["cov_w"], sto["cov_eta"])
+                self.friction_ub = friction_backoffs_batched(batch, gains, covs, sto["beta_u"])
+        L.check(self.lib.cmpc_set_friction_ub(self.handle, _ptr(self.friction_ub)), self.lib)
 
     def solve(self, scp_params, qp_overrides=None, stream=None):
         torch = _torch_cuda()

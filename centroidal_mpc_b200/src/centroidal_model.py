@@ -156,6 +156,11 @@ class Centroidal_model:
             contact_R=self._contact_data["contacts_orient"].astype(np.float64),
             contact_active=self._contact_data["contacts_logic"].astype(np.int32),
             DYNAMICS_FIRST=bool(self._DYNAMICS_FIRST),
+            # stochastic mode (constraints.py:157-163,187-214): what the friction back-offs need
+            stochastic=dict(beta_u=float(self._beta_u), Q=np.asarray(self._Q, dtype=np.float64),
+                            R=np.asarray(self._R, dtype=np.float64),
+                            cov_w=np.asarray(self._Cov_w, dtype=np.float64),
+                            cov_eta=np.asarray(self._Cov_eta, dtype=np.float64)) if self._STOCHASTIC_OCP else None,
         )
         if self._robot == "TALOS":
             prob["foot_range"] = {k: np.asarray(v, dtype=np.float64)

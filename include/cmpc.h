@@ -87,6 +87,12 @@ int cmpc_set_problem(cmpc_handle h, const cmpc_model* model, const double* x_ini
                      const double* X_ref, const double* U_init, const double* contact_pos,
                      const double* contact_R, const int32_t* contact_active);
 
+/* Stochastic mode (Centroidal_model(conf, STOCHASTIC_OCP=True), src/constraints.py:157-163,187-214):
+ * binds the upper bounds of the friction-pyramid rows, friction_ub [B][N][nc][4] (device pointer, kept,
+ * not copied; the output of cmpc_friction_backoffs), used by every following cmpc_solve_scp /
+ * cmpc_solve_scp_host on this handle.  NULL returns to the nominal rows G f <= 0. */
+int cmpc_set_friction_ub(cmpc_handle h, const double* friction_ub);
+
 /* solve_scp(model, scp_params) for the whole batch: src/scp_solver.py:118-179, including
  * compute_trajectory_data (src/centroidal_model.py:257-291), the QP assembly
  * (src/cost.py:9-39, src/constraints.py:12-50,104-109,153-185,260-293), the OSQP solve

@@ -48,6 +48,10 @@ static void run_tile_host(const Params& prm, const Batch& bt, int tile) {
   }
 }
 
+// stochastic mode: friction-row upper bounds [B][N][nc][4] used by the following solves (null = nominal)
+static const double* g_fub = nullptr;
+extern "C" void cmpc_emu_set_friction_ub(const double* fub) { g_fub = fub; }
+
 extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model, const cmpc_scp_params* scp,
                                   const cmpc_qp_settings* qp, const double* x_init, const double* x_final,
                                   const double* X_ref, const double* U_init, const double* contact_pos,
@@ -57,6 +61,7 @@ extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model
   Params prm;
   int rc = fill_params(&prm, dims, model, scp, qp, contact_R == nullptr);
   if (rc) return rc;
+  if (g_fub) prm.fast = 0;
   const int B = dims->batch, N = dims->N;
   WsSizes w1 = ws_sizes(TL, N);   // tiles run one after the other: one tile of workspace
   WsSizes wb = ws_sizes(B, N);
@@ -68,6 +73,7 @@ extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model
     bt.B = B; bt.x_init = x_init; bt.x_final = x_final; bt.X_ref = X_ref; bt.U_init = U_init;
     bt.cpos = contact_pos; bt.cR = contact_R; bt.cact = contact_active;
     bt.plan_stride = dims->shared_plan ? 0 : 1;
+    bt.fub = g_fub;
     // workspace views shifted so that this tile lands on the single-tile buffers
     bt.ws = ws.data() - (long)tile * w1.ws;
     bt.gtab = prm.fast ? nullptr : gtab.data() - (long)tile * w1.gtab;

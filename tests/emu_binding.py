@@ -35,9 +35,21 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def solve_scp(batch, scp_params, qp_overrides=None):
-    """Run the host build of the device solver on a ProblemBatch; returns a dict of arrays."""
+def solve_scp(batch, scp_params, qp_overrides=None, friction_ub=None):
+    """Run the host build of the device solver on a ProblemBatch; returns a dict of arrays.
+    ``friction_ub`` [B,N,nc,4]: stochastic mode (upper bounds of the friction rows)."""
     lib = load()
+    lib.cmpc_emu_set_friction_ub.argtypes = [C.c_void_p]
+    lib.cmpc_emu_set_friction_ub.restype = None
+    fub = None if friction_ub is None else np.ascontiguousarray(friction_ub, dtype=np.float64)
+    lib.cmpc_emu_set_friction_ub(_p(fub))
+    try:
+        return _solve_scp(lib, batch, scp_params, qp_overrides)
+    finally:
+        lib.cmpc_emu_set_friction_ub(None)
+
+
+def _solve_scp(lib, batch, scp_params, qp_overrides):
     B, N, nu = batch.B, batch.N, batch.nu
     dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0)
     model = L.make_model_struct(batch.proto)

@@ -284,3 +284,50 @@ def test_friction_backoffs_with_rotated_contacts():
     ub = E.friction_backoffs(batch, xi, gains, covs)
     assert np.abs(ub[0] - ref).max() <= 1e-12 * np.abs(ref).max()
     assert np.count_nonzero(ub[0]) > np.count_nonzero(ub[0][..., [0, 2]]) - 1   # rotated rows gain back-offs
+
+
+# ---- stochastic mode: friction rows G f <= ub inside the solver ----
+def oracle_backoffs(m):
+    """Friction upper bounds of one model along its warm start, from the oracle alone."""
+    from oracle import dynamics, qp_build
+    prob = m.problem_arrays()
+    g, c = dynamics.lqr_gains_covs(prob["X_ref"], prob["U_init"], prob, m._Q, m._R, m._Cov_w, m._Cov_eta)
+    return qp_build.friction_backoffs(prob, g, c, m._beta_u)[0]
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
+def test_stochastic_mode_matches_oracle(cases, name):
+    conf, models = cases[name]
+    ub = np.stack([oracle_backoffs(m) for m in models[:2]])
+    out = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params, friction_ub=ub)
+    nom = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params)
+    for b in range(2):
+        ref = scp.solve_scp(dict(models[b].problem_arrays(), friction_ub=ub[b]), conf.scp_params)
+        if ref is False:            # the backed-off QP is infeasible / hits OSQP's cap: both report failure
+            assert out["status"][b] != 0
+            continue
+        assert out["status"][b] == 0 and out["scp_iters"][b] == ref["iterations"]
+        tol = TOL if name != "bolt" else 5e-6
+        assert relerr(out["X"][b].T, ref["state"][-1]) < tol
+        assert relerr(out["U"][b].T, ref["control"][-1]) < tol
+        # on the trot the back-offs bind: the forces move away from the nominal solution
+        if name == "solo12_trot":
+            assert relerr(out["U"][b], nom["U"][b]) > 1e-3
+        # and the returned forces honour the tightened rows
+        prob = models[b].problem_arrays()
+        kf = prob["mu"] / np.sqrt(2.0)
+        for k in range(conf.N):
+            for c in range(prob["contact_active"].shape[1]):
+                if prob["contact_active"][k, c]:
+                    f = out["U"][b][k, 3 * c:3 * c + 3]
+                    rows = np.array([f[0], -f[0], f[1], -f[1]]) - kf * f[2]
+                    assert (rows - ub[b, k, c]).max() < 1e-7
+
+
+def test_zero_upper_bounds_through_the_general_path_equal_the_nominal_solve(cases):
+    conf, models = cases["solo12_trot"]
+    batch = ProblemBatch(models)
+    nom = E.solve_scp(batch, conf.scp_params)
+    gen = E.solve_scp(batch, conf.scp_params, friction_ub=np.zeros((3, conf.N, 4, 4)))
+    assert np.array_equal(nom["scp_iters"], gen["scp_iters"]) and np.array_equal(nom["status"], gen["status"])
+    assert relerr(gen["X"], nom["X"]) < 1e-9 and relerr(gen["U"], nom["U"]) < 1e-9

@@ -334,3 +334,41 @@ def test_friction_backoffs_through_cabi(gpu, cases, name):
         assert np.abs(ub[b] - ref).max() <= 1e-12 * np.abs(ref).max()
     one = friction_backoffs(m0)
     assert one.shape == (conf.N, batch.nc, 4) and np.all(one <= 0.0) and np.any(one < 0.0)
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_bound"])
+def test_stochastic_mode_on_device(gpu, name):
+    """Centroidal_model(conf, STOCHASTIC_OCP=True) through solve_scp_batched: back-offs computed on
+    the device, friction rows G f <= ub inside cmpc_scp_kernel; against the oracle's stochastic
+    solve (1e-6) and bitwise against the host build fed with the same upper bounds."""
+    import emu_binding as E
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.batch import ProblemBatch
+    from centroidal_mpc_b200.device import BatchSolver
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    from centroidal_mpc_b200.src.scp_solver import solve_scp, solve_scp_batched
+    from oracle import scp
+    from test_emu_parity import oracle_backoffs
+    conf = synthetic.load_conf(name, N=40)
+    models = [Centroidal_model(conf, STOCHASTIC_OCP=True, centroidal_traj=synthetic.reference_trajectory(conf, b))
+              for b in range(40)]
+    batch = ProblemBatch(models)
+    solver = BatchSolver(batch)
+    out = solve_scp_batched(batch, conf.scp_params, solver=solver)
+    ub = solver.friction_ub.cpu().numpy()
+    solver.close()
+    assert (out["status"] == 0).all() and ub.min() < -0.05
+    host = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
+    assert np.array_equal(out["X"], host["X"]) and np.array_equal(out["U"], host["U"])
+    assert np.array_equal(out["scp_iters"], host["scp_iters"])
+    for b in (0, 39):
+        ubo = oracle_backoffs(models[b])
+        assert np.abs(ub[b] - ubo).max() <= 1e-12 * np.abs(ubo).max()
+        ref = scp.solve_scp(dict(models[b].problem_arrays(), friction_ub=ubo), conf.scp_params)
+        assert out["scp_iters"][b] == ref["iterations"]
+        assert relerr(out["X"][b].T, ref["state"][-1]) < TOL and relerr(out["U"][b].T, ref["control"][-1]) < TOL
+    # the nominal model of the same problem gives a different answer; the drop-in entry agrees with the batch
+    nominal = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 0))
+    sol_n, sol_s = solve_scp(nominal, conf.scp_params), solve_scp(models[0], conf.scp_params)
+    assert np.array_equal(sol_s["control"][-1], out["U"][0].T)
+    assert relerr(sol_s["control"][-1], sol_n["control"][-1]) > 5e-4
