@@ -87,7 +87,8 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tiles) {
+cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tile0,
+                int tiles) {   // this launch solves the tiles [tile0, tiles), pulled from its own queue counter
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31u;
   TileCtx T;
@@ -109,7 +110,7 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
   }
   for (;;) {
     int tile = 0;
-    if (lane == 0) tile = atomicAdd(queue, 1);
+    if (lane == 0) tile = tile0 + atomicAdd(queue, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= tiles) break;
     if (prm.fast) run_tile<true>(prm, bt, tile, T, nst_s);
@@ -238,7 +239,13 @@ struct cmpc_handle_s {
   // staging for the host entry point
   void *d_in, *d_out, *h_pin;
   long in_bytes, out_bytes;
+  // host entry point: the batch is cut into up to MAX_CHUNKS tile-aligned chunks, each with its own
+  // stream (H2D of chunk c+1 and D2H of chunk c-1 overlap the solve of chunk c)
+  cudaStream_t cs[8];
+  cudaEvent_t ev_small;
+  int have_streams;
 };
+static const int MAX_CHUNKS = 8;
 
 extern "C" {
 
@@ -290,6 +297,10 @@ int cmpc_destroy(cmpc_handle h) {
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->have_streams) {
+    for (int c = 0; c < MAX_CHUNKS; ++c) cudaStreamDestroy(h->cs[c]);
+    cudaEventDestroy(h->ev_small);
+  }
   free(h);
   return 0;
 }
@@ -312,33 +323,39 @@ int cmpc_set_friction_ub(cmpc_handle h, const double* friction_ub) {
   return 0;
 }
 
-int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
-                   double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, void* stream) {
-  if (!h || !scp || !X_out || !U_out || !scp_iters || !status) return fail(-1, "null argument");
-  if (!h->have_problem) return fail(-2, "cmpc_set_problem has not been called");
+// launches the solver for the tiles [tile0, tile1) of the bound batch on `st`; `slot` picks the queue counter
+static int launch_tiles(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
+                        double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, int tile0,
+                        int tile1, int slot, cudaStream_t st) {
   Params prm;
   int rc = fill_params(&prm, &h->dims, &h->model, scp, qp, h->bt.cR == nullptr);
   if (rc) return fail(rc, rc == -2 ? "cost weights must be positive" : "bad dims");
-  cudaStream_t st = (cudaStream_t)stream;
   Batch bt = h->bt;
   if (bt.fub) prm.fast = 0;   // upper bounds live in the general friction table
   bt.gtab = prm.fast ? nullptr : h->gtab;
   bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = (int*)scp_iters; bt.status = (int*)status;
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
-  CUDA_TRY(cudaMemsetAsync(h->queue, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(h->queue + slot, 0, sizeof(int), st));
   const long smem = scp_smem_bytes(h->dims.N);
   if (smem > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
   int per_sm = (int)(h->smem_max / (smem + 1024));   // 1 KB per block is reserved by the driver
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;                        // 255 registers per thread
-  int blocks = h->tiles;
+  int blocks = tile1 - tile0;
   const int cap = h->num_sms * per_sm;
   if (blocks > cap) blocks = cap;
-  cmpc_scp_kernel<<<blocks, THREADS, smem, st>>>(prm, bt, h->queue, h->tiles);
+  cmpc_scp_kernel<<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
+                   double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, void* stream) {
+  if (!h || !scp || !X_out || !U_out || !scp_iters || !status) return fail(-1, "null argument");
+  if (!h->have_problem) return fail(-2, "cmpc_set_problem has not been called");
+  return launch_tiles(h, scp, qp, X_out, U_out, scp_iters, status, n_accepted, 0, h->tiles, 0, (cudaStream_t)stream);
 }
 
 int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info) {
@@ -376,27 +393,47 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   double* d = (double*)h->d_in;
   double *dxi = d, *dxf = d + n_xi, *dX = d + 2 * n_xi, *dU = dX + n_X, *dcp = dU + n_U, *dcR = dcp + n_cp;
   int* dca = (int*)(dcR + n_cR);
-  cudaStream_t st = 0;
-  CUDA_TRY(cudaMemcpyAsync(dxi, x_init, n_xi * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dxf, x_final, n_xi * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dX, X_ref, n_X * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dU, U_init, n_U * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dcp, contact_pos, n_cp * 8, cudaMemcpyHostToDevice, st));
-  if (contact_R) CUDA_TRY(cudaMemcpyAsync(dcR, contact_R, n_cR * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(dca, contact_active, n_ca * 4, cudaMemcpyHostToDevice, st));
+  if (!h->have_streams) {
+    for (int c = 0; c < MAX_CHUNKS; ++c) CUDA_TRY(cudaStreamCreate(&h->cs[c]));   // blocking: ordered after earlier work on the null stream
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_small, cudaEventDisableTiming));
+    h->have_streams = 1;
+  }
+  // Small inputs and the contact plan first, on chunk 0's stream; the other chunks wait for them.
+  cudaStream_t s0 = h->cs[0];
+  CUDA_TRY(cudaMemcpyAsync(dxi, x_init, n_xi * 8, cudaMemcpyHostToDevice, s0));
+  CUDA_TRY(cudaMemcpyAsync(dxf, x_final, n_xi * 8, cudaMemcpyHostToDevice, s0));
+  CUDA_TRY(cudaMemcpyAsync(dcp, contact_pos, n_cp * 8, cudaMemcpyHostToDevice, s0));
+  if (contact_R) CUDA_TRY(cudaMemcpyAsync(dcR, contact_R, n_cR * 8, cudaMemcpyHostToDevice, s0));
+  CUDA_TRY(cudaMemcpyAsync(dca, contact_active, n_ca * 4, cudaMemcpyHostToDevice, s0));
+  CUDA_TRY(cudaEventRecord(h->ev_small, s0));
   int rc = cmpc_set_problem(h, model, dxi, dxf, dX, dU, dcp, contact_R ? dcR : nullptr, dca);
   if (rc) return rc;
   double* oX = (double*)h->d_out;
   double* oU = oX + n_X;
   int* oi = (int*)(oU + n_U);
-  rc = cmpc_solve_scp(h, scp, qp, oX, oU, oi, oi + B, oi + 2 * B, st);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(X_out, oX, n_X * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(U_out, oU, n_U * 8, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(scp_iters, oi, B * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(status, oi + B, B * 4, cudaMemcpyDeviceToHost, st));
-  if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted, oi + 2 * B, B * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  // Chunks of whole tiles: the trajectories of chunk c+1 are uploaded and the results of chunk c-1 are
+  // downloaded while chunk c is being solved; with one tile per SM the chunks' kernels run side by side.
+  const int tiles = h->tiles;
+  int chunks = tiles >= 4 * MAX_CHUNKS ? MAX_CHUNKS : (tiles >= 8 ? 4 : 1);
+  const int per = (tiles + chunks - 1) / chunks;
+  for (int c = 0; c < chunks; ++c) {
+    const int t0 = c * per, t1 = (c + 1) * per < tiles ? (c + 1) * per : tiles;
+    if (t0 >= t1) break;
+    const long b0 = (long)t0 * TL, b1 = (long)t1 * TL < B ? (long)t1 * TL : B, nb = b1 - b0;
+    cudaStream_t st = h->cs[c];
+    if (c) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_small, 0));
+    const long xo = b0 * (N + 1) * 9, uo = b0 * N * nu;
+    CUDA_TRY(cudaMemcpyAsync(dX + xo, X_ref + xo, nb * (N + 1) * 9 * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dU + uo, U_init + uo, nb * N * nu * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_tiles(h, scp, qp, oX, oU, oi, oi + B, oi + 2 * B, t0, t1, c, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(X_out + xo, oX + xo, nb * (N + 1) * 9 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(U_out + uo, oU + uo, nb * N * nu * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(scp_iters + b0, oi + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status + b0, oi + B + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+    if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted + b0, oi + 2 * B + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+  }
+  for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(h->cs[c]));
   return 0;
 }
 

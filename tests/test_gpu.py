@@ -372,3 +372,27 @@ def test_stochastic_mode_on_device(gpu, name):
     sol_n, sol_s = solve_scp(nominal, conf.scp_params), solve_scp(models[0], conf.scp_params)
     assert np.array_equal(sol_s["control"][-1], out["U"][0].T)
     assert relerr(sol_s["control"][-1], sol_n["control"][-1]) > 5e-4
+
+
+@pytest.mark.parametrize("B", [1, 33, 300, 1100])
+def test_host_entry_point_chunking(gpu, B):
+    """cmpc_solve_scp_host cuts the batch into tile-aligned chunks on their own streams (copies
+    overlap the solves): ragged last tile, one chunk / four / eight; unshared plans at B=33.
+    Results must equal the device-pointer entry bit for bit, all outputs included."""
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.batch import ProblemBatch
+    from centroidal_mpc_b200.device import BatchSolver
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    conf = synthetic.load_conf("solo12_trot", N=30)
+    if B == 33:
+        models = [Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b)) for b in range(B)]
+        batch = ProblemBatch(models, shared_plan=False)
+    else:
+        batch = synthetic.make_batch(conf, B)
+    solver = BatchSolver(batch)
+    dev = solver.solve(conf.scp_params).results()
+    host = solver.solve_host(conf.scp_params)
+    for key in ("X", "U", "scp_iters", "status", "n_accepted"):
+        np.testing.assert_array_equal(host[key], dev[key], err_msg=key)
+    assert (host["status"] == 0).all()
+    solver.close()
