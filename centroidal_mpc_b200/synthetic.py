@@ -57,14 +57,16 @@ def perturbed_x_init(conf, b):
     return reference_trajectory(conf, 0, mode="A")[0] + rng.normal(0.0, 1.0, size=9) * sig
 
 
-def make_batch(conf, B, mode="B", first=0):
+def make_batch(conf, B, mode="B", first=0, stochastic=False):
     """ProblemBatch of B synthetic instances sharing the contact plan of ``conf``.
 
     mode 'B': independent reference trajectories (every instance has its own linearisation);
-    mode 'A': one shared reference, only x_init perturbed (BASELINE.json config 2)."""
+    mode 'A': one shared reference, only x_init perturbed (BASELINE.json config 2).
+    ``stochastic``: the instances are Centroidal_model(conf, STOCHASTIC_OCP=True)."""
     from .batch import ProblemBatch
     from .src.centroidal_model import Centroidal_model
-    proto_model = Centroidal_model(conf, centroidal_traj=reference_trajectory(conf, first, mode=mode))
+    proto_model = Centroidal_model(conf, STOCHASTIC_OCP=stochastic,
+                                   centroidal_traj=reference_trajectory(conf, first, mode=mode))
     proto = proto_model.problem_arrays()
     X_ref = np.stack([reference_trajectory(conf, first + b, mode=mode) for b in range(B)])   # [B,N+1,9]
     U_init = np.broadcast_to(proto["U_init"].T[None], (B,) + proto["U_init"].T.shape).copy()

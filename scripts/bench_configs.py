@@ -9,9 +9,9 @@ from centroidal_mpc_b200 import synthetic
 from centroidal_mpc_b200.device import BatchSolver
 
 
-def run(name, N, B, mode="B", reps=5):
+def run(name, N, B, mode="B", reps=5, stochastic=False):
     conf = synthetic.load_conf(name, N=N)
-    solver = BatchSolver(synthetic.make_batch(conf, B, mode=mode))
+    solver = BatchSolver(synthetic.make_batch(conf, B, mode=mode, stochastic=stochastic))
     for _ in range(3):
         solver.solve(conf.scp_params)
     torch.cuda.synchronize()
@@ -22,7 +22,7 @@ def run(name, N, B, mode="B", reps=5):
         ts.append(e0.elapsed_time(e1))
     res, st = solver.results(), solver.stats()
     ms = float(np.median(ts))
-    print(json.dumps({"workload": name, "N": N, "batch": B, "mode": mode, "ms_p50": ms, "solves_per_s": B / ms * 1e3,
+    print(json.dumps({"workload": name, "N": N, "batch": B, "mode": mode, "stochastic": stochastic, "ms_p50": ms, "solves_per_s": B / ms * 1e3,
                       "failed": int((res["status"] != 0).sum()), "accepted": int((res["n_accepted"] > 0).sum()),
                       "scp_iters_mean": float(res["scp_iters"].mean()), "admm_iters_mean": float(st["qp_iters"].mean()),
                       "admm_iters_max": int(st["qp_iters"].max()), "factorisations_mean": float(st["n_factor"].mean())}), flush=True)
@@ -34,5 +34,7 @@ if __name__ == "__main__":
     run("solo12_pace", 100, 1024, mode="A")         # config 2: perturbed initial states
     run("solo12_bound", 100, 4096)                  # config 3
     run("bolt", 100, 1024)                          # config 4: 8192 over 8 GPUs = 1024 per GPU
+    run("solo12_trot", 100, 4096, stochastic=True)  # stochastic mode: friction rows with chance-constraint back-offs
+    run("solo12_bound", 100, 4096, stochastic=True)
     for B in (256, 1024, 4096, 16384, 65536):       # config 5's batch sweep, on the solo12 trot problem
         run("solo12_trot", 100, B, reps=3)

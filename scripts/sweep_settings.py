@@ -10,7 +10,8 @@ from centroidal_mpc_b200.device import BatchSolver
 
 conf = synthetic.load_conf(os.environ.get("SWEEP_CONF", "solo12_trot"), N=100)
 B = int(os.environ.get("SWEEP_BATCH", "4096"))
-solver = BatchSolver(synthetic.make_batch(conf, B))
+STOCH = os.environ.get("SWEEP_STOCH", "0") == "1"
+solver = BatchSolver(synthetic.make_batch(conf, B, stochastic=STOCH))
 
 
 def run(qp):
@@ -38,6 +39,11 @@ for a, rho in ((10, 4.0), (10, 8.0), (8, 4.0), (12, 4.0), (6, 8.0)):
     grid.append(dict(active_set_start=a, active_set_step=a, rho=rho))
 for al in (1.0, 1.8):
     grid.append(dict(alpha=al))
+if STOCH:
+    grid = [dict(polish_active_set_rounds=r) for r in (19, 39)]
+    grid += [dict(active_set_start=a, active_set_step=a) for a in (40, 80)]
+    grid += [dict(active_set_start=a, active_set_step=a, polish_active_set_rounds=29) for a in (20, 40)]
+    grid += [dict(rho=r) for r in (0.5, 8.0)]
 for qp in grid:
     t, r, s = run(qp)
     ex = np.linalg.norm(r["X"] - r0["X"]) / np.linalg.norm(r0["X"])

@@ -331,3 +331,23 @@ def test_zero_upper_bounds_through_the_general_path_equal_the_nominal_solve(case
     gen = E.solve_scp(batch, conf.scp_params, friction_ub=np.zeros((3, conf.N, 4, 4)))
     assert np.array_equal(nom["scp_iters"], gen["scp_iters"]) and np.array_equal(nom["status"], gen["status"])
     assert relerr(gen["X"], nom["X"]) < 1e-9 and relerr(gen["U"], nom["U"]) < 1e-9
+
+
+def check_against_stochastic_golden(g, gains, covs, ub, X, U, scp_iters):
+    """gains (N,nu,9), covs (N+1,9,9), ub (N,nc,4), X (9,N+1), U (nu,N) against a stoch*.npz fixture."""
+    assert relerr(gains, g["gains"]) < 1e-12 and relerr(covs, g["covs"]) < 1e-12
+    assert np.abs(ub - g["friction_ub"]).max() <= 1e-12 * np.abs(g["friction_ub"]).max()
+    assert scp_iters == int(g["iterations"])
+    assert relerr(X, g["X_tight"]) < TOL and relerr(U, g["U_tight"]) < TOL
+
+
+@pytest.mark.parametrize("path", __import__("test_oracle")._stoch_golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_emu_matches_stochastic_golden(path):
+    from test_oracle import load_stoch_golden
+    g, conf, m = load_stoch_golden(path)
+    batch = ProblemBatch([m])
+    gains, covs = E.lqr_covs(batch, batch.X_ref, batch.U_init, m._Q, m._R, m._Cov_w, m._Cov_eta)
+    ub = E.friction_backoffs(batch, float(g["xi"]), gains, covs)
+    out = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
+    assert out["status"][0] == 0
+    check_against_stochastic_golden(g, gains[0], covs[0], ub[0], out["X"][0].T, out["U"][0].T, int(out["scp_iters"][0]))

@@ -396,3 +396,19 @@ def test_host_entry_point_chunking(gpu, B):
         np.testing.assert_array_equal(host[key], dev[key], err_msg=key)
     assert (host["status"] == 0).all()
     solver.close()
+
+
+def test_stochastic_golden_through_cabi(gpu):
+    """tests/golden/stoch*.npz: gains, covariances, back-offs and the stochastic solve, all on the device."""
+    from centroidal_mpc_b200.device import friction_backoffs
+    from centroidal_mpc_b200.src.scp_solver import solve_scp
+    from test_emu_parity import check_against_stochastic_golden
+    from test_oracle import _stoch_golden_files, load_stoch_golden
+    files = _stoch_golden_files()
+    assert len(files) == 4
+    for path in files:
+        g, conf, m = load_stoch_golden(path)
+        sol = solve_scp(m, conf.scp_params)
+        assert sol is not False and len(sol["state"]) == int(g["iterations"]) == 1
+        check_against_stochastic_golden(g, sol["gains"][-1], sol["covs"][-1], friction_backoffs(m),
+                                        sol["state"][-1], sol["control"][-1], len(sol["state"]))

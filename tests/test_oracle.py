@@ -185,3 +185,35 @@ def test_oracle_stochastic_mode_tightens_the_friction_rows(cases):
             if prob["contact_active"][k, cc]:
                 assert (pyr @ U[3 * cc:3 * cc + 3, k] - ub[k, cc]).max() < 1e-7
     assert np.linalg.norm(U - Un) / np.linalg.norm(Un) > 1e-3
+
+
+def _stoch_golden_files():
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(glob.glob(os.path.join(here, "stoch*.npz")))
+
+
+def load_stoch_golden(path):
+    """(fixture, conf, stochastic model) of a tests/golden/stoch*.npz file."""
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
+    g = np.load(path)
+    conf = synthetic.load_conf(str(g["name"]), N=int(g["N"]))
+    model = Centroidal_model(conf, STOCHASTIC_OCP=True,
+                             centroidal_traj=synthetic.reference_trajectory(conf, int(g["b"])))
+    return g, conf, model
+
+
+@pytest.mark.parametrize("path", _stoch_golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_reproduces_stochastic_golden(path):
+    from oracle import dynamics, qp_build
+    g, conf, m = load_stoch_golden(path)
+    prob = m.problem_arrays()
+    gains, covs = dynamics.lqr_gains_covs(prob["X_ref"], prob["U_init"], prob, m._Q, m._R, m._Cov_w, m._Cov_eta)
+    ub, xi = qp_build.friction_backoffs(prob, gains, covs, m._beta_u)
+    assert relerr(gains, g["gains"]) < 1e-12 and relerr(covs, g["covs"]) < 1e-12
+    assert relerr(ub, g["friction_ub"]) < 1e-12 and xi == float(g["xi"])
+    sol = scp.solve_scp(dict(prob, friction_ub=ub), conf.scp_params)
+    assert sol["iterations"] == int(g["iterations"])
+    assert relerr(sol["state"][-1], g["X"]) < 1e-9 and relerr(sol["control"][-1], g["U"]) < 1e-9
+    # OSQP's answer at its default settings against the tightly solved one
+    assert relerr(g["X"], g["X_tight"]) < 5e-6 and relerr(g["U"], g["U_tight"]) < 5e-6
