@@ -20,6 +20,13 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# QP settings used when friction upper bounds are bound (stochastic mode) unless the caller overrides
+# them: the multiplier iteration of a polish round needs more sweeps to reach the 1e-9 certificate with
+# back-offs (bound gait: 3 sweeps leave a quarter of the instances uncertified for several attempts),
+# and the active set needs up to 13 correction rounds at N = 100.
+STOCHASTIC_QP_DEFAULTS = dict(polish_refine_iter=10, polish_active_set_rounds=19)
+
+
 class BatchSolver:
     """Owns a cmpc handle (solver workspace) for a fixed (B, N, nc) and the device copies of one
     ProblemBatch.  ``solve`` runs solve_scp for all instances on the current stream."""
@@ -68,13 +75,18 @@ class BatchSolver:
     def solve(self, scp_params, qp_overrides=None, stream=None):
         torch = _torch_cuda()
         scp = L.make_scp_struct(scp_params)
-        qp = L.make_qp_struct(qp_overrides, self.lib)
+        qp = L.make_qp_struct(self._qp(qp_overrides), self.lib)
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         with torch.cuda.device(self.device):
             L.check(self.lib.cmpc_solve_scp(self.handle, C.byref(scp), C.byref(qp), _ptr(self.X), _ptr(self.U),
                                             _ptr(self.ints[0]), _ptr(self.ints[1]), _ptr(self.ints[2]),
                                             C.c_void_p(st)), self.lib)
         return self
+
+    def _qp(self, overrides):
+        if self.friction_ub is None:
+            return overrides
+        return dict(STOCHASTIC_QP_DEFAULTS, **(overrides or {}))
 
     def stats(self):
         L.check(self.lib.cmpc_get_stats(self.handle, _ptr(self.ints[3]), _ptr(self.ints[4]), _ptr(self.info)),
@@ -96,7 +108,7 @@ class BatchSolver:
             out = dict(X=np.empty((B, N + 1, 9)), U=np.empty((B, N, nu)), scp_iters=np.empty(B, np.int32),
                        status=np.empty(B, np.int32), n_accepted=np.empty(B, np.int32))
         scp = L.make_scp_struct(scp_params)
-        qp = L.make_qp_struct(qp_overrides, self.lib)
+        qp = L.make_qp_struct(self._qp(qp_overrides), self.lib)
 
         def p(a):
             return None if a is None else a.ctypes.data_as(C.c_void_p)

@@ -90,7 +90,9 @@ int cmpc_set_problem(cmpc_handle h, const cmpc_model* model, const double* x_ini
 /* Stochastic mode (Centroidal_model(conf, STOCHASTIC_OCP=True), src/constraints.py:157-163,187-214):
  * binds the upper bounds of the friction-pyramid rows, friction_ub [B][N][nc][4] (device pointer, kept,
  * not copied; the output of cmpc_friction_backoffs), used by every following cmpc_solve_scp /
- * cmpc_solve_scp_host on this handle.  NULL returns to the nominal rows G f <= 0. */
+ * cmpc_solve_scp_host on this handle.  NULL returns to the nominal rows G f <= 0.
+ * Recommended cmpc_qp_settings with upper bounds: polish_refine_iter = 10, polish_active_set_rounds = 19
+ * (the defaults are correct but leave some instances to several polish attempts). */
 int cmpc_set_friction_ub(cmpc_handle h, const double* friction_ub);
 
 /* solve_scp(model, scp_params) for the whole batch: src/scp_solver.py:118-179, including

@@ -295,11 +295,13 @@ def oracle_backoffs(m):
     return qp_build.friction_backoffs(prob, g, c, m._beta_u)[0]
 
 
+@pytest.mark.parametrize("qp", [None, dict(polish_refine_iter=10, polish_active_set_rounds=19)],
+                         ids=["library-defaults", "host-stochastic-defaults"])
 @pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
-def test_stochastic_mode_matches_oracle(cases, name):
+def test_stochastic_mode_matches_oracle(cases, name, qp):
     conf, models = cases[name]
     ub = np.stack([oracle_backoffs(m) for m in models[:2]])
-    out = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params, friction_ub=ub)
+    out = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params, qp, friction_ub=ub)
     nom = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params)
     for b in range(2):
         ref = scp.solve_scp(dict(models[b].problem_arrays(), friction_ub=ub[b]), conf.scp_params)
@@ -348,6 +350,22 @@ def test_emu_matches_stochastic_golden(path):
     batch = ProblemBatch([m])
     gains, covs = E.lqr_covs(batch, batch.X_ref, batch.U_init, m._Q, m._R, m._Cov_w, m._Cov_eta)
     ub = E.friction_backoffs(batch, float(g["xi"]), gains, covs)
-    out = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
+    out = E.solve_scp(batch, conf.scp_params, dict(polish_refine_iter=10, polish_active_set_rounds=19), friction_ub=ub)
     assert out["status"][0] == 0
     check_against_stochastic_golden(g, gains[0], covs[0], ub[0], out["X"][0].T, out["U"][0].T, int(out["scp_iters"][0]))
+
+
+def test_stochastic_headline_horizon_certifies_at_the_first_attempt():
+    """N = 100 bound gait with back-offs: with the host side's stochastic QP settings every instance is
+    certified by the first polish attempt (20 ADMM iterations); the library defaults leave some to retry."""
+    from centroidal_mpc_b200.device import chance_constraint_xi
+    conf = synthetic.load_conf("solo12_bound", N=100)
+    batch = synthetic.make_batch(conf, 8, stochastic=True)
+    sto = batch.proto["stochastic"]
+    g, c = E.lqr_covs(batch, batch.X_ref, batch.U_init, sto["Q"], sto["R"], sto["cov_w"], sto["cov_eta"])
+    ub = E.friction_backoffs(batch, chance_constraint_xi(sto["beta_u"]), g, c)
+    tuned = E.solve_scp(batch, conf.scp_params, dict(polish_refine_iter=10, polish_active_set_rounds=19), friction_ub=ub)
+    plain = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
+    assert (tuned["status"] == 0).all() and (tuned["qp_iters"] == 20).all() and (tuned["info"][:, 9] == 1).all()
+    assert plain["qp_iters"].max() > 20
+    assert relerr(tuned["X"], plain["X"]) < TOL and relerr(tuned["U"], plain["U"]) < TOL

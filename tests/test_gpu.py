@@ -358,7 +358,8 @@ def test_stochastic_mode_on_device(gpu, name):
     ub = solver.friction_ub.cpu().numpy()
     solver.close()
     assert (out["status"] == 0).all() and ub.min() < -0.05
-    host = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
+    from centroidal_mpc_b200.device import STOCHASTIC_QP_DEFAULTS
+    host = E.solve_scp(batch, conf.scp_params, STOCHASTIC_QP_DEFAULTS, friction_ub=ub)
     assert np.array_equal(out["X"], host["X"]) and np.array_equal(out["U"], host["U"])
     assert np.array_equal(out["scp_iters"], host["scp_iters"])
     for b in (0, 39):
