@@ -39,6 +39,12 @@ for a, rho in ((10, 4.0), (10, 8.0), (8, 4.0), (12, 4.0), (6, 8.0)):
     grid.append(dict(active_set_start=a, active_set_step=a, rho=rho))
 for al in (1.0, 1.8):
     grid.append(dict(alpha=al))
+for rf in (1, 2, 5, 10):
+    grid.append(dict(polish_refine_iter=rf))
+for rf, a in ((5, 15), (10, 15), (10, 12), (10, 10)):
+    grid.append(dict(polish_refine_iter=rf, active_set_start=a, active_set_step=a))
+if os.environ.get("SWEEP_ONLY_REFINE", "0") == "1":
+    grid = grid[-8:]
 if STOCH:
     grid = [dict(polish_active_set_rounds=r) for r in (19, 39)]
     grid += [dict(active_set_start=a, active_set_step=a) for a in (40, 80)]
