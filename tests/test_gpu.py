@@ -413,3 +413,46 @@ def test_stochastic_golden_through_cabi(gpu):
         assert sol is not False and len(sol["state"]) == int(g["iterations"]) == 1
         check_against_stochastic_golden(g, sol["gains"][-1], sol["covs"][-1], friction_backoffs(m),
                                         sol["state"][-1], sol["control"][-1], len(sol["state"]))
+
+
+def test_stochastic_full_size_properties(gpu):
+    """Stochastic mode at the headline shape (4096 x N=100, trot): every instance accepted after one SCP
+    iteration and certified by the first polish attempt; the forces honour the backed-off rows; the forces
+    of inactive contacts are exact zeros; the dynamics hold; the first tile equals the host build bit for bit."""
+    import emu_binding as E
+    from centroidal_mpc_b200 import synthetic
+    from centroidal_mpc_b200.batch import ProblemBatch
+    from centroidal_mpc_b200.device import STOCHASTIC_QP_DEFAULTS, BatchSolver
+    conf = synthetic.load_conf("solo12_trot", N=100)
+    batch = synthetic.make_batch(conf, 4096, stochastic=True)
+    solver = BatchSolver(batch)
+    out = solver.solve(conf.scp_params).results()
+    st = solver.stats()
+    ub = solver.friction_ub.cpu().numpy()
+    solver.close()
+    assert (out["status"] == 0).all() and (out["scp_iters"] == 1).all() and (out["n_accepted"] == 1).all()
+    assert (st["qp_iters"] == 20).all() and (st["info"][:, 9] == 1).all()
+    act = batch.contact_active[0].astype(bool)                       # [N, nc], shared plan
+    U = out["U"].reshape(4096, 100, 4, 3)
+    assert np.all(U[:, ~act] == 0.0)
+    kf = batch.proto["mu"] / np.sqrt(2.0)
+    rows = np.stack([U[..., 0], -U[..., 0], U[..., 1], -U[..., 1]], -1) - kf * U[..., 2:3] - ub
+    assert rows[:, act].max() < 1e-7 and ub.min() < -1.0 and np.all(ub[:, ~act] == 0.0)
+    # dynamics x_{k+1} = f(x_k, u_k) are linear in (x, u) about the warm start: check through the rollout
+    X = out["X"]
+    m, dt, g = batch.proto["m"], batch.proto["dt"], batch.proto["g"]
+    F = U.sum(2)
+    assert np.abs(X[:, 1:, 0:3] - (X[:, :-1, 0:3] + dt / m * X[:, :-1, 3:6])).max() < 1e-9
+    lin = X[:, :-1, 3:6] + dt * F
+    lin[..., 2] += dt * m * g
+    assert np.abs(X[:, 1:, 3:6] - lin).max() < 1e-9
+    np.testing.assert_allclose(X[:, 0], batch.x_init, atol=1e-9)
+    np.testing.assert_allclose(X[:, -1], batch.x_final, atol=1e-7)
+    # first tile against the host build of the kernel source
+    import copy
+    sub = copy.copy(batch)
+    sub.B = 32
+    for k in ("x_init", "x_final", "X_ref", "U_init"):
+        setattr(sub, k, np.ascontiguousarray(getattr(batch, k)[:32]))
+    host = E.solve_scp(sub, conf.scp_params, STOCHASTIC_QP_DEFAULTS, friction_ub=ub[:32])
+    assert np.array_equal(host["X"], out["X"][:32]) and np.array_equal(host["U"], out["U"][:32])
