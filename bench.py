@@ -168,14 +168,15 @@ def algorithmic_work(batch, stats):
     ns = batch.contact_active[0].sum(axis=1).astype(float)   # active contacts per knot (shared plan)
     na = 3 * ns
     N = batch.N
-    tri = na * (na + 1) / 2
-    segA, segB, segC, segD, segE, segF = 9 + tri, 9 * na, 16 + na, 3 + 4 * ns, na, 4 + 4 * ns
-    term = 16 + 3                                             # terminal knot: stage data + kappa copy
-    bwd_admm = (segA + segB + segC + segD + na).sum() + term            # + writes d_k
-    fwd_admm = (segB + segC + segD + segE + 3 + 4 * ns).sum() + term + 3   # + writes vk, vf
-    bwd_pmm = (segA + segB + segC + segF + na).sum() + 16 + 4
-    fwd_pmm = (segB + segC + segE + segF + 9 + na + 4 * ns).sum() + 16 + 4 + 9   # + writes x, u, yf
-    fac = (segC + 9 + tri + 9 * na).sum() + 16                             # reads stage, writes Pc, Hinv, K
+    # record ranges of csrc/cmpc_core.cuh (lay_of) / cmpc_tile.cuh (ranges_of): A Pc[9]; M Hn[na*na] + Kt[9 na];
+    # C meta + xbar + S + ck + d; D vk + vf; E dv; F yk + yf
+    segA, segHn, segKt, segC, segD, segE, segF = 9 + 0 * na, na * na, 9 * na, 16 + na, 3 + 4 * ns, na, 4 + 4 * ns
+    term = 9 + 16 + 3                                         # terminal knot: Pc slot + stage data + kappa copy
+    bwd_admm = (segA + segHn + segKt + segC + segD + na).sum() + term          # [A .. D] + writes d_k
+    fwd_admm = (segKt + segC + segD + segE + 3 + 4 * ns).sum() + term + 3      # [Kt .. E] + writes vk, vf
+    bwd_pmm = (segA + segHn + segKt + segC + segF + na).sum() + 9 + 16 + 4
+    fwd_pmm = (segKt + segC + segE + segF + 9 + na + 4 * ns).sum() + 16 + 4 + 9   # + writes x, u, yf
+    fac = (segC + 9 + na * na + 9 * na).sum() + 16                             # reads stage, writes Pc, Hn, Kt
     sweep_bytes = 8.0 * float(bwd_admm + fwd_admm)
     pmm_bytes = 8.0 * float(bwd_pmm + fwd_pmm)
     factor_bytes = 8.0 * float(fac)

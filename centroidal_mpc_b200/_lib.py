@@ -141,7 +141,7 @@ def load():
                                    dp, dp, ip, ip, ip, vp]
     lib.cmpc_solve_scp_host.argtypes = [C.c_void_p, C.POINTER(cmpc_model), C.POINTER(cmpc_scp_params),
                                         C.POINTER(cmpc_qp_settings)] + [dp] * 7 + [dp, dp, ip, ip, ip]
-    lib.cmpc_get_stats.argtypes = [C.c_void_p, ip, ip, dp]
+    lib.cmpc_get_stats.argtypes = [C.c_void_p, ip, ip, dp, vp]
     lib.cmpc_linearize.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, dp, dp, vp]
     lib.cmpc_rollout.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, vp]
     lib.cmpc_lqr_covs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.POINTER(cmpc_lqr_weights),

@@ -29,44 +29,44 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// The SCP kernel: one thread per MPC instance, one warp per tile of 32 instances, persistent
-// over a queue of tiles.  Each lane runs the driver state machine of its instance
-// (cmpc_tile.cuh: advance()); the warp executes one whole-horizon operation at a time for the
-// lanes that asked for it, lowest operation code first, so that lanes that are ahead wait at
-// the later operations (evaluate, write) and the tile does those together.  Warps never
-// synchronise with each other.
+// The SCP kernel: one warp per tile of TL = 32 / NL instances, NL lanes per instance (cmpc_core.cuh),
+// persistent over a queue of tiles; a CTA is one warp, several CTAs share an SM.  Each instance runs
+// the driver state machine (cmpc_tile.cuh: advance(), replicated in the lanes of its team); the warp
+// executes one whole-horizon operation at a time for the instances that asked for it, lowest operation
+// code first, so that instances that are ahead wait at the later operations (evaluate, write) and the
+// tile does those together.  Warps never synchronise with each other.
 // ------------------------------------------------------------------------------------------
-constexpr int THREADS = 64;   // solver warp (one tile at a time) + producer / helper warp
-constexpr long RING_BYTES = (long)RING_DEPTH * R_STAGED * TL * 8;
-inline long scp_smem_bytes(int N) { return RING_BYTES + 64 + ((N + 1 + 15) & ~15); }
+constexpr int THREADS = 32;
+constexpr int BAR_BYTES = 64;   // 4 mbarriers ("full" per ring slot) + padding
+inline long scp_smem_bytes(int N, bool gen) { return (long)tile_smem_fields(gen) * TL * 8 + BAR_BYTES + ((N + 1 + 15) & ~15); }
 
 template <bool FAST>
 __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& T, unsigned char* nst_s) {
   const int lane = (int)(threadIdx.x & 31u);
+  const int t = lane & (TL - 1), q = lane / TL;
   bind_tile(T, prm, bt, tile);
-  const int b = tile * TL + lane;
-  const bool live = lane < TL && b < bt.B;
+  const int b = tile * TL + t;
+  const bool live = b < bt.B;
   Inst I;
   Sv S;
   Drv D;
-  I.lane = lane & (TL - 1);
   D.check = D.upd = 0;
-  if (live) bind_instance(I, prm, bt, b);
-  {   // even knots here, odd knots on the producer warp
-    helper_fork(T, CMD_SETUP, __ballot_sync(0xffffffffu, live));
-    double mq = 0.0, mc = 0.0;
-    if (live) setup_knots(prm, T, I, 0, 2, &mq, &mc);
-    helper_join();
-    if (live) {
-      mq = fmax(mq, sc_ld(T.ring_sa + (unsigned)lane * 8u, 0));
-      mc = fmax(mc, sc_ld(T.ring_sa + (unsigned)lane * 8u, TL));
-      setup_finish(I, S, mq, mc);
-    }
+  bind_instance(I, prm, bt, live ? b : bt.B - 1);   // lanes past the batch run along on a valid instance, without writing
+  I.lane = t;
+  I.sub = q;
+  for (int k0 = 0; k0 <= prm.N; k0 += NL) {   // slots per knot of the tile: the record layout of the knot
+    const int k = k0 + q;
+    int ns = (live && k < prm.N) ? active_slots(prm, I, k) : 0;
+#pragma unroll
+    for (int m = 1; m < TL; m <<= 1) ns = max(ns, __shfl_xor_sync(0xffffffffu, ns, m));
+    if (t == 0 && k <= prm.N) { T.nst[k] = ns; nst_s[k] = (unsigned char)ns; }
   }
-  for (int k = 0; k <= prm.N; ++k) {   // slots per knot of the tile
-    const int ns = live ? (meta_of(T, I, k)[0] & 7) : 0;
-    const int mx = __reduce_max_sync(0xffffffffu, ns);
-    if (lane == 0) { T.nst[k] = mx; nst_s[k] = (unsigned char)mx; }
+  __syncwarp();
+  {
+    double mq = 0.0, mc = 0.0;
+    int nconv = 0;
+    setup_knots(prm, T, I, live, &mq, &mc, &nconv);
+    setup_finish(I, S, mq, mc, nconv);
   }
   __syncwarp();
   int op = OP_DONE;
@@ -86,39 +86,33 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
   if (live) write_stats(bt, I, S, D);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool FAST>
+__global__ void __launch_bounds__(THREADS, 8)
 cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tile0,
                 int tiles) {   // this launch solves the tiles [tile0, tiles), pulled from its own queue counter
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31u;
+  constexpr long SCR_BYTES = (long)tile_smem_fields(!FAST) * TL * 8;
   TileCtx T;
-  T.ring = reinterpret_cast<double*>(smem_raw);
-  T.ring_sa = smem_addr(smem_raw);
-  T.bars_sa = T.ring_sa + (unsigned)RING_BYTES;
+  T.smem_sa = smem_addr(smem_raw);
+  T.bars_sa = T.smem_sa + (unsigned)SCR_BYTES;
   T.phases = 0;
-  unsigned char* nst_s = smem_raw + RING_BYTES + 64;
+  unsigned char* nst_s = smem_raw + SCR_BYTES + BAR_BYTES;
   T.nst_s = nst_s;
-  if (threadIdx.x == 0) {
-    for (int d = 0; d < 2 * RING_DEPTH; ++d)   // "full" barriers (bulk-copy completion), then "empty" ones
+  if (lane == 0) {
+    for (int d = 0; d < 4; ++d)   // "full" barriers of the ring slots (bulk-copy completion)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(T.bars_sa + 8u * d) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  if (threadIdx.x >= 32) {   // bulk-copy producer and factorisation helper
-    producer_warp(prm, bt, T.ring_sa, T.bars_sa, nst_s);
-    return;
-  }
+  __syncwarp();
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = tile0 + atomicAdd(queue, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= tiles) break;
-    if (prm.fast) run_tile<true>(prm, bt, tile, T, nst_s);
-    else run_tile<false>(prm, bt, tile, T, nst_s);
+    run_tile<FAST>(prm, bt, tile, T, nst_s);
     __syncwarp();
   }
-  if (lane == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(T.bars_sa + 32u + 16u + 12u), "r"(CMD_EXIT) : "memory");
-  asm volatile("bar.arrive 1, 64;" ::: "memory");
 }
 
 // compute_trajectory_data / integrate_dynamics_trajectory (one thread per instance and knot)
@@ -229,9 +223,9 @@ struct cmpc_handle_s {
   int device;
   int num_sms;
   Batch bt;          // device pointers
-  double* gtab;      // general friction-row table (used when the fast path does not apply)
   int tiles;
-  long smem_max;
+  long smem_max, smem_sm;
+  cudaStream_t last_stream;
   void* ws;          // one allocation
   long ws_bytes;
   int* queue;
@@ -254,22 +248,36 @@ const char* cmpc_version(void) { return "cmpc_b200 0.1.0 (sm_100a)"; }
 int64_t cmpc_launch_count(void) { return g_launches.load(); }
 void cmpc_default_qp_settings(cmpc_qp_settings* s) { default_qp_settings(s); }
 
+// every error path after the allocation releases the handle
+static int create_fail(cmpc_handle h, int code, const std::string& msg) {
+  if (h) {
+    if (h->ws) cudaFree(h->ws);
+    free(h);
+  }
+  return fail(code, msg);
+}
+#define CREATE_TRY(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) return create_fail(h, -100 - (int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
 int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   if (!dims || !out) return fail(-1, "null argument");
   if (dims->N < 1 || dims->nc < 1 || dims->nc > MAXC || dims->batch < 1) return fail(-1, "bad dims");
   cmpc_handle h = (cmpc_handle)calloc(1, sizeof(cmpc_handle_s));
+  if (!h) return fail(-1, "out of host memory");
   h->dims = *dims;
-  CUDA_TRY(cudaGetDevice(&h->device));
-  CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  CREATE_TRY(cudaGetDevice(&h->device));
+  CREATE_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   const int B = dims->batch, N = dims->N;
-  WsSizes w = ws_sizes(B, N);
-  const long nd = w.ws + w.gtab + w.info;
+  WsSizes w = ws_sizes(B, N, dims->nc);
+  const long nd = w.ws + w.info;
   const long ni = w.nst + 3L * B + 64;
   h->ws_bytes = nd * 8 + ni * 4;
-  CUDA_TRY(cudaMalloc(&h->ws, h->ws_bytes));
+  CREATE_TRY(cudaMalloc(&h->ws, h->ws_bytes));
   double* d = (double*)h->ws;
   h->bt.ws = d; d += w.ws;        // 256-byte aligned records first
-  h->gtab = d; d += w.gtab;
   h->bt.info = d; d += w.info;
   int* ip = (int*)d;
   h->bt.nst = ip; ip += w.nst;
@@ -278,11 +286,16 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   h->d_nfac = ip; ip += B;
   h->queue = ip;
   h->tiles = (int)w.tiles;
-  int smem_optin = 0;
-  CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  int smem_optin = 0, smem_sm = 0;
+  CREATE_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  CREATE_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
   h->smem_max = smem_optin;
-  if (scp_smem_bytes(N) > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
-  CUDA_TRY(cudaFuncSetAttribute(cmpc_scp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scp_smem_bytes(N)));
+  h->smem_sm = smem_sm;
+  if (scp_smem_bytes(N, true) > h->smem_max) return create_fail(h, -3, "horizon too long for the shared-memory slot table");
+  // the attribute is per function and device: always the device maximum, so that handles with different
+  // horizons can be alive at the same time
+  CREATE_TRY(cudaFuncSetAttribute(cmpc_scp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CREATE_TRY(cudaFuncSetAttribute(cmpc_scp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
   h->bt.B = B;
   h->bt.plan_stride = dims->shared_plan ? 0 : 1;
   *out = h;
@@ -323,29 +336,37 @@ int cmpc_set_friction_ub(cmpc_handle h, const double* friction_ub) {
   return 0;
 }
 
-// launches the solver for the tiles [tile0, tile1) of the bound batch on `st`; `slot` picks the queue counter
-static int launch_tiles(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
-                        double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, int tile0,
-                        int tile1, int slot, cudaStream_t st) {
+// launches the solver for the tiles [tile0, tile1) of the batch `bt_in` on `st`; `slot` picks the queue counter
+static int launch_tiles(cmpc_handle h, const Batch& bt_in, const cmpc_model* model, const cmpc_scp_params* scp,
+                        const cmpc_qp_settings* qp, double* X_out, double* U_out, int32_t* scp_iters, int32_t* status,
+                        int32_t* n_accepted, int tile0, int tile1, int slot, cudaStream_t st) {
   Params prm;
-  int rc = fill_params(&prm, &h->dims, &h->model, scp, qp, h->bt.cR == nullptr);
+  cmpc_qp_settings dq;
+  if (!qp && bt_in.fub) {   // upper bounds on the friction rows (stochastic mode): the polish needs more
+    default_qp_settings(&dq);   // multiplier sweeps and active-set rounds to certify
+    dq.polish_refine_iter = 10;
+    dq.polish_active_set_rounds = 19;
+    qp = &dq;
+  }
+  int rc = fill_params(&prm, &h->dims, model, scp, qp, bt_in.cR == nullptr);
   if (rc) return fail(rc, rc == -2 ? "cost weights must be positive" : "bad dims");
-  Batch bt = h->bt;
+  Batch bt = bt_in;
   if (bt.fub) prm.fast = 0;   // upper bounds live in the general friction table
-  bt.gtab = prm.fast ? nullptr : h->gtab;
+  bt.rfields = rec_fields(h->dims.nc, !prm.fast);
   bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = (int*)scp_iters; bt.status = (int*)status;
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
   CUDA_TRY(cudaMemsetAsync(h->queue + slot, 0, sizeof(int), st));
-  const long smem = scp_smem_bytes(h->dims.N);
+  const long smem = scp_smem_bytes(h->dims.N, !prm.fast);
   if (smem > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
-  int per_sm = (int)(h->smem_max / (smem + 1024));   // 1 KB per block is reserved by the driver
+  int per_sm = (int)(h->smem_sm / (smem + 1024));   // 1 KB per block is reserved by the driver
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;                        // 255 registers per thread
+  if (per_sm > 8) per_sm = 8;                        // registers: __launch_bounds__(32, 8)
   int blocks = tile1 - tile0;
   const int cap = h->num_sms * per_sm;
   if (blocks > cap) blocks = cap;
-  cmpc_scp_kernel<<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
+  if (prm.fast) cmpc_scp_kernel<true><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
+  else cmpc_scp_kernel<false><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -355,15 +376,18 @@ int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_sett
                    double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted, void* stream) {
   if (!h || !scp || !X_out || !U_out || !scp_iters || !status) return fail(-1, "null argument");
   if (!h->have_problem) return fail(-2, "cmpc_set_problem has not been called");
-  return launch_tiles(h, scp, qp, X_out, U_out, scp_iters, status, n_accepted, 0, h->tiles, 0, (cudaStream_t)stream);
+  h->last_stream = (cudaStream_t)stream;
+  return launch_tiles(h, h->bt, &h->model, scp, qp, X_out, U_out, scp_iters, status, n_accepted, 0, h->tiles, 0,
+                      (cudaStream_t)stream);
 }
 
-int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info) {
+int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info, void* stream) {
   if (!h) return fail(-1, "null handle");
   const int B = h->dims.batch;
-  if (qp_iters) CUDA_TRY(cudaMemcpy(qp_iters, h->d_qpit, B * sizeof(int), cudaMemcpyDeviceToDevice));
-  if (n_factor) CUDA_TRY(cudaMemcpy(n_factor, h->d_nfac, B * sizeof(int), cudaMemcpyDeviceToDevice));
-  if (info) CUDA_TRY(cudaMemcpy(info, h->bt.info, (long)B * INFO * sizeof(double), cudaMemcpyDeviceToDevice));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (qp_iters) CUDA_TRY(cudaMemcpyAsync(qp_iters, h->d_qpit, B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (n_factor) CUDA_TRY(cudaMemcpyAsync(n_factor, h->d_nfac, B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (info) CUDA_TRY(cudaMemcpyAsync(info, h->bt.info, (long)B * INFO * sizeof(double), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -373,6 +397,8 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
                         const double* contact_R, const int32_t* contact_active, double* X_out,
                         double* U_out, int32_t* scp_iters, int32_t* status, int32_t* n_accepted) {
   if (!h || !model || !scp) return fail(-1, "null argument");
+  if (!x_init || !x_final || !X_ref || !U_init || !contact_pos || !contact_active || !X_out || !U_out || !scp_iters || !status)
+    return fail(-1, "null argument");
   const int B = h->dims.batch, N = h->dims.N, nc = h->dims.nc, nu = 3 * nc;
   const long Bp = h->dims.shared_plan ? 1 : B;
   const long n_xi = (long)B * 9, n_X = (long)B * (N + 1) * 9, n_U = (long)B * N * nu;
@@ -382,11 +408,13 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   const long out_bytes = (n_X + n_U) * 8 + 3L * B * 4;
   if (!h->d_in || h->in_bytes < in_bytes) {
     if (h->d_in) cudaFree(h->d_in);
+    h->d_in = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_in, in_bytes));
     h->in_bytes = in_bytes;
   }
   if (!h->d_out || h->out_bytes < out_bytes) {
     if (h->d_out) cudaFree(h->d_out);
+    h->d_out = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_out, out_bytes));
     h->out_bytes = out_bytes;
   }
@@ -406,16 +434,20 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   if (contact_R) CUDA_TRY(cudaMemcpyAsync(dcR, contact_R, n_cR * 8, cudaMemcpyHostToDevice, s0));
   CUDA_TRY(cudaMemcpyAsync(dca, contact_active, n_ca * 4, cudaMemcpyHostToDevice, s0));
   CUDA_TRY(cudaEventRecord(h->ev_small, s0));
-  int rc = cmpc_set_problem(h, model, dxi, dxf, dX, dU, dcp, contact_R ? dcR : nullptr, dca);
-  if (rc) return rc;
+  // a private view of the batch over the staging buffers: the problem bound with cmpc_set_problem (and the
+  // friction upper bounds, which are device data of the caller) stays as it is
+  Batch bt = h->bt;
+  bt.x_init = dxi; bt.x_final = dxf; bt.X_ref = dX; bt.U_init = dU;
+  bt.cpos = dcp; bt.cR = contact_R ? dcR : nullptr; bt.cact = dca;
   double* oX = (double*)h->d_out;
   double* oU = oX + n_X;
   int* oi = (int*)(oU + n_U);
   // Chunks of whole tiles: the trajectories of chunk c+1 are uploaded and the results of chunk c-1 are
-  // downloaded while chunk c is being solved; with one tile per SM the chunks' kernels run side by side.
+  // downloaded while chunk c is being solved.
   const int tiles = h->tiles;
   int chunks = tiles >= 4 * MAX_CHUNKS ? MAX_CHUNKS : (tiles >= 8 ? 4 : 1);
   const int per = (tiles + chunks - 1) / chunks;
+  int rc = 0;
   for (int c = 0; c < chunks; ++c) {
     const int t0 = c * per, t1 = (c + 1) * per < tiles ? (c + 1) * per : tiles;
     if (t0 >= t1) break;
@@ -425,8 +457,8 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
     const long xo = b0 * (N + 1) * 9, uo = b0 * N * nu;
     CUDA_TRY(cudaMemcpyAsync(dX + xo, X_ref + xo, nb * (N + 1) * 9 * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dU + uo, U_init + uo, nb * N * nu * 8, cudaMemcpyHostToDevice, st));
-    rc = launch_tiles(h, scp, qp, oX, oU, oi, oi + B, oi + 2 * B, t0, t1, c, st);
-    if (rc) return rc;
+    rc = launch_tiles(h, bt, model, scp, qp, oX, oU, oi, oi + B, oi + 2 * B, t0, t1, c, st);
+    if (rc) break;
     CUDA_TRY(cudaMemcpyAsync(X_out + xo, oX + xo, nb * (N + 1) * 9 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(U_out + uo, oU + uo, nb * N * nu * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(scp_iters + b0, oi + b0, nb * 4, cudaMemcpyDeviceToHost, st));
@@ -434,7 +466,7 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
     if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted + b0, oi + 2 * B + b0, nb * 4, cudaMemcpyDeviceToHost, st));
   }
   for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(h->cs[c]));
-  return 0;
+  return rc;
 }
 
 static int lin_common(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,

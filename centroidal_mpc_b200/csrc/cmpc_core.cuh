@@ -18,9 +18,11 @@
 #if defined(__CUDACC__)   // the solver is device code in the CUDA build, host code in the test build (g++)
 #define CMPC_HD __device__ __forceinline__
 #define CMPC_FN __device__ __forceinline__
+#define CMPC_CX __host__ __device__ constexpr inline
 #else
 #define CMPC_HD inline
 #define CMPC_FN
+#define CMPC_CX constexpr inline
 #endif
 
 namespace cmpc {
@@ -28,53 +30,75 @@ namespace cmpc {
 constexpr int NX = 9;
 constexpr int MAXC = 4;    // contacts
 constexpr int MAXU = 12;   // 3 * MAXC
+// Execution model: NL lanes of a warp cooperate on one MPC instance (each lane owns rows of the
+// knot's small dense systems; vectors that every lane needs are exchanged through shared memory
+// and __syncwarp), TL = 32 / NL instances share a warp ("a tile").  Every output element is
+// computed by exactly one lane with a fixed operation order and cross-lane reductions are only
+// max / or / integer sums, so the results are bit-identical for every NL -- the host build runs
+// NL = 1 (tests/emu) and a lock-step host build runs NL = 8 (tests/emu, coroutines).
+#ifndef CMPC_NL
+#if defined(__CUDACC__)
+#define CMPC_NL 8
+#else
+#define CMPC_NL 1
+#endif
+#endif
+constexpr int NL = CMPC_NL;
 #ifndef CMPC_TL
-#define CMPC_TL 32
+#if defined(__CUDACC__)
+#define CMPC_TL (32 / CMPC_NL)
+#else
+#define CMPC_TL 4
 #endif
-constexpr int TL = CMPC_TL;   // instances per tile (lanes of the warp that carry an instance)
+#endif
+constexpr int TL = CMPC_TL;   // instances per tile
 
-// ---- knot record: REC doubles per instance and knot.  A tile's workspace is
-// [N+1 knots][REC fields][TL lanes]; field f of lane l at knot k lives at ((k*REC + f)*TL + l).
-// "slot" = position of a contact among the knot's ACTIVE contacts; controls (3 per slot) and
-// friction rows (4 per slot) are stored compactly by slot.  The number of slots of a knot is
-// tile-uniform (the maximum over the tile's lanes); a lane with fewer active contacts pads with
-// slots whose B columns are zero, which leaves exact zeros in their controls.
-// Fields are grouped into SEGMENTS, the units the sweeps stage into shared memory with one bulk
-// copy each (cp.async.bulk); variable-length fields sit at the end of their segment so that only
-// the used prefix (a function of the knot's slot count) is moved.
-//   A  Pc, Hinv          factor -> backward sweep
-//   B  K                 factor -> both sweeps
-//   C  meta, xbar, S, ck, d      stage data, constant during a solve
-//   D  vk, vf            ADMM iterate
-//   E  d_k               backward -> forward sweep
-//   F  yk, yf            multiplier method
-constexpr int R_PC = 0;      // Pc[9]      = P_{k+1} c_k
-constexpr int R_HI = 9;      // Hinv       packed lower triangle (j,l), l <= j, at j(j+1)/2 + l   (78)
-constexpr int R_K = 87;      // K[j*9+i]   feedback gain, na x 9                                   (108)
-constexpr int R_META = 195;  // 2*TL int32: [lane] meta (bits 0..2 slots, 4..11 contact id per slot), [TL+lane] active set
-constexpr int R_XB = 196;    // xbar[9]    linearisation point: q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
-constexpr int R_S = 205;     // S[3]       sum of active fbar:  A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
-constexpr int R_CK = 208;    // ck[3]      affine term rows 6..8: -dt S x cbar (row 5 is dt m g)
-constexpr int R_D = 211;     // d[slot][3] = p_contact - cbar:  B_k[:,3s:3s+3] = dt [0; I; [d]x]
-constexpr int R_VK = 223;    // vk[3]           kappa copy:    w = prox(v),  y = rho_k (v - w)
-constexpr int R_VF = 226;    // vf[4*slot+row]  friction rows: w = min(v,0), y = rho e2 max(v,0)
-constexpr int R_DV = 242;    // feed-forward d_k (compact, 12)
-constexpr int R_YK = 254;    // multiplier method: yk[4]  (3 pins + surface row)
-constexpr int R_YF = 258;    //                    yf[16] (compact rows)
-constexpr int R_X = 274;     // solution x[9]
-constexpr int R_U = 283;     // solution u[12] (compact)
-constexpr int REC = 296;     // 2368 bytes per instance and knot
-constexpr int R_STAGED = 274;  // fields [0, R_STAGED) can be staged by the sweeps
-constexpr int SEG_A = 1, SEG_B = 2, SEG_C = 4, SEG_D = 8, SEG_E = 16, SEG_F = 32;
+// ---- knot record.  A tile's workspace is [N+1 knots][rstride doubles]; field f of instance-lane t
+// at knot k lives at k*rstride + f*TL + t, so the TL values of a field are one contiguous 8*TL-byte
+// row and a range of fields is one contiguous block (one cp.async.bulk).  The field offsets depend on
+// the knot's slot count ns ("slot" = position of a contact among the knot's ACTIVE contacts; tile-
+// uniform: the maximum over the tile's instances, an instance with fewer active contacts pads with
+// slots whose B columns are zero) and on whether the general friction table is present (gen):
+//   A  Pc[9]                       factor -> backward sweep            P_{k+1} c_k
+//   M  Hn[na*na], Kt[9*na]         factor -> sweeps     Hn = -Huu^-1 (full square), Kt[i*na+j] = K[j][i]
+//   C  meta, xbar[9], S[3], ck[3], d[na]     stage data, constant during a solve
+//   G  per slot G[12] e2[4] ub[4]            general friction rows (rotated contacts / stochastic mode)
+//   D  vk[3], vf[4 ns]             ADMM iterate
+//   E  dv[na]                      backward -> forward sweep (feed-forward)
+//   F  yk[4], yf[4 ns]             multiplier method
+//   -  x[9], u[na]                 solution
+// The order makes the fields of the ADMM sweeps contiguous: backward = [A .. D], forward = [Kt .. E].
+struct Lay {
+  int na, pc, hn, kt, meta, xb, s, ck, d, g, vk, vf, dv, yk, yf, x, u, end;
+};
+CMPC_CX Lay lay_of(int ns, bool gen) {
+  Lay L{};
+  L.na = 3 * ns;
+  L.pc = 0;
+  L.hn = 9;
+  L.kt = L.hn + L.na * L.na;
+  L.meta = L.kt + 9 * L.na;   // one field = 2*TL int32: [t] meta (bits 0..2 slots, 4..11 contact id per slot), [TL+t] active set
+  L.xb = L.meta + 1;          // xbar[9]: linearisation point, q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
+  L.s = L.xb + 9;             // S[3]: sum of active fbar, A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
+  L.ck = L.s + 3;             // ck[3]: affine term rows 6..8, -dt S x cbar (row 5 is dt m g)
+  L.d = L.ck + 3;             // d[slot][3] = p_contact - cbar: B_k[:,3s:3s+3] = dt [0; I; [d]x]
+  L.g = L.d + L.na;
+  L.vk = L.g + (gen ? 20 * ns : 0);   // vk[3]: kappa copy, w = prox(v), y = rho_k (v - w)
+  L.vf = L.vk + 3;            // vf[4*slot+row]: friction rows, w = min(v,0), y = rho e2 max(v,0)
+  L.dv = L.vf + 4 * ns;
+  L.yk = L.dv + L.na;         // multiplier method: yk[4] (3 pins + surface row)
+  L.yf = L.yk + 4;            //                    yf[4 ns]
+  L.x = L.yf + 4 * ns;
+  L.u = L.x + 9;
+  L.end = L.u + L.na;
+  return L;
+}
 constexpr int GS = 20;       // general friction table, per slot: G (12, row-major 4x3), e2 (4), upper bound (4)
-constexpr int GT = 4 * GS;   // ... per knot
+CMPC_CX int rec_fields(int nc, bool gen) { return (lay_of(nc, gen).end + 3) & ~3; }
+constexpr int REC_MAX = rec_fields(MAXC, true);
 constexpr int INFO = 12;     // per-instance statistics (cmpc_get_stats)
-#ifndef CMPC_RING_DEPTH
-#define CMPC_RING_DEPTH 2
-#endif
-constexpr int RING_DEPTH = CMPC_RING_DEPTH;  // knots in flight per tile
 
-enum Status { ST_OK = 0, ST_QP_MAXITER = 1, ST_QP_NUMERIC = 2 };
+enum Status { ST_OK = 0, ST_QP_MAXITER = 1, ST_QP_NUMERIC = 2, ST_DEVICE = 3 };
 
 struct Params {
   int N, nc, nu, identity_R, fast;   // fast: identity R and the same W_u for every contact
@@ -103,8 +127,8 @@ struct Batch {
   long plan_stride;       // 0 (shared plan) or 1
   const double* fub;      // [B][N][nc][4] friction-row upper bounds (stochastic mode) or null (all zero)
   // workspace
-  double* ws;             // [tiles][N+1][REC][32]
-  double* gtab;           // [tiles][N][GT][32]   general friction rows; null on the fast path
+  double* ws;             // [tiles][N+1][rfields][TL]
+  int rfields;            // fields per knot record (rec_fields(nc, gen))
   int* nst;               // [tiles][N+1]         slots per knot of the tile
   // outputs
   double* X_out;          // [B][N+1][9]
@@ -126,8 +150,8 @@ CMPC_HD void cross3(const double* a, const double* b, double* o) {
   o[1] = a[2] * b[0] - a[0] * b[2];
   o[2] = a[0] * b[1] - a[1] * b[0];
 }
-CMPC_HD constexpr int nxt3(int a) { return a == 2 ? 0 : a + 1; }
-CMPC_HD constexpr int prv3(int a) { return a == 0 ? 2 : a - 1; }
+CMPC_CX int nxt3(int a) { return a == 2 ? 0 : a + 1; }
+CMPC_CX int prv3(int a) { return a == 0 ? 2 : a - 1; }
 
 // K1: closed-form Jacobian data and affine term of one knot
 //     (centroidal_model.py:189-232), point-contact model:

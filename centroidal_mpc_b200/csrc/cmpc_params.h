@@ -72,13 +72,15 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   return 0;
 }
 
-// workspace sizes for a batch: doubles of the knot records / friction table, ints of the slot table
-struct WsSizes { long tiles, ws, gtab, nst, info; };
-inline WsSizes ws_sizes(int B, int N) {
+// workspace sizes for a batch: doubles of the knot records, ints of the slot table.  The records are
+// allocated for the general layout of the problem's contact count (friction table included), so that a
+// handle can switch between the nominal and the stochastic / rotated-contact path without reallocating.
+struct WsSizes { long tiles, ws, nst, info; int rfields; };
+inline WsSizes ws_sizes(int B, int N, int nc) {
   WsSizes w;
   w.tiles = (B + TL - 1) / TL;
-  w.ws = w.tiles * (N + 1) * (long)(REC * TL);
-  w.gtab = w.tiles * N * (long)(GT * TL);
+  w.rfields = rec_fields(nc, true);
+  w.ws = w.tiles * (N + 1) * (long)(w.rfields * TL);
   w.nst = w.tiles * (N + 1);
   w.info = (long)B * INFO;
   return w;

@@ -1,17 +1,20 @@
-// cmpc_tile.cuh — the SCP solver of one MPC instance, written as plain scalar code that runs
-// once per LANE: Riccati factorisation, ADMM / multiplier-method sweeps, certified active-set
-// polish, trust-region loop.  32 instances (a tile) share a warp; each lane walks its own
-// column of the lane-interleaved knot records (cmpc_core.cuh), so every load and store of the
-// warp is one coalesced 256-byte access and no lane ever talks to another.  DESIGN.md "device
-// algorithm" has the mathematics; oracle/device_model.py is the executable numpy specification.
+// cmpc_tile.cuh — the SCP solver of one MPC instance: Riccati factorisation, ADMM / multiplier-
+// method sweeps, certified active-set polish, trust-region loop.
 //
-// Control flow: every lane owns a small state machine (advance()) that names the next whole-
+// Execution model (cmpc_core.cuh): NL lanes of a warp form the TEAM of one instance, TL = 32 / NL
+// instances (a tile) share the warp.  Every per-knot operation is written "owner computes": lane q
+// of the team owns the rows q, q + NL, ... of the knot's small dense systems, vectors that every
+// lane needs (u, hu, p, the pivot column) go through a few shared-memory words per instance and a
+// __syncwarp.  An output element is produced by exactly one lane with a fixed operation order and
+// the only cross-lane reductions are max / or / integer sums, so the results do not depend on NL:
+// the host build (tests/emu) runs NL = 1, a lock-step host build runs NL = 8 on coroutines, and
+// both are bit-identical to the GPU (FMA contraction is explicit, automatic contraction is off).
+// Scalars of the driver state machine are replicated in the lanes of a team.
+//
+// Control flow: every instance owns a small state machine (advance()) that names the next whole-
 // horizon operation it needs (factorise, sweep, build active set, evaluate, ...).  The warp
-// executes one operation at a time for the lanes that asked for it (run_tile in cmpc_api.cu),
-// so lanes whose QPs need more iterations or polish rounds do not change what the others
-// compute.  The host build (tests/emu) runs the same state machine one lane at a time: the
-// arithmetic of a lane does not depend on its neighbours, so both builds are bit-identical
-// (FMA contraction is explicit, automatic contraction is off in both).
+// executes one operation at a time for the instances that asked for it (run_tile in cmpc_api.cu).
+// DESIGN.md "device algorithm" has the mathematics; oracle/device_model.py is the numpy model.
 #pragma once
 #include "cmpc_core.cuh"
 
@@ -21,102 +24,184 @@ constexpr int MODE_ADMM = 0, MODE_PMM = 1;
 // forward-sweep kinds
 constexpr int FW_ADMM = 0, FW_ADMM_CHECK = 1, FW_PMM = 2, FW_COPY = 4;
 
-#define CMPC_R(p, f) (p)[(f) * TL]
-// Staged data (what a KnotStream hands out) and per-lane scratch live in shared memory on the
-// device and are addressed by their 32-bit shared-space byte address through explicit
-// ld/st.shared (the compiler cannot see the address space through the ring bookkeeping, and
-// generic accesses cost a long-scoreboard round trip); in the host build they are plain pointers.
-// A StagedPtr addresses field BASE of the current knot for this lane (BASE = first field the
-// operation stages; a constexpr in the scope of every user of CMPC_S).
+// ---------------------------------------------------------------- staged ranges of the streamed operations
+// A streamed operation walks the knots; per knot it stages one or two contiguous field ranges of the
+// record into a ring slot (one cp.async.bulk each).  so() maps a record field to its slot position.
+enum StreamKind { SK_FAC_ADMM = 0, SK_FAC_PMM, SK_BWD_ADMM, SK_BWD_PMM, SK_FWD_ADMM, SK_FWD_PMM, SK_FWD_COPY };
+struct Ranges { int s1, e1, s2, e2; };
+CMPC_CX Ranges ranges_of(int sk, int ns, bool gen) {
+  const Lay L = lay_of(ns, gen);
+  return sk == SK_FAC_ADMM ? Ranges{L.meta, L.vk, 0, 0}
+       : sk == SK_FAC_PMM  ? Ranges{L.meta, L.vk, L.yk, L.x}
+       : sk == SK_BWD_ADMM ? Ranges{0, L.dv, 0, 0}
+       : sk == SK_BWD_PMM  ? Ranges{0, L.vk, L.yk, L.x}
+       : sk == SK_FWD_ADMM ? Ranges{L.kt, L.yk, 0, 0}
+       : sk == SK_FWD_PMM  ? Ranges{L.kt, L.vk, L.dv, L.x}
+                           : Ranges{L.kt, L.vk, L.dv, L.yk};
+}
+CMPC_CX int slot_fields(int sk, bool gen) {
+  const Ranges R = ranges_of(sk, MAXC, gen);
+  return (R.e1 - R.s1) + (R.e2 - R.s2);
+}
+CMPC_CX int imax(int a, int b) { return a > b ? a : b; }
+CMPC_CX int imin(int a, int b) { return a < b ? a : b; }
+// per-instance scratch words (exchange vectors of the sweeps, tableau data of the factorisation)
+constexpr int X_PX = 0;            // p, double-buffered   [2][9]
+constexpr int X_UX = 18;           // u / hu               [12]
+constexpr int X_KX = 30;           // kappa terms          [12]  (kl 3 | kM 9)
+constexpr int X_DX = 42;           // friction residual terms of a CHECK sweep [16]
+constexpr int X_RX = 58;           // team reductions of the host lock-step build [NL]
+constexpr int X_COMMON = 58 + 8;
+constexpr int X_CX = X_COMMON;     // factorisation: pivot column, double-buffered [2][21]
+constexpr int X_PS = X_CX + 42;    // P (full square 9 x 9)
+constexpr int X_Y = X_PS + 81;     // Y = P [B A]  (9 x (na + 9))
+constexpr int X_FAC_END = X_Y + 9 * 21;
+// shared memory of a tile (in field rows of TL doubles): common scratch, then a region that holds the
+// ring of a sweep or the factorisation scratch plus its small ring
+CMPC_CX int ring_fields(bool gen) { return 2 * imax(slot_fields(SK_BWD_ADMM, gen), slot_fields(SK_BWD_PMM, gen)); }
+CMPC_CX int ring_depth(int sk, bool gen) {
+  const int avail = (sk == SK_FAC_ADMM || sk == SK_FAC_PMM) ? ring_fields(gen) - (X_FAC_END - X_COMMON) : ring_fields(gen);
+  return imin(4, imax(2, avail / slot_fields(sk, gen)));
+}
+CMPC_CX int ring_base(int sk) { return (sk == SK_FAC_ADMM || sk == SK_FAC_PMM) ? X_FAC_END : X_COMMON; }
+CMPC_CX int tile_smem_fields(bool gen) { return X_COMMON + ring_fields(gen); }
+static_assert(X_FAC_END - X_COMMON + 2 * slot_fields(SK_FAC_PMM, true) <= ring_fields(true), "factor scratch");
+static_assert(X_FAC_END - X_COMMON + 2 * slot_fields(SK_FAC_PMM, false) <= ring_fields(false), "factor scratch");
+
+#ifndef CMPC_PF
+#define CMPC_PF 4   // knots of L2 prefetch ahead of the ring
+#endif
+
+// ---------------------------------------------------------------- memory spaces
+// Device: staged data and scratch live in shared memory and are addressed by 32-bit shared-space byte
+// addresses through explicit ld/st.shared (generic accesses cost a long-scoreboard round trip).
+// Host build: plain pointers; "staged" data is the global record itself.
 #if defined(__CUDACC__)
 typedef unsigned StagedPtr;
 typedef unsigned ScratchPtr;
-CMPC_HD double staged_ld(StagedPtr p, int idx) {
+CMPC_HD double sp_ld(unsigned p, int e) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p + (unsigned)idx * 8u));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p + (unsigned)e * (TL * 8u)));
   return v;
 }
-template <int BASE>
-CMPC_HD int staged_meta(StagedPtr p, int lane, int which) {   // which: 0 meta word, 1 active-set word
+CMPC_HD void sp_st(unsigned p, int e, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(p + (unsigned)e * (TL * 8u)), "d"(v) : "memory");
+}
+CMPC_HD int sp_ldi(unsigned p, int e, int t, int which) {   // int32 pair field: [t] word 0, [TL + t] word 1
   int v;
-  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(p - (unsigned)lane * 8u + (unsigned)((R_META - BASE) * TL * 8 + (which * TL + lane) * 4)));
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(p - (unsigned)t * 8u + (unsigned)e * (TL * 8u) + (unsigned)(which * TL + t) * 4u));
   return v;
-}
-CMPC_HD double sc_ld(ScratchPtr t, int idx) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(t + (unsigned)idx * 8u));
-  return v;
-}
-CMPC_HD void sc_st(ScratchPtr t, int idx, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(t + (unsigned)idx * 8u), "d"(v) : "memory");
 }
 #else
 typedef const double* StagedPtr;
 typedef double* ScratchPtr;
-CMPC_HD double staged_ld(StagedPtr p, int idx) { return p[idx]; }
-template <int BASE>
-CMPC_HD int staged_meta(StagedPtr p, int lane, int which) {
-  return (reinterpret_cast<const int*>(p - lane + (R_META - BASE) * TL) + lane)[which * TL];
+CMPC_HD double sp_ld(const double* p, int e) { return p[(long)e * TL]; }
+CMPC_HD void sp_st(double* p, int e, double v) { p[(long)e * TL] = v; }
+CMPC_HD int sp_ldi(const double* p, int e, int t, int which) {
+  return (reinterpret_cast<const int*>(p - t + (long)e * TL))[which * TL + t];
 }
-CMPC_HD double sc_ld(ScratchPtr t, int idx) { return t[idx]; }
-CMPC_HD void sc_st(ScratchPtr t, int idx, double v) { t[idx] = v; }
 #endif
-#define CMPC_S(p, f) staged_ld(p, ((f) - BASE) * TL)
+#define CMPC_R(p, f) (p)[(long)(f) * TL]
+
+// ---------------------------------------------------------------- team primitives
+struct Inst {
+  int b, lane, sub;   // batch index, instance lane t within the tile, lane q within the team
+  const double *Xr, *Ui, *xi, *xf, *cpos, *cR, *fub;
+  const int* cact;
+};
+#if defined(__CUDACC__)
+CMPC_HD void team_sync(const Inst&) { if (NL > 1) __syncwarp(); }
+CMPC_HD double team_max(const Inst&, ScratchPtr, double v) {
+#pragma unroll
+  for (int m = TL; m < 32; m <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+CMPC_HD int team_or(const Inst&, ScratchPtr, int v) {
+#pragma unroll
+  for (int m = TL; m < 32; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+CMPC_HD int team_sum(const Inst&, ScratchPtr, int v) {
+#pragma unroll
+  for (int m = TL; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+#elif CMPC_NL == 1
+CMPC_HD void team_sync(const Inst&) {}
+CMPC_HD double team_max(const Inst&, ScratchPtr, double v) { return v; }
+CMPC_HD int team_or(const Inst&, ScratchPtr, int v) { return v; }
+CMPC_HD int team_sum(const Inst&, ScratchPtr, int v) { return v; }
+#else
+// lock-step host build: the NL lanes of a team are coroutines; cmpc_emu_yield() returns when every
+// lane of the team has reached its own yield (tests/emu/cmpc_emu.cpp)
+void cmpc_emu_yield();
+CMPC_HD void team_sync(const Inst&) { cmpc_emu_yield(); }
+CMPC_HD double team_max(const Inst& I, ScratchPtr xs, double v) {
+  sp_st(xs, X_RX + I.sub, v);
+  cmpc_emu_yield();
+  double m = sp_ld(xs, X_RX);
+  for (int q = 1; q < NL; ++q) m = fmax(m, sp_ld(xs, X_RX + q));
+  cmpc_emu_yield();
+  return m;
+}
+CMPC_HD int team_or(const Inst& I, ScratchPtr xs, int v) {
+  sp_st(xs, X_RX + I.sub, (double)(unsigned)v);
+  cmpc_emu_yield();
+  unsigned m = 0;
+  for (int q = 0; q < NL; ++q) m |= (unsigned)sp_ld(xs, X_RX + q);
+  cmpc_emu_yield();
+  return (int)m;
+}
+CMPC_HD int team_sum(const Inst& I, ScratchPtr xs, int v) {
+  sp_st(xs, X_RX + I.sub, (double)v);
+  cmpc_emu_yield();
+  int m = 0;
+  for (int q = 0; q < NL; ++q) m += (int)sp_ld(xs, X_RX + q);
+  cmpc_emu_yield();
+  return m;
+}
+#endif
+CMPC_HD int sub_of(const Inst& I) { return NL == 1 ? 0 : I.sub; }
 
 struct TileCtx {
-  const Params* prm;
-  double* ws;      // tile workspace [N+1][REC][TL]
-  double* gt;      // tile friction table [N][GT][TL], null on the fast path
+  double* ws;      // tile workspace [N+1][rfields][TL]
+  long rstride;    // doubles per knot record (rfields * TL)
   int* nst;        // [N+1] slots per knot (tile maximum; 0 at the terminal knot), global memory
+  int gen;         // general friction table present
 #if defined(__CUDACC__)
-  // the warp's shared-memory ring (RING_DEPTH slots of R_STAGED fields), its mbarriers and a
-  // shared copy of nst; all warp-uniform
-  double* ring;
-  unsigned ring_sa, bars_sa, phases;
+  unsigned smem_sa, bars_sa, phases;   // the warp's shared memory (scratch, ring), its mbarriers; warp-uniform
   int tile;
-  const unsigned char* nst_s;
+  const unsigned char* nst_s;          // shared copy of nst
   CMPC_HD int ns(int k) const { return nst_s[k]; }
 #else
+  double* scratch;                     // [X_FAC_END][TL]
   CMPC_HD int ns(int k) const { return nst[k]; }
 #endif
 };
 
-struct Inst {
-  int b, lane;
-  const double *Xr, *Ui, *xi, *xf, *cpos, *cR, *fub;
-  const int* cact;
-};
-
-CMPC_HD double* rec_of(const TileCtx& T, const Inst& I, int k) {
-  return T.ws + (long)k * (REC * TL) + I.lane;
+CMPC_HD double* rec_of(const TileCtx& T, const Inst& I, int k) { return T.ws + (long)k * T.rstride + I.lane; }
+CMPC_HD int* meta_of(const TileCtx& T, const Inst& I, int k, int f_meta) {
+  return reinterpret_cast<int*>(T.ws + (long)k * T.rstride + (long)f_meta * TL) + I.lane;   // [0] meta, [TL] active set
 }
-CMPC_HD int* meta_of(const TileCtx& T, const Inst& I, int k) {
-  return reinterpret_cast<int*>(T.ws + (long)k * (REC * TL) + R_META * TL) + I.lane;   // [0] meta, [TL] active set
+CMPC_HD ScratchPtr scratch_of(const TileCtx& T, const Inst& I) {
+#if defined(__CUDACC__)
+  return T.smem_sa + (unsigned)I.lane * 8u;
+#else
+  return T.scratch + I.lane;
+#endif
 }
-CMPC_HD double* gt_of(const TileCtx& T, const Inst& I, int k) { return T.gt ? T.gt + (long)k * (GT * TL) + I.lane : nullptr; }
 
 // ---------------------------------------------------------------- knot stream
-// Walks the knots of a tile in one direction and hands out a pointer through which the fields
-// of the requested segments of the current knot can be read (CMPC_S(r, field)).
-// Device: a ring of RING_DEPTH shared-memory slots filled by cp.async.bulk (one elected lane,
-// one bulk copy per segment, completion on an mbarrier), so the HBM latency of knot k+3 hides
-// behind the arithmetic of knots k..k+2 and every operand read is a shared-memory read.
+// Walks the knots of a tile in one direction and hands out a pointer through which the staged fields of
+// the current knot can be read.  Device: a ring of DEPTH shared-memory slots filled by cp.async.bulk
+// (lane 0 of the warp issues the copy of knot k + DEPTH when it releases knot k; completion on an
+// mbarrier) plus an L2 prefetch CMPC_PF knots further ahead, so that the HBM latency hides behind
+// the arithmetic of the knots in between and every operand read is a shared-memory read.
 // Host build: the pointer is the global record itself.
-CMPC_HD int seg_start(int seg) {
-  return seg == SEG_A ? R_PC : seg == SEG_B ? R_K : seg == SEG_C ? R_META : seg == SEG_D ? R_VK : seg == SEG_E ? R_DV : R_YK;
-}
-CMPC_HD int seg_len(int seg, int ns) {
-  const int na = 3 * ns;
-  return seg == SEG_A ? 9 + na * (na + 1) / 2 : seg == SEG_B ? 9 * na : seg == SEG_C ? 16 + na
-       : seg == SEG_D ? 3 + 4 * ns : seg == SEG_E ? na : 4 + 4 * ns;
-}
-
 #if defined(__CUDACC__)
 CMPC_HD unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-// commands to the producer warp other than a stream (the descriptor's count field)
-constexpr int CMD_EXIT = -1, CMD_SETUP = -2, CMD_WRITE = -3;
-// bounded wait on an mbarrier phase: a bulk copy that never lands traps instead of hanging
-CMPC_HD void mbar_wait(unsigned bar, unsigned parity) {
+// bounded wait on an mbarrier phase: returns false when the bulk copy never lands
+CMPC_HD bool mbar_wait(unsigned bar, unsigned parity) {
   unsigned done = 0;
   for (unsigned spins = 0; !done; ++spins) {
     asm volatile(
@@ -125,141 +210,108 @@ CMPC_HD void mbar_wait(unsigned bar, unsigned parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spins > (1u << 24)) asm volatile("trap;");
+    if (spins > (1u << 22)) return false;
   }
+  return true;
 }
 
-// solver warp: hand the producer warp the odd knots of a per-knot operation of this tile (mask:
-// the lanes that take part), and wait for it to finish
-CMPC_HD void helper_fork(const TileCtx& T, int cmd, unsigned mask);
-CMPC_HD void helper_join() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
-
+template <int SK, bool GEN>
 struct KnotStream {
-  // copies of the tile's ring description (kept by value so that they live in registers)
+  static constexpr int DEPTH = ring_depth(SK, GEN);
+  static constexpr int SLOTF = slot_fields(SK, GEN);
   unsigned ring_sa, bars_sa, phases;
-  int lane, slot_f, s_wait;
+  int lane, s_wait, k_issue, n_left, dir, s_issue, lost;
+  const double* ws;
+  long rstride;
+  const unsigned char* nst_s;
 
-  // knots k_first, k_first + dir, ... (count of them); fields below base_field are not staged.
-  // The stream is handed to the CTA's producer warp: descriptor in shared memory, named barrier 1.
-  CMPC_HD void open(TileCtx& Tc, const Inst& I, int segments, int base_field, int k_first, int count, int direction) {
-    ring_sa = Tc.ring_sa; bars_sa = Tc.bars_sa; phases = Tc.phases;
-    lane = I.lane; slot_f = R_STAGED - base_field; s_wait = 0;
-    // earlier generic-proxy writes of this warp (records written by the previous operation) must
-    // be visible to the async proxy before the bulk copies read them
+  CMPC_HD void issue() {   // lane 0: knot k_issue into slot s_issue
+    const int k = k_issue;
+    const Ranges R = ranges_of(SK, nst_s[k], GEN);
+    const unsigned b1 = (unsigned)(R.e1 - R.s1) * (TL * 8u), b2 = (unsigned)(R.e2 - R.s2) * (TL * 8u);
+    const unsigned bar = bars_sa + 8u * s_issue;
+    const unsigned dst = ring_sa + (unsigned)(s_issue * SLOTF) * (TL * 8u);
+    const double* src = ws + (long)k * rstride;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b1 + b2) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src + (long)R.s1 * TL), "r"(b1), "r"(bar) : "memory");
+    if (b2)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + b1), "l"(src + (long)R.s2 * TL), "r"(b2), "r"(bar) : "memory");
+    if (CMPC_PF > 0 && n_left > CMPC_PF) {   // L2 prefetch of the knot CMPC_PF further along
+      const int kp = k + CMPC_PF * dir;
+      const Ranges Q = ranges_of(SK, nst_s[kp], GEN);
+      const double* sp = ws + (long)kp * rstride;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp + (long)Q.s1 * TL), "r"((unsigned)(Q.e1 - Q.s1) * (TL * 8u)) : "memory");
+      if (Q.e2 > Q.s2)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp + (long)Q.s2 * TL), "r"((unsigned)(Q.e2 - Q.s2) * (TL * 8u)) : "memory");
+    }
+    k_issue += dir;
+    --n_left;
+    s_issue = (s_issue + 1 == DEPTH) ? 0 : s_issue + 1;
+  }
+  // knots k_first, k_first + dir, ... (count of them)
+  CMPC_HD void open(TileCtx& Tc, const Inst& I, int k_first, int count, int direction) {
+    ring_sa = Tc.smem_sa + (unsigned)ring_base(SK) * (TL * 8u);
+    bars_sa = Tc.bars_sa; phases = Tc.phases;
+    lane = I.lane; s_wait = 0; s_issue = 0; k_issue = k_first; n_left = count; dir = direction; lost = 0;
+    ws = Tc.ws; rstride = Tc.rstride; nst_s = Tc.nst_s;
+    // earlier generic-proxy writes of this warp (records written by the previous operation) must be
+    // visible to the async proxy before the bulk copies read them
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncwarp();
-    if ((threadIdx.x & 31u) == 0) {   // (lane is the instance's lane, which wraps for tiles narrower than a warp)
-      const unsigned c = bars_sa + 32u;
-      asm volatile("st.shared.u64 [%0], %1;" ::"r"(c), "l"(Tc.ws) : "memory");
-      asm volatile("st.shared.s32 [%0], %1;" ::"r"(c + 8u), "r"(direction) : "memory");
-      asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(c + 16u), "r"(segments), "r"(base_field), "r"(k_first), "r"(count) : "memory");
+    if ((threadIdx.x & 31u) == 0) {
+      if (CMPC_PF > 0) {   // warm the L2 for the first knots
+        for (int i = DEPTH; i < DEPTH + CMPC_PF && i < count; ++i) {
+          const int kp = k_first + i * direction;
+          const Ranges Q = ranges_of(SK, nst_s[kp], GEN);
+          const double* sp = ws + (long)kp * rstride;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp + (long)Q.s1 * TL), "r"((unsigned)(Q.e1 - Q.s1) * (TL * 8u)) : "memory");
+        }
+      }
+      for (int i = 0; i < DEPTH && n_left > 0; ++i) issue();
     }
-    asm volatile("bar.arrive 1, 64;" ::: "memory");
   }
   CMPC_HD StagedPtr acquire() {
     const unsigned bar = bars_sa + 8u * s_wait;
-    mbar_wait(bar, (phases >> s_wait) & 1u);
+    if (!mbar_wait(bar, (phases >> s_wait) & 1u)) lost = 1;
     phases ^= 1u << s_wait;
-    return ring_sa + (unsigned)((s_wait * slot_f) * TL + lane) * 8u;
+    return ring_sa + (unsigned)((s_wait * SLOTF) * TL + lane) * 8u;
   }
   CMPC_HD void release() {
     __syncwarp();          // every lane is done reading the slot
-    if ((threadIdx.x & 31u) == 0)   // tell the producer warp that the slot is free
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_sa + 8u * (RING_DEPTH + s_wait)) : "memory");
-    s_wait = (s_wait + 1 == RING_DEPTH) ? 0 : s_wait + 1;
+    if ((threadIdx.x & 31u) == 0 && n_left > 0) issue();
+    s_wait = (s_wait + 1 == DEPTH) ? 0 : s_wait + 1;
   }
-  CMPC_HD void close(TileCtx& Tc) { Tc.phases = phases; }   // every issued copy has been consumed
+  CMPC_HD int close(TileCtx& Tc) { Tc.phases = phases; return lost; }   // every issued copy has been consumed
 };
-
-// The producer warp of a CTA: waits for a stream descriptor (named barrier 1), then issues the
-// bulk copies of the stream's knots as ring slots fall free ("empty" mbarriers, one arrival per
-// release of the solver warp), and goes back to waiting.  count < 0 ends it.
-CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k0, int kstep, double* mq_out, double* mc_out);
-CMPC_FN void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out, int k0, int kstep);
-CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b);
-CMPC_HD void bind_tile(TileCtx& T, const Params& P, const Batch& bt, int tile);
-
-CMPC_HD void producer_warp(const Params& P, const Batch& bt, unsigned ring_sa, unsigned bars_sa, const unsigned char* nst_s) {
-  const int lane = (int)(threadIdx.x & 31u);
-  unsigned eph = 0xffffffffu;   // parity to wait for per "empty" barrier: a fresh barrier passes parity 1
-  for (;;) {
-    asm volatile("bar.sync 1, 64;" ::: "memory");
-    const unsigned c = bars_sa + 32u;
-    const double* ws;
-    int segs, base_f, k0, count, dir;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ws) : "r"(c) : "memory");
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dir) : "r"(c + 8u) : "memory");
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(segs), "=r"(base_f), "=r"(k0), "=r"(count) : "r"(c + 16u) : "memory");
-    if (count == CMD_EXIT) break;
-    if (count == CMD_SETUP || count == CMD_WRITE) {   // half of a per-knot operation: the odd knots
-      const int tile = segs;
-      const unsigned mask = (unsigned)base_f;
-      TileCtx T;
-      bind_tile(T, P, bt, tile);
-      Inst I;
-      I.lane = lane;
-      if ((mask >> lane) & 1u) {
-        bind_instance(I, P, bt, tile * TL + lane);
-        if (count == CMD_SETUP) {
-          double mq, mc;
-          setup_knots(P, T, I, 1, 2, &mq, &mc);
-          sc_st(ring_sa + (unsigned)lane * 8u, 0, mq);      // the ring is idle during setup
-          sc_st(ring_sa + (unsigned)lane * 8u, TL, mc);
-        } else {
-          write_solution_knots(P, T, I, bt.X_out, bt.U_out, 1, 2);
-        }
-      }
-      asm volatile("bar.sync 2, 64;" ::: "memory");         // join
-      continue;
-    }
-    const int slot_f = R_STAGED - base_f;
-    auto issue = [&](int i, int s) {   // knot number i of the stream into slot s
-      mbar_wait(bars_sa + 8u * (RING_DEPTH + s), (eph >> s) & 1u);
-      eph ^= 1u << s;
-      if (lane == 0) {
-        const int k = k0 + i * dir;
-        const int ns = nst_s[k];
-        const unsigned bar = bars_sa + 8u * s;
-        const unsigned dst0 = ring_sa + (unsigned)(s * slot_f) * (TL * 8);
-        const double* src0 = ws + (long)k * (REC * TL);
-        unsigned bytes = 0;
-#pragma unroll
-        for (int sg = 1; sg <= SEG_F; sg <<= 1)
-          if (segs & sg) bytes += (unsigned)seg_len(sg, ns) * (TL * 8);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-#pragma unroll
-        for (int sg = 1; sg <= SEG_F; sg <<= 1) {
-          if (!(segs & sg)) continue;
-          const unsigned len = (unsigned)seg_len(sg, ns) * (TL * 8);
-          if (len == 0) continue;
-          const int st = seg_start(sg);
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst0 + (unsigned)(st - base_f) * (TL * 8)), "l"(src0 + st * TL), "r"(len), "r"(bar) : "memory");
-        }
-      }
-    };
-    for (int i = 0; i < RING_DEPTH && i < count; ++i) issue(i, i);
-    int s = 0;
-    for (int i = 0; i < count; ++i) {
-      if (i + RING_DEPTH < count) issue(i + RING_DEPTH, s);
-      s = (s + 1 == RING_DEPTH) ? 0 : s + 1;
-    }
-  }
+template <int SK, int NS, bool GEN>
+CMPC_CX int so_of(int f) {
+  const Ranges R = ranges_of(SK, NS, GEN);
+  return f < R.e1 ? f - R.s1 : f - R.s2 + (R.e1 - R.s1);
 }
 #else
+template <int SK, bool GEN>
 struct KnotStream {
   const double* ws;
-  int lane, dir, k, base_f;
-  CMPC_HD void open(TileCtx& T, const Inst& I, int, int base_field, int k_first, int, int direction) {
-    ws = T.ws; lane = I.lane; dir = direction; k = k_first; base_f = base_field;
+  long rstride;
+  int lane, dir, k;
+  CMPC_HD void open(TileCtx& T, const Inst& I, int k_first, int, int direction) {
+    ws = T.ws; rstride = T.rstride; lane = I.lane; dir = direction; k = k_first;
   }
-  CMPC_HD StagedPtr acquire() const { return ws + (long)k * (REC * TL) + base_f * TL + lane; }
+  CMPC_HD StagedPtr acquire() const { return ws + (long)k * rstride + lane; }
   CMPC_HD void release() { k += dir; }
-  CMPC_HD void close(TileCtx&) {}
+  CMPC_HD int close(TileCtx&) { return 0; }
 };
+template <int SK, int NS, bool GEN>
+CMPC_CX int so_of(int f) { return f; }
 #endif
+// staged field f (+ runtime offset o) of the current knot; SK, NS, GEN are constants of the enclosing scope
+#define CMPC_S(r, f) sp_ld(r, so_of<SK, NS, !FAST>(f))
+#define CMPC_SO(r, f, o) sp_ld(r, so_of<SK, NS, !FAST>(f) + (o))
+#define CMPC_SI(r, f, which) sp_ldi(r, so_of<SK, NS, !FAST>(f), I.lane, which)
 
-// Solver scalars of one lane.
+// Solver scalars of one instance (replicated in the lanes of its team).
 struct Sv {
   double rho, rhok, rhoe, rhoep, radius, weight;
   double tau;                      // weight / rhok: threshold of the trust-region prox
@@ -267,6 +319,8 @@ struct Sv {
   double nq, dynrow;               // constant parts of the residual norms
   int kap;                         // multiplier method: some knot has trust-region rows
   int fail;                        // a pivot was not positive
+  int lost;                        // a bulk copy never landed (device)
+  int nconv;                       // all-zero warm start: the reference's convergence() is NaN, never below the threshold
   int n_pmm, n_polish;             // statistics: multiplier-method sweeps, polish attempts
   double ye[9];                    // multiplier of x_N = x_final
 };
@@ -274,65 +328,44 @@ struct Sv {
 // ---------------------------------------------------------------- friction rows
 // G = pyr4 * R^T, pyr4 = [[1,0,-k],[-1,0,-k],[0,1,-k],[0,-1,-k]], k = mu/sqrt2
 // (utils.py:9-16, constraints.py:178-184); e2 = row equilibration under D_u = 1/sqrt(W_u).
-// Fast path (identity R, same W_u for all contacts): constants; else the per-knot table.
+// Fast path (identity R, same W_u for all contacts): constants; else the staged table (segment G).
+// The rows are carried SHIFTED by their upper bound (stochastic mode: the chance-constraint back-offs,
+// constraints.py:187-214; zero otherwise): cf = G u - ub, so that w = min(v, 0), y ~ max(v, 0),
+// "active <=> cf = 0" and "violated <=> cf > 0" hold unchanged for the shifted values.
 CMPC_HD double pyr4(const Params& P, int row, int a) {
   if (a == 2) return -P.kf;
   if (a == 0) return row == 0 ? 1.0 : (row == 1 ? -1.0 : 0.0);
   return row == 2 ? 1.0 : (row == 3 ? -1.0 : 0.0);
 }
-
-template <bool FAST> struct Fric;
-template <> struct Fric<true> {
-  double kf, ea, eb;
-  CMPC_HD void load(const Params& P, const double*, int) { kf = P.kf; ea = P.e2[0]; eb = P.e2[2]; }
-  CMPC_HD double e2(int r) const { return r < 2 ? ea : eb; }
-  CMPC_HD double ub(int) const { return 0.0; }
-  CMPC_HD double G(int r, int a) const {
-    if (a == 2) return -kf;
-    if (a == 0) return r == 0 ? 1.0 : (r == 1 ? -1.0 : 0.0);
-    return r == 2 ? 1.0 : (r == 3 ? -1.0 : 0.0);
-  }
-  CMPC_HD void rows(const double* u, double* cf) const {          // cf = G u
-    cf[0] = fma(-kf, u[2], u[0]);
-    cf[1] = fma(-kf, u[2], -u[0]);
-    cf[2] = fma(-kf, u[2], u[1]);
-    cf[3] = fma(-kf, u[2], -u[1]);
-  }
-  CMPC_HD void trans(const double* t, double* o) const {          // o = G' t
-    o[0] = t[0] - t[1];
-    o[1] = t[2] - t[3];
-    o[2] = -kf * ((t[0] + t[1]) + (t[2] + t[3]));
-  }
-};
-template <> struct Fric<false> {
-  double g[12], e[4], b[4];
-  CMPC_HD void load(const Params&, const double* gt, int s) {
-#pragma unroll
-    for (int i = 0; i < 12; ++i) g[i] = CMPC_R(gt, s * GS + i);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { e[i] = CMPC_R(gt, s * GS + 12 + i); b[i] = CMPC_R(gt, s * GS + 16 + i); }
-  }
-  CMPC_HD double e2(int r) const { return e[r]; }
-  CMPC_HD double ub(int r) const { return b[r]; }
-  CMPC_HD double G(int r, int a) const { return g[r * 3 + a]; }
-  // cf = G u - ub: the rows are carried SHIFTED by their upper bound (stochastic mode: the
-  // chance-constraint back-offs, constraints.py:187-214; zero otherwise), so that w = min(v, 0),
-  // y ~ max(v, 0), "active <=> cf = 0" and "violated <=> cf > 0" hold unchanged for the shifted values
-  CMPC_HD void rows(const double* u, double* cf) const {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) cf[r] = fma(g[r * 3 + 2], u[2], fma(g[r * 3 + 1], u[1], g[r * 3] * u[0])) - b[r];
-  }
-  CMPC_HD void trans(const double* t, double* o) const {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) o[a] = fma(g[9 + a], t[3], fma(g[6 + a], t[2], fma(g[3 + a], t[1], g[a] * t[0])));
-  }
-};
+struct FRow { double gx, gy, gz, e2, ub; };   // one pyramid row of a slot
+#define CMPC_FROW(fr, r, s, row)                                                       \
+  do {                                                                                 \
+    if (FAST) {                                                                        \
+      fr.gx = (row) == 0 ? 1.0 : ((row) == 1 ? -1.0 : 0.0);                            \
+      fr.gy = (row) == 2 ? 1.0 : ((row) == 3 ? -1.0 : 0.0);                            \
+      fr.gz = -P.kf; fr.e2 = (row) < 2 ? P.e2[0] : P.e2[2]; fr.ub = 0.0;               \
+    } else {                                                                           \
+      const int o_ = (s) * GS;                                                         \
+      fr.gx = CMPC_SO(r, L.g, o_ + (row) * 3); fr.gy = CMPC_SO(r, L.g, o_ + (row) * 3 + 1); \
+      fr.gz = CMPC_SO(r, L.g, o_ + (row) * 3 + 2);                                     \
+      fr.e2 = CMPC_SO(r, L.g, o_ + 12 + (row)); fr.ub = CMPC_SO(r, L.g, o_ + 16 + (row)); \
+    }                                                                                  \
+  } while (0)
+// column a of G for the four rows of slot s (G' t needs it)
+#define CMPC_GCOL(gc, r, s, a)                                                         \
+  do {                                                                                 \
+    if (FAST) {                                                                        \
+      gc[0] = (a) == 0 ? 1.0 : ((a) == 2 ? -P.kf : 0.0); gc[1] = (a) == 0 ? -1.0 : ((a) == 2 ? -P.kf : 0.0); \
+      gc[2] = (a) == 1 ? 1.0 : ((a) == 2 ? -P.kf : 0.0); gc[3] = (a) == 1 ? -1.0 : ((a) == 2 ? -P.kf : 0.0); \
+    } else {                                                                           \
+      _Pragma("unroll") for (int row_ = 0; row_ < 4; ++row_) gc[row_] = CMPC_SO(r, L.g, (s) * GS + row_ * 3 + (a)); \
+    }                                                                                  \
+  } while (0)
 
 // ---------------------------------------------------------------- trust-region prox
 // argmin_v omega*max(0, |v - kbar|_1 - r) + rho/2 |v - a|^2  (oracle/device_model.py prox_trust)
 // branch 0: inside the L1 ball; 1: outside after soft-thresholding; 2: on the surface.
-// tau = omega / rho is passed in (no division on the device in the per-knot path: a double
-// division is a subroutine call in SASS and spills every live register around it)
+// tau = omega / rho is passed in (no division on the device in the per-knot path)
 CMPC_HD int prox_trust(const double* a, const double* kbar, double r, double tau_in, double* w) {
   double b[3], ab[3];
   double s1 = 0.0;
@@ -419,166 +452,215 @@ CMPC_HD void set_rho(const Params& P, double rho, double* rho_out, double* rhok_
   if (rhoe) *rhoe = P.rho_e_rel * wm;
   if (rhoep) *rhoep = P.rho_e_pol_rel * wm;
 }
+// entry i of a 9-vector of kernel parameters with a run-time index (a select chain: a dynamically
+// indexed copy of the parameter block would live in local memory)
+CMPC_HD double pick9(const double* w, int i) {
+  double v = w[0];
+#pragma unroll
+  for (int c = 1; c < 9; ++c) v = (i == c) ? w[c] : v;
+  return v;
+}
+CMPC_HD double pick3(double a, double b, double c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
 
 // ---------------------------------------------------------------- Riccati factorisation
-// Backward over k.  The symmetric tableau  T = [[Huu, Hux],[Hux', Q + A'PA]]  (Huu = R + B'PB,
-// Hux = B'PA; lower triangle, u indices first) is swept on its na control pivots (SPD, no
-// pivoting):  T -> [[-Huu^-1, .],[Hux' Huu^-1, Q + A'PA - Hux' Huu^-1 Hux]], which delivers Hinv,
-// K = -Huu^-1 Hux and P_k in one pass and keeps all three exactly symmetric.  Pc = P c.
-// ADMM mode: R = W_u + rho G'E2G, Q = W_x + rho_k I (kappa); multiplier mode: active friction
-// rows and kappa rows carry the penalty 1/delta.
-// The tableau lives in per-lane scratch tb (stride TS: shared memory on the device, a local
-// array in the host build); P (packed lower triangle) stays in registers across the knots.
-CMPC_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
-CMPC_HD constexpr int trs(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
-
-template <int NS, int MODE, bool FAST, int TS>
-CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k,
-                         double* Pm, ScratchPtr tb, bool on) {
-  constexpr int BASE = R_META;
+// Backward over k.  The symmetric tableau  T = [[Huu, Hux],[Hux', Q + A'PA]]  (Huu = R + B'PB, Hux = B'PA;
+// n = na + 9 rows, controls first) is swept on its na control pivots (SPD, no pivoting):
+//   T -> [[-Huu^-1, Huu^-1 Hux],[Hux' Huu^-1, Q + A'PA - Hux' Huu^-1 Hux]],
+// which delivers Hn = -Huu^-1, K' = -Hux' Huu^-1 and P_k in one pass.  Pc = P c.
+// ADMM mode: R = W_u + rho G'E2G, Q = W_x + rho_k I (kappa); multiplier mode: active friction rows and
+// kappa rows carry the penalty 1/delta.
+// Team work split: lane q owns the tableau rows q, q + NL, ... as FULL rows in registers.  P (square,
+// symmetric) and Y = P [B A] go through the scratch; per pivot the owners publish their entry of the
+// pivot column (double-buffered), everybody reads the column and updates its own rows.
+template <int NS, int MODE, bool FAST, int SK>
+CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const Inst& I, int k, ScratchPtr xs, bool on) {
+  constexpr Lay L = lay_of(NS, !FAST);
   constexpr int NA = 3 * NS, n = NA + 9;
+  constexpr int RT = (n + NL - 1) / NL;   // tableau rows per lane
+  constexpr int ST = (9 + NL - 1) / NL;   // state rows per lane
+  const int q = sub_of(I);
   const double inv = P.inv_delta;
-  const int mt = staged_meta<BASE>(r, lane, 0), nsl = mt & 7;
-  const int pm = (MODE == MODE_PMM) ? staged_meta<BASE>(r, lane, 1) : 0;
-  const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
-  const double ck[3] = {CMPC_S(r, R_CK), CMPC_S(r, R_CK + 1), CMPC_S(r, R_CK + 2)};
-  // Pc = P c
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    double pc = Pm[trs(i, 5)] * P.dtmg;
-    pc = fma(Pm[trs(i, 6)], ck[0], pc);
-    pc = fma(Pm[trs(i, 7)], ck[1], pc);
-    pc = fma(Pm[trs(i, 8)], ck[2], pc);
-    if (on) CMPC_R(w, R_PC + i) = pc;
-  }
-  // control part of the tableau, one slot at a time:  W = P B (rows 3..8 kept), Hux = W'A, Huu = R + B'W
-  double Wm[6][NA > 0 ? NA : 1];   // rows 3..8 of P B
+  const int mt = CMPC_SI(r, L.meta, 0), nsl = mt & 7;
+  const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
+  const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
+  const double ck[3] = {CMPC_S(r, L.ck), CMPC_S(r, L.ck + 1), CMPC_S(r, L.ck + 2)};
+  double ds[NS > 0 ? NS : 1][3], dts[NS > 0 ? NS : 1];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    const double dts = s < nsl ? P.dt : 0.0;
-    const double ds[3] = {CMPC_S(r, R_D + 3 * s), CMPC_S(r, R_D + 3 * s + 1), CMPC_S(r, R_D + 3 * s + 2)};
-    Fric<FAST> fr;
-    fr.load(P, gt, s);
-    double rr[4];
+    dts[s] = s < nsl ? P.dt : 0.0;
 #pragma unroll
-    for (int row = 0; row < 4; ++row) {
-      if (MODE == MODE_ADMM) rr[row] = S.rho * fr.e2(row);
-      else rr[row] = ((pm >> (4 * s + row)) & 1) ? inv : 0.0;
-    }
-    const int cid = (s < nsl) ? ((mt >> (4 + 2 * s)) & 3) : 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int a1 = nxt3(a), a2 = prv3(a), j = 3 * s + a;
-      // (P B)[i][(s,a)] = dt_s (P[i][3+a] + P[i][6+a1] d[a2] - P[i][6+a2] d[a1])
-      double wc[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i)
-        wc[i] = dts * fma(Pm[trs(i, 6 + a1)], ds[a2], fma(-Pm[trs(i, 6 + a2)], ds[a1], Pm[trs(i, 3 + a)]));
-#pragma unroll
-      for (int i = 0; i < 6; ++i) Wm[i][j] = wc[3 + i];
-      // Hux[j][q] = (W'A)[j][q]
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int q1 = nxt3(q), q2 = prv3(q);
-        sc_st(tb, (tri(NA + q, j)) * TS, fma(P.dt, fma(wc[6 + q1], S3[q2], -(wc[6 + q2] * S3[q1])), wc[q]));
-        sc_st(tb, (tri(NA + 3 + q, j)) * TS, fma(P.dt_m, wc[q], wc[3 + q]));
-        sc_st(tb, (tri(NA + 6 + q, j)) * TS, wc[6 + q]);
-      }
-      // Huu[j][l], l <= j:  row (s,a) of B' v = dt_s (v[3+a] + v[6+a1] d[a2] - v[6+a2] d[a1])
-#pragma unroll
-      for (int l = 0; l <= j; ++l) {
-        double v = dts * fma(Wm[3 + a1][l], ds[a2], fma(-Wm[3 + a2][l], ds[a1], Wm[a][l]));
-        if (l >= 3 * s) {   // R block of the slot: W_u + G' diag(rr) G
-          const int b2 = l - 3 * s;
-          double radd = (b2 == a) ? (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) : 0.0;
-#pragma unroll
-          for (int row = 0; row < 4; ++row) radd = fma(rr[row] * fr.G(row, a), fr.G(row, b2), radd);
-          v += radd;
-        }
-        sc_st(tb, (tri(j, l)) * TS, v);
-      }
-    }
+    for (int a = 0; a < 3; ++a) ds[s][a] = CMPC_S(r, L.d + 3 * s + a);
   }
-  // Q + A'(PA), lower triangle.  This state block of the tableau (the future P_k) never goes to
-  // the scratch: it is built, swept and handed on in registers.
-  double Pn[45];
-  {
+  const bool kap = MODE == MODE_PMM && S.kap && k >= 1;
+  if (kap) {   // kappa penalty block of the multiplier method -> scratch (every lane writes the same values)
+    const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
+    const double yk[4] = {CMPC_S(r, L.yk), CMPC_S(r, L.yk + 1), CMPC_S(r, L.yk + 2), CMPC_S(r, L.yk + 3)};
     double kM[9], kl[3];
-    const bool kap = MODE == MODE_PMM && S.kap && k >= 1;
-    if (kap) {
-      const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
-      const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
-      pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
-    }
-    double PA[9][9];
+    pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
+    for (int i = 0; i < 9; ++i) sp_st(xs, X_KX + 3 + i, kM[i]);
+  }
+  // ---- phase 1: rows of Y = P [B A] and Pc = P c, by the owners of the state rows
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {     // (P [S]x)[i][q] = P[i][6+q1] S[q2] - P[i][6+q2] S[q1]
-        const int q1 = nxt3(q), q2 = prv3(q);
-        PA[i][q] = fma(P.dt, fma(Pm[trs(i, 6 + q1)], S3[q2], -(Pm[trs(i, 6 + q2)] * S3[q1])), Pm[trs(i, q)]);
-        PA[i][3 + q] = fma(P.dt_m, Pm[trs(i, q)], Pm[trs(i, 3 + q)]);
-        PA[i][6 + q] = Pm[trs(i, 6 + q)];
-      }
-    }
+  for (int t = 0; t < ST; ++t) {
+    const int i = q + NL * t;
+    if (i < 9) {
+      double Pr[9];
 #pragma unroll
-    for (int rr2 = 0; rr2 < 9; ++rr2) {
-      const int g3 = rr2 / 3, a = rr2 - 3 * g3, a1 = nxt3(a), a2 = prv3(a);
+      for (int c = 0; c < 9; ++c) Pr[c] = sp_ld(xs, X_PS + i * 9 + c);
+      double pc = Pr[5] * P.dtmg;
+      pc = fma(Pr[6], ck[0], pc);
+      pc = fma(Pr[7], ck[1], pc);
+      pc = fma(Pr[8], ck[2], pc);
+      if (on) CMPC_R(w, L.pc + i) = pc;
 #pragma unroll
-      for (int c = 0; c <= rr2; ++c) {
-        double v = PA[rr2][c];
-        if (g3 == 0) v = fma(P.dt, fma(PA[6 + a1][c], S3[a2], -(PA[6 + a2][c] * S3[a1])), v);
-        else if (g3 == 1) v = fma(P.dt_m, PA[a][c], v);
-        if (c == rr2) {
-          v += P.Wx[rr2];
-          if (MODE == MODE_ADMM && k >= 1 && rr2 >= 6) v += S.rhok;
+      for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {   // (P B)[i][(s,a)] = dt_s (P[i][3+a] + P[i][6+a1] d[a2] - P[i][6+a2] d[a1])
+          const int a1 = nxt3(a), a2 = prv3(a);
+          sp_st(xs, X_Y + i * n + 3 * s + a, dts[s] * fma(Pr[6 + a1], ds[s][a2], fma(-Pr[6 + a2], ds[s][a1], Pr[3 + a])));
         }
-        if (MODE == MODE_PMM && c >= 6 && kap) v += kM[3 * (rr2 - 6) + (c - 6)];
-        Pn[tri(rr2, c)] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {     // (P A)[i][:]
+        const int c1 = nxt3(c), c2 = prv3(c);
+        sp_st(xs, X_Y + i * n + NA + c, fma(P.dt, fma(Pr[6 + c1], S3[c2], -(Pr[6 + c2] * S3[c1])), Pr[c]));
+        sp_st(xs, X_Y + i * n + NA + 3 + c, fma(P.dt_m, Pr[c], Pr[3 + c]));
+        sp_st(xs, X_Y + i * n + NA + 6 + c, Pr[6 + c]);
       }
     }
   }
-  // sweep the control pivots.  Row / column pv of the generic update is garbage and is
-  // overwritten afterwards, so that the update itself has no pv-dependent addressing.
+  team_sync(I);
+  // ---- phase 2: the lane's tableau rows, full rows in registers
+  double T[RT][n];
+#pragma unroll
+  for (int t = 0; t < RT; ++t) {
+    const int rr = q + NL * t;
+    if (rr < NA) {   // control row (s, a):  B' Y  + R block
+      const int s = rr / 3, a = rr - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
+      const double dtr = s < nsl ? P.dt : 0.0;
+      const double dA = CMPC_SO(r, L.d, 3 * s + a2), dB = CMPC_SO(r, L.d, 3 * s + a1);
+#pragma unroll
+      for (int e = 0; e < n; ++e)
+        T[t][e] = dtr * fma(sp_ld(xs, X_Y + (6 + a1) * n + e), dA, fma(-sp_ld(xs, X_Y + (6 + a2) * n + e), dB, sp_ld(xs, X_Y + (3 + a) * n + e)));
+      // R block of the slot: W_u + G' diag(rr) G, columns 3s .. 3s+2
+      double gc[3][4], rw[4];
+#pragma unroll
+      for (int b2 = 0; b2 < 3; ++b2) CMPC_GCOL(gc[b2], r, s, b2);
+#pragma unroll
+      for (int row = 0; row < 4; ++row) {
+        if (MODE == MODE_ADMM) { FRow fr; CMPC_FROW(fr, r, s, row); rw[row] = S.rho * fr.e2; }
+        else rw[row] = ((pm >> (4 * s + row)) & 1) ? inv : 0.0;
+      }
+      const double ga[4] = {pick3(gc[0][0], gc[1][0], gc[2][0], a), pick3(gc[0][1], gc[1][1], gc[2][1], a),
+                            pick3(gc[0][2], gc[1][2], gc[2][2], a), pick3(gc[0][3], gc[1][3], gc[2][3], a)};
+      const int cid = (s < nsl) ? ((mt >> (4 + 2 * s)) & 3) : 0;
+      double radd[3];
+#pragma unroll
+      for (int b2 = 0; b2 < 3; ++b2) {
+        double v = 0.0;
+        if (b2 == a) {
+          if (FAST) v = pick3(P.Wu[0], P.Wu[1], P.Wu[2], a);
+          else {
+            double wsel = P.Wu[b2];
+#pragma unroll
+            for (int c = 1; c < MAXC; ++c) wsel = (cid == c) ? P.Wu[3 * c + b2] : wsel;
+            v = wsel;
+          }
+        }
+#pragma unroll
+        for (int row = 0; row < 4; ++row) v = fma(rw[row] * ga[row], gc[b2][row], v);
+        radd[b2] = v;
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        if (s2 == s) {
+#pragma unroll
+          for (int b2 = 0; b2 < 3; ++b2) T[t][3 * s2 + b2] += radd[b2];
+        }
+      }
+    } else if (rr < n) {   // state row i:  Hux' | Q + A'(P A)
+      const int i = rr - NA;
+      const int g3 = i / 3, a = i - 3 * g3, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int b2 = 0; b2 < 3; ++b2) {   // Hux[(s,b2)][i], the expression of the control row's owner
+          const int b1 = nxt3(b2), bp = prv3(b2);
+          T[t][3 * s + b2] = dts[s] * fma(sp_ld(xs, X_Y + (6 + b1) * n + NA + i), ds[s][bp],
+                                          fma(-sp_ld(xs, X_Y + (6 + bp) * n + NA + i), ds[s][b1], sp_ld(xs, X_Y + (3 + b2) * n + NA + i)));
+        }
+      }
+      // (A'X)[i][c] = X[i][c] + mul (X[rA][c] sA - X[rB][c] sB):  rows 0..2: dt [S]x', rows 3..5: dt/m, rows 6..8: -
+      const double mul = g3 == 0 ? P.dt : (g3 == 1 ? P.dt_m : 0.0);
+      const int rA = g3 == 0 ? 6 + a1 : a, rB = g3 == 0 ? 6 + a2 : a;
+      const double sA = g3 == 0 ? pick3(S3[0], S3[1], S3[2], a2) : 1.0, sB = g3 == 0 ? pick3(S3[0], S3[1], S3[2], a1) : 0.0;
+      const double wxi = pick9(P.Wx, i);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        double v = sp_ld(xs, X_Y + i * n + NA + c);
+        v = fma(mul, fma(sp_ld(xs, X_Y + rA * n + NA + c), sA, -(sp_ld(xs, X_Y + rB * n + NA + c) * sB)), v);
+        if (c == i) {
+          v += wxi;
+          if (MODE == MODE_ADMM && k >= 1 && i >= 6) v += S.rhok;
+        }
+        if (MODE == MODE_PMM && c >= 6 && kap && i >= 6) v += sp_ld(xs, X_KX + 3 + 3 * (i - 6) + (c - 6));
+        T[t][NA + c] = v;
+      }
+    }
+  }
+  // ---- phase 3: sweep the control pivots
+#pragma unroll
   for (int pv = 0; pv < NA; ++pv) {
-    const int tpv = pv * (pv + 1) / 2;
-    const double piv = sc_ld(tb, ((tpv + pv)) * TS);
+    const int cb = X_CX + (pv & 1) * 21;
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
+      const int rr = q + NL * t;
+      if (rr < n) sp_st(xs, cb + rr, T[t][pv]);
+    }
+    team_sync(I);
+    double c[n];
+#pragma unroll
+    for (int e = 0; e < n; ++e) c[e] = sp_ld(xs, cb + e);
+    const double piv = c[pv];
     if (!(piv > 0.0) && on) S.fail = 1;
     const double ip = 1.0 / piv;
-    double c[n], bc[n];
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const int idx = i < pv ? tpv + i : i * (i + 1) / 2 + pv;
-      c[i] = sc_ld(tb, (idx) * TS);
-      bc[i] = c[i] * ip;
-    }
+    for (int t = 0; t < RT; ++t) {
+      const int rr = q + NL * t;
+      if (rr == pv) {            // the pivot row: scaled column, -1/pivot on the diagonal
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
+        for (int e = 0; e < n; ++e) T[t][e] = (e == pv) ? -ip : c[e] * ip;
+      } else {
+        const double bc = T[t][pv] * ip;
 #pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        if (j >= NA) Pn[tri(i - NA, j - NA)] = fma(-bc[i], c[j], Pn[tri(i - NA, j - NA)]);   // state block: registers
-        else sc_st(tb, tri(i, j) * TS, fma(-bc[i], c[j], sc_ld(tb, tri(i, j) * TS)));
+        for (int e = 0; e < n; ++e) T[t][e] = (e == pv) ? bc : fma(-bc, c[e], T[t][e]);
       }
     }
+  }
+  // ---- factor record M = [Hn; K'] and P_k (lower triangle, mirrored: P stays exactly symmetric)
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const int idx = i < pv ? tpv + i : i * (i + 1) / 2 + pv;
-      sc_st(tb, (idx) * TS, (i == pv) ? -ip : bc[i]);
+  for (int t = 0; t < RT; ++t) {
+    const int rr = q + NL * t;
+    if (rr < n) {
+      const double sg = rr < NA ? 1.0 : -1.0;
+      if (on) {
+#pragma unroll
+        for (int l = 0; l < NA; ++l) CMPC_R(w, L.hn + rr * NA + l) = sg * T[t][l];
+      }
+      if (rr >= NA) {
+        const int i = rr - NA;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          if (c <= i) {
+            sp_st(xs, X_PS + i * 9 + c, T[t][NA + c]);
+            sp_st(xs, X_PS + c * 9 + i, T[t][NA + c]);
+          }
+        }
+      }
     }
   }
-  // factor record and P_k
-#pragma unroll
-  for (int j = 0; j < NA; ++j) {
-#pragma unroll
-    for (int l = 0; l <= j; ++l) { const double v = -sc_ld(tb, (tri(j, l)) * TS); if (on) CMPC_R(w, R_HI + tri(j, l)) = v; }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { const double v = -sc_ld(tb, (tri(NA + i, j)) * TS); if (on) CMPC_R(w, R_K + 9 * j + i) = v; }
-  }
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-#pragma unroll
-    for (int j = 0; j <= i; ++j) Pm[tri(i, j)] = Pn[tri(i, j)];
-  }
+  team_sync(I);
 }
 
 template <int MODE, bool FAST>
@@ -588,48 +670,44 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
   const Params P = P_in;
   const Inst I = I_in;
   Sv S = S_in;
-  constexpr int BASE = R_META;
+  constexpr int SK = MODE == MODE_ADMM ? SK_FAC_ADMM : SK_FAC_PMM;
+  constexpr int NS = 0;
+  constexpr Lay L = lay_of(0, !FAST);
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
-  KnotStream ks;
-  ks.open(T, I, SEG_C | (MODE == MODE_PMM ? SEG_F : 0), R_META, N, N + 1, -1);
-#if defined(__CUDACC__)
-  constexpr int TS = TL;
-  const ScratchPtr tb = T.ring_sa + (unsigned)(RING_DEPTH * (R_STAGED - R_META) * TL + I.lane) * 8u;   // behind the stream's slots
-#else
-  constexpr int TS = 1;
-  double tbl[231];
-  const ScratchPtr tb = tbl;
-#endif
-  double Pm[45];
-  {
+  const ScratchPtr xs = scratch_of(T, I);
+  KnotStream<SK, !FAST> ks;
+  ks.open(T, I, N, N + 1, -1);
+  {   // P_N (every lane of the team writes the same values)
     const StagedPtr r = ks.acquire();
-    if (on) {
+    double Pm[81];
 #pragma unroll
-      for (int i = 0; i < 45; ++i) Pm[i] = 0.0;
+    for (int i = 0; i < 81; ++i) Pm[i] = 0.0;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) Pm[tri(i, i)] = P.Wx[i] + rho_e;
-      if (MODE == MODE_ADMM) {
+    for (int i = 0; i < 9; ++i) Pm[10 * i] = P.Wx[i] + rho_e;
+    if (MODE == MODE_ADMM) {
 #pragma unroll
-        for (int i = 6; i < 9; ++i) Pm[tri(i, i)] += S.rhok;
-      } else if (S.kap) {
-        double kM[9], kl[3];
-        const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
-        const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
-        pmm_kappa_terms(P, S, staged_meta<BASE>(r, I.lane, 1), kb, yk, kM, kl);
+      for (int i = 6; i < 9; ++i) Pm[10 * i] += S.rhok;
+    } else if (S.kap) {
+      double kM[9], kl[3];
+      const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
+      const double yk[4] = {CMPC_S(r, L.yk), CMPC_S(r, L.yk + 1), CMPC_S(r, L.yk + 2), CMPC_S(r, L.yk + 3)};
+      pmm_kappa_terms(P, S, CMPC_SI(r, L.meta, 1), kb, yk, kM, kl);
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j <= i; ++j) Pm[tri(6 + i, 6 + j)] += kM[3 * i + j];
-      }
+        for (int j = 0; j < 3; ++j) Pm[(6 + i) * 9 + 6 + j] += (j <= i) ? kM[3 * i + j] : kM[3 * j + i];
     }
+#pragma unroll
+    for (int i = 0; i < 81; ++i) sp_st(xs, X_PS + i, Pm[i]);
     ks.release();
+    team_sync(I);
   }
-  // runs of equal slot count: one specialisation of the knot step per inner loop, P in registers
+  // runs of equal slot count: one specialisation of the knot step per inner loop
 #define CMPC_FAC_RUN(NS_)                                                             \
   do {                                                                                \
     const StagedPtr r = ks.acquire();                                                 \
-    if (on) factor_knot<NS_, MODE, FAST, TS>(P, S, r, rec_of(T, I, k), I.lane, gt_of(T, I, k), k, Pm, tb, on); \
+    factor_knot<NS_, MODE, FAST, SK>(P, S, r, rec_of(T, I, k), I, k, xs, on);         \
     ks.release();                                                                     \
     --k;                                                                              \
   } while (k >= 0 && T.ns(k) == NS_)
@@ -643,127 +721,142 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
     }
   }
 #undef CMPC_FAC_RUN
-  ks.close(T);
+  if (ks.close(T)) S_in.lost = 1;
   if (S.fail) S_in.fail = 1;
 }
 
 // ---------------------------------------------------------------- backward sweep (linear term)
-// p_N = qx_N;  g = p + Pc;  hu = ru + B'g;  d = -Hinv hu;  p = qx + A'g + K'hu.
+// p_N = qx_N;  g = p + Pc;  hu = ru + B'g;  d = Hn hu;  p = qx + A'g + K'hu.
 // qx = -Wx xbar (+ kappa / terminal penalty terms), ru = friction penalty terms.
-// r: staged read pointer, w: the knot's record in global memory (writes).
-template <int MODE>
-CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, StagedPtr r, int pm, double* p) {
-  constexpr int BASE = 0;
-  const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
+// Team work split: phase 1 the owners of the control rows publish hu; phase 2 the rows of [Hn; K'] hu
+// (na + 9 row tasks) by their owners, who write d to the record and the new p to the scratch.
+// kl[3]: linear term of the kappa rows (replicated in every lane)
+template <int NS, int MODE, bool FAST, int SK>
+CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, StagedPtr r, const Inst& I, int pm, double* kl) {
+  constexpr Lay L = lay_of(NS, !FAST);
+  const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) kl[a] = 0.0;
   if (MODE == MODE_ADMM) {
-    const double vk[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
+    const double vk[3] = {CMPC_S(r, L.vk), CMPC_S(r, L.vk + 1), CMPC_S(r, L.vk + 2)};
     double w[3];
     prox_kappa(S, vk, kb, w);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) p[6 + a] += -S.rhok * (w[a] + w[a] - vk[a]);
+    for (int a = 0; a < 3; ++a) kl[a] = -S.rhok * (w[a] + w[a] - vk[a]);
   } else if (S.kap) {
-    const double yk[4] = {CMPC_S(r, R_YK), CMPC_S(r, R_YK + 1), CMPC_S(r, R_YK + 2), CMPC_S(r, R_YK + 3)};
-    double kM[9], kl[3];
+    const double yk[4] = {CMPC_S(r, L.yk), CMPC_S(r, L.yk + 1), CMPC_S(r, L.yk + 2), CMPC_S(r, L.yk + 3)};
+    double kM[9];
     pmm_kappa_terms(P, S, pm, kb, yk, kM, kl);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p[6 + a] += kl[a];
   }
 }
 
-template <int NS, int MODE, bool FAST>
-CMPC_HD void bwd_knot(const Params& P, const Sv& S, StagedPtr r, double* w, int lane, const double* gt, int k, double* p) {
-  constexpr int BASE = 0;
-  constexpr int NA = 3 * NS;
-  const int nsl = staged_meta<BASE>(r, lane, 0) & 7;
-  const int pm = (MODE == MODE_PMM) ? staged_meta<BASE>(r, lane, 1) : 0;
-  double g[9];
+template <int NS, int MODE, bool FAST, int SK>
+CMPC_HD void bwd_knot(const Params& P, const Sv& S, StagedPtr r, double* w, const Inst& I, int k, ScratchPtr xs, int buf, bool on) {
+  constexpr Lay L = lay_of(NS, !FAST);
+  constexpr int NA = 3 * NS, n = NA + 9;
+  constexpr int CT = (NA + NL - 1) / NL, RT = (n + NL - 1) / NL;
+  const int q = sub_of(I);
+  const int nsl = CMPC_SI(r, L.meta, 0) & 7;
+  const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
+  const int pin = X_PX + buf * 9, pout = X_PX + (buf ^ 1) * 9;
+  if (k >= 1) {
+    double kl[3];
+    kappa_linear_term<NS, MODE, FAST, SK>(P, S, r, I, pm, kl);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) g[i] = p[i] + CMPC_S(r, R_PC + i);
+    for (int a = 0; a < 3; ++a) sp_st(xs, X_KX + a, kl[a]);
+  }
+  // ---- phase 1: hu of the lane's control rows
+#pragma unroll
+  for (int t = 0; t < CT; ++t) {
+    const int j = q + NL * t;
+    if (j < NA) {
+      const int s = j / 3, a = j - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
+      const double dtr = s < nsl ? P.dt : 0.0;
+      double tt[4], gc[4];
+      CMPC_GCOL(gc, r, s, a);
+#pragma unroll
+      for (int row = 0; row < 4; ++row) {
+        FRow fr;
+        CMPC_FROW(fr, r, s, row);
+        if (MODE == MODE_ADMM) {
+          tt[row] = S.rho * fr.e2 * fabs(CMPC_SO(r, L.vf, 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
+          if (!FAST) tt[row] = fma(-S.rho * fr.e2, fr.ub, tt[row]);         // unshifted w = min(v, 0) + ub
+        } else {
+          const double y = CMPC_SO(r, L.yf, 4 * s + row);
+          tt[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? y : fma(-P.inv_delta, fr.ub, y)) : 0.0;
+        }
+      }
+      const double o = fma(gc[3], tt[3], fma(gc[2], tt[2], fma(gc[1], tt[1], gc[0] * tt[0])));
+      const double g0 = sp_ld(xs, pin + 3 + a) + CMPC_SO(r, L.pc, 3 + a);
+      const double gA = sp_ld(xs, pin + 6 + a1) + CMPC_SO(r, L.pc, 6 + a1);
+      const double gB = sp_ld(xs, pin + 6 + a2) + CMPC_SO(r, L.pc, 6 + a2);
+      sp_st(xs, X_UX + j, dtr * fma(gA, CMPC_SO(r, L.d, 3 * s + a2), fma(-gB, CMPC_SO(r, L.d, 3 * s + a1), g0)) + o);
+    }
+  }
+  team_sync(I);
+  // ---- phase 2: rows of [Hn; K'] hu
   double hu[NA > 0 ? NA : 1];
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    const double dts = s < nsl ? P.dt : 0.0;
-    const double ds[3] = {CMPC_S(r, R_D + 3 * s), CMPC_S(r, R_D + 3 * s + 1), CMPC_S(r, R_D + 3 * s + 2)};
-    Fric<FAST> fr;
-    fr.load(P, gt, s);
-    double t[4], o[3];
+  for (int l = 0; l < NA; ++l) hu[l] = sp_ld(xs, X_UX + l);
 #pragma unroll
-    for (int row = 0; row < 4; ++row) {
-      if (MODE == MODE_ADMM) {
-        t[row] = S.rho * fr.e2(row) * fabs(CMPC_S(r, R_VF + 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
-        if (!FAST) t[row] = fma(-S.rho * fr.e2(row), fr.ub(row), t[row]);     // unshifted w = min(v, 0) + ub
-      } else {
-        const double y = CMPC_S(r, R_YF + 4 * s + row);
-        t[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? y : fma(-P.inv_delta, fr.ub(row), y)) : 0.0;
+  for (int t = 0; t < RT; ++t) {
+    const int rr = q + NL * t;
+    if (rr < n) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < NA; ++l) acc = fma(CMPC_SO(r, L.hn, rr * NA + l), hu[l], acc);
+      if (rr < NA) {
+        if (on) CMPC_R(w, L.dv + rr) = acc;
+      } else {   // p_i = qx_i + (A'g)_i + (K'hu)_i
+        const int i = rr - NA;
+        const int g3 = i / 3, a = i - 3 * g3, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
+        const double mul = g3 == 0 ? P.dt : (g3 == 1 ? P.dt_m : 0.0);
+        const int rA = g3 == 0 ? 6 + a1 : a, rB = g3 == 0 ? 6 + a2 : a;
+        const double sA = g3 == 0 ? CMPC_SO(r, L.s, a2) : 1.0, sB = g3 == 0 ? CMPC_SO(r, L.s, a1) : 0.0;
+        const double gi = sp_ld(xs, pin + i) + CMPC_SO(r, L.pc, i);
+        const double gA = sp_ld(xs, pin + rA) + CMPC_SO(r, L.pc, rA);
+        const double gB = sp_ld(xs, pin + rB) + CMPC_SO(r, L.pc, rB);
+        double pi = fma(mul, fma(gA, sA, -(gB * sB)), gi) + acc - pick9(P.Wx, i) * CMPC_SO(r, L.xb, i);
+        if (k >= 1 && i >= 6) pi += sp_ld(xs, X_KX + (i - 6));
+        sp_st(xs, pout + i, pi);
       }
     }
-    fr.trans(t, o);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int a1 = nxt3(a), a2 = prv3(a);
-      hu[3 * s + a] = dts * fma(g[6 + a1], ds[a2], fma(-g[6 + a2], ds[a1], g[3 + a])) + o[a];
-    }
   }
-  // d = -Hinv hu (packed symmetric), K'hu
-  double acc[NA > 0 ? NA : 1], kh[9];
-#pragma unroll
-  for (int j = 0; j < NA; ++j) acc[j] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) kh[i] = 0.0;
-#pragma unroll
-  for (int j = 0; j < NA; ++j) {
-#pragma unroll
-    for (int l = 0; l <= j; ++l) {
-      const double h = CMPC_S(r, R_HI + j * (j + 1) / 2 + l);
-      acc[j] = fma(h, hu[l], acc[j]);
-      if (l < j) acc[l] = fma(h, hu[j], acc[l]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NA; ++j) CMPC_R(w, R_DV + j) = -acc[j];
-#pragma unroll
-  for (int j = 0; j < NA; ++j) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) kh[i] = fma(CMPC_S(r, R_K + 9 * j + i), hu[j], kh[i]);
-  }
-  // p = qx + A'g + K'hu
-  const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const int a1 = nxt3(a), a2 = prv3(a);
-    p[a] = fma(P.dt, fma(g[6 + a1], S3[a2], -(g[6 + a2] * S3[a1])), g[a]) + kh[a] - P.Wx[a] * CMPC_S(r, R_XB + a);
-    p[3 + a] = fma(P.dt_m, g[a], g[3 + a]) + kh[3 + a] - P.Wx[3 + a] * CMPC_S(r, R_XB + 3 + a);
-    p[6 + a] = g[6 + a] + kh[6 + a] - P.Wx[6 + a] * CMPC_S(r, R_XB + 6 + a);
-  }
-  if (k >= 1) kappa_linear_term<MODE>(P, S, r, pm, p);
+  team_sync(I);
 }
 
 template <int MODE, bool FAST>
-CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, const Sv& S_in, bool on) {
+CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on) {
   const Params P = P_in;
   const Inst I = I_in;
   const Sv S = S_in;
-  constexpr int BASE = 0;
+  constexpr int SK = MODE == MODE_ADMM ? SK_BWD_ADMM : SK_BWD_PMM;
   const int N = P.N;
   const double rho_e = (MODE == MODE_ADMM) ? S.rhoe : S.rhoep;
-  KnotStream ks;
-  ks.open(T, I, SEG_A | SEG_B | SEG_C | (MODE == MODE_ADMM ? SEG_D : SEG_F), 0, N, N + 1, -1);
-  double p[9];
-  {
+  const ScratchPtr xs = scratch_of(T, I);
+  KnotStream<SK, !FAST> ks;
+  ks.open(T, I, N, N + 1, -1);
+  int buf = 0;
+  {   // p_N (every lane of the team writes the same values)
+    constexpr int NS = 0;
+    constexpr Lay L = lay_of(0, !FAST);
     const StagedPtr r = ks.acquire();
-    if (on) {
+    double kl[3];
+    kappa_linear_term<0, MODE, FAST, SK>(P, S, r, I, CMPC_SI(r, L.meta, 1), kl);
 #pragma unroll
-      for (int i = 0; i < 9; ++i) p[i] = -(P.Wx[i] * CMPC_S(r, R_XB + i)) - (rho_e * I.xf[i] - S.ye[i]);
-      kappa_linear_term<MODE>(P, S, r, staged_meta<BASE>(r, I.lane, 1), p);
+    for (int i = 0; i < 9; ++i) {
+      double p = -(P.Wx[i] * CMPC_S(r, L.xb + i)) - (rho_e * I.xf[i] - S.ye[i]);
+      if (i >= 6) p += kl[i - 6];
+      sp_st(xs, X_PX + i, p);
     }
     ks.release();
+    team_sync(I);
   }
-  // the knots are walked in runs of equal slot count, so that the inner loop is one
-  // specialisation of the knot step and the carried vector p stays in registers
 #define CMPC_BWD_RUN(NS_)                                                             \
   do {                                                                                \
     const StagedPtr r = ks.acquire();                                                 \
-    if (on) bwd_knot<NS_, MODE, FAST>(P, S, r, rec_of(T, I, k), I.lane, gt_of(T, I, k), k, p); \
+    bwd_knot<NS_, MODE, FAST, SK>(P, S, r, rec_of(T, I, k), I, k, xs, buf, on);       \
+    buf ^= 1;                                                                         \
     ks.release();                                                                     \
     --k;                                                                              \
   } while (k >= 0 && T.ns(k) == NS_)
@@ -777,7 +870,7 @@ CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, const
     }
   }
 #undef CMPC_BWD_RUN
-  ks.close(T);
+  if (ks.close(T)) S_in.lost = 1;
 }
 
 // ---------------------------------------------------------------- forward sweep + local updates
@@ -788,30 +881,35 @@ CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, const
 // and (upd) the corrected friction active set: violated rows join, rows with a negative
 // multiplier leave; the number of changes is accumulated in nchg.
 // COPY: read-only LQR roll-out of the ADMM iterate into the solution record.
+// Team work split: x~ is replicated; phase 1 the owners of the control rows publish u~; phase 2 every
+// lane forms x~+, the friction rows (4 per slot) are updated by their owners.
 struct Res { double pri, dua, npri, ndua; };
 
-template <int KIND>
+template <int NS, int KIND, bool FAST, int SK>
 CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, const Inst& I, int k, const double* x) {
-  constexpr int BASE = R_K;
+  constexpr Lay L = lay_of(NS, !FAST);
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const int N = P.N;
   const double al = ADMM ? P.alpha : 1.0;
   if (PMMK || COPY) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) CMPC_R(w, R_X + i) = x[i];
+    for (int i = 0; i < 9; ++i) CMPC_R(w, L.x + i) = x[i];
   }
+  // the kappa rows (a read-modify-write of the record) belong to lane 0 of the team; its residual
+  // terms reach the other lanes through the team maxima at the end of the sweep
+  const bool lead = sub_of(I) == 0;
   double rdx[3] = {0.0, 0.0, 0.0};
-  if (k >= 1) {
+  if (k >= 1 && lead) {
     if (ADMM) {
-      const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
-      const double vk[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
+      const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
+      const double vk[3] = {CMPC_S(r, L.vk), CMPC_S(r, L.vk + 1), CMPC_S(r, L.vk + 2)};
       double wk[3], vn[3];
       prox_kappa(S, vk, kb, wk);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         vn[a] = fma(al, x[6 + a], fma(1.0 - al, wk[a], vk[a] - wk[a]));
-        CMPC_R(w, R_VK + a) = vn[a];
+        CMPC_R(w, L.vk + a) = vn[a];
       }
       if (CHK) {
         double wn[3];
@@ -825,7 +923,7 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
       }
     } else if (PMMK) {
       if (S.kap) {
-        const int pm = staged_meta<BASE>(r, I.lane, 1);
+        const int pm = CMPC_SI(r, L.meta, 1);
         const int br = (pm >> 16) & 3;
         if (br != 0) {
           const double inv = P.inv_delta;
@@ -834,11 +932,11 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
           for (int i = 0; i < 3; ++i) {
             const int code = (pm >> (18 + 2 * i)) & 3;
             const double sgn = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
-            const double dk = x[6 + i] - CMPC_S(r, R_XB + 6 + i);
-            if (code == 0) CMPC_R(w, R_YK + i) = CMPC_S(r, R_YK + i) + inv * dk;
+            const double dk = x[6 + i] - CMPC_S(r, L.xb + 6 + i);
+            if (code == 0) CMPC_R(w, L.yk + i) = CMPC_S(r, L.yk + i) + inv * dk;
             accv += sgn * dk;
           }
-          if (br == 2) CMPC_R(w, R_YK + 3) = CMPC_S(r, R_YK + 3) + inv * accv;
+          if (br == 2) CMPC_R(w, L.yk + 3) = CMPC_S(r, L.yk + 3) + inv * accv;
         }
       }
 #pragma unroll
@@ -859,46 +957,54 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
       }
     }
   }
-  if (CHK && k >= 1) {
+  if (CHK && k >= 1 && lead) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
       const double Px = P.Wx[i] * x[i];
       const double rd = i >= 6 ? rdx[i - 6] : 0.0;
-      const double aty = rd - Px + P.Wx[i] * CMPC_S(r, R_XB + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
+      const double aty = rd - Px + P.Wx[i] * CMPC_S(r, L.xb + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
       R.dua = fmax(R.dua, fabs(rd));
       R.ndua = fmax(R.ndua, fmax(fabs(Px), fabs(aty)));
     }
   }
 }
 
-template <int NS, int KIND, bool FAST>
-CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double* w, int* imw, int lane,
-                      const double* gt, double* x, bool upd, int& nchg) {
-  constexpr int BASE = R_K;
+template <int NS, int KIND, bool FAST, int SK>
+CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double* w, int* imw, const Inst& I,
+                      ScratchPtr xs, double* x, bool on, bool upd, int& nchg) {
+  constexpr Lay L = lay_of(NS, !FAST);
   constexpr int NA = 3 * NS;
+  constexpr int CT = (NA + NL - 1) / NL, FT = (4 * NS + NL - 1) / NL;
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
+  const int q = sub_of(I);
   const double al = ADMM ? P.alpha : 1.0;
   const double inv = P.inv_delta;
   const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
-  // controls u~ = K x + d
+  // ---- phase 1: controls u~ = K x + d of the lane's rows
+  double uo[CT > 0 ? CT : 1];
+#pragma unroll
+  for (int t = 0; t < CT; ++t) {
+    const int j = q + NL * t;
+    uo[t] = 0.0;
+    if (j < NA) {
+      double v = CMPC_SO(r, L.dv, j);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) v = fma(CMPC_SO(r, L.kt, i * NA + j), x[i], v);
+      uo[t] = v;
+      sp_st(xs, X_UX + j, v);
+      if ((PMMK || COPY) && on) CMPC_R(w, L.u + j) = v;
+    }
+  }
+  team_sync(I);
+  // ---- phase 2: next state (replicated), friction rows of the lane
   double u[NA > 0 ? NA : 1];
 #pragma unroll
-  for (int j = 0; j < NA; ++j) {
-    double t = CMPC_S(r, R_DV + j);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) t = fma(CMPC_S(r, R_K + 9 * j + i), x[i], t);
-    u[j] = t;
-  }
-  if (PMMK || COPY) {
-#pragma unroll
-    for (int j = 0; j < NA; ++j) CMPC_R(w, R_U + j) = u[j];
-  }
-  // next state
+  for (int j = 0; j < NA; ++j) u[j] = sp_ld(xs, X_UX + j);
   double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    const double ds[3] = {CMPC_S(r, R_D + 3 * s), CMPC_S(r, R_D + 3 * s + 1), CMPC_S(r, R_D + 3 * s + 2)};
+    const double ds[3] = {CMPC_S(r, L.d + 3 * s), CMPC_S(r, L.d + 3 * s + 1), CMPC_S(r, L.d + 3 * s + 2)};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int a1 = nxt3(a), a2 = prv3(a);
@@ -908,81 +1014,92 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
   }
   double xn[9];
   {
-    const double S3[3] = {CMPC_S(r, R_S), CMPC_S(r, R_S + 1), CMPC_S(r, R_S + 2)};
+    const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int a1 = nxt3(a), a2 = prv3(a);
       xn[a] = fma(P.dt_m, x[3 + a], x[a]);
       xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
-      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_S(r, R_CK + a));
+      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_S(r, L.ck + a));
     }
   }
-  // friction rows of the knot
   if (!COPY) {
-    const int mt = staged_meta<BASE>(r, lane, 0);
-    const int pm = PMMK ? staged_meta<BASE>(r, lane, 1) : 0;
+    const int mt = CMPC_SI(r, L.meta, 0);
+    const int pm = PMMK ? CMPC_SI(r, L.meta, 1) : 0;
     int newpm = 0;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      Fric<FAST> fr;
-      fr.load(P, gt, s);
-      double cf[4];
-      fr.rows(u + 3 * s, cf);
-      if (ADMM) {
-        double dl[4];
-#pragma unroll
-        for (int row = 0; row < 4; ++row) {
-          const double v = CMPC_S(r, R_VF + 4 * s + row);
+    for (int t = 0; t < FT; ++t) {
+      const int bit = q + NL * t;   // friction row 4 s + row
+      if (bit < 4 * NS) {
+        const int s = bit >> 2, row = bit & 3;
+        FRow fr;
+        CMPC_FROW(fr, r, s, row);
+        const double u0 = sp_ld(xs, X_UX + 3 * s), u1 = sp_ld(xs, X_UX + 3 * s + 1), u2 = sp_ld(xs, X_UX + 3 * s + 2);
+        double cf = fma(fr.gz, u2, fma(fr.gy, u1, fr.gx * u0));
+        if (!FAST) cf -= fr.ub;
+        if (ADMM) {
+          const double v = CMPC_SO(r, L.vf, bit);
           const double w0 = fmin(v, 0.0), y0 = fmax(v, 0.0);
-          const double vn = fma(al, cf[row], fma(1.0 - al, w0, y0));
-          CMPC_R(w, R_VF + 4 * s + row) = vn;
+          const double vn = fma(al, cf, fma(1.0 - al, w0, y0));
+          if (on) CMPC_R(w, L.vf + bit) = vn;
           if (CHK) {
             const double wn = fmin(vn, 0.0);
-            R.pri = fmax(R.pri, fabs(cf[row] - wn));
-            R.npri = fmax(R.npri, FAST ? fmax(fabs(cf[row]), fabs(wn))
-                                       : fmax(fabs(cf[row] + fr.ub(row)), fabs(wn + fr.ub(row))));
-            dl[row] = S.rho * fr.e2(row) * (fmax(vn, 0.0) - y0 - cf[row] + w0);
+            R.pri = fmax(R.pri, fabs(cf - wn));
+            R.npri = fmax(R.npri, FAST ? fmax(fabs(cf), fabs(wn)) : fmax(fabs(cf + fr.ub), fabs(wn + fr.ub)));
+            sp_st(xs, X_DX + bit, S.rho * fr.e2 * (fmax(vn, 0.0) - y0 - cf + w0));
           }
-        }
-        if (CHK) {   // u rows of the stationarity residual: G' delta; norms of P u and A'y
-          double rdu[3];
-          fr.trans(dl, rdu);
-          const int cid = (s < (mt & 7)) ? ((mt >> (4 + 2 * s)) & 3) : 0;
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            const double Pu = (FAST ? P.Wu[a] : P.Wu[3 * cid + a]) * u[3 * s + a];
-            R.dua = fmax(R.dua, fabs(rdu[a]));
-            R.ndua = fmax(R.ndua, fmax(fabs(Pu), fabs(rdu[a] - Pu)));
-          }
-        }
-      } else {
-#pragma unroll
-        for (int row = 0; row < 4; ++row) {
-          const int bit = 4 * s + row;
-          const bool on = (pm >> bit) & 1;
-          const double yn = fma(inv, cf[row], on ? CMPC_S(r, R_YF + bit) : 0.0);
-          R.pri = fmax(R.pri, on ? fabs(cf[row]) : fmax(cf[row], 0.0));
-          R.npri = fmax(R.npri, FAST ? fabs(cf[row]) : fabs(cf[row] + fr.ub(row)));
+        } else {
+          const bool act = (pm >> bit) & 1;
+          const double yn = fma(inv, cf, act ? CMPC_SO(r, L.yf, bit) : 0.0);
+          R.pri = fmax(R.pri, act ? fabs(cf) : fmax(cf, 0.0));
+          R.npri = fmax(R.npri, FAST ? fabs(cf) : fabs(cf + fr.ub));
           if (upd) {
-            const bool keep = on && !(yn < 0.0);
-            const bool join = !on && (cf[row] > tolc);
+            const bool keep = act && !(yn < 0.0);
+            const bool join = !act && (cf > tolc);
             const bool nb = keep || join;
-            nchg += (nb != on) ? 1 : 0;
-            CMPC_R(w, R_YF + bit) = keep ? yn : 0.0;
+            nchg += (nb != act) ? 1 : 0;
+            if (on) CMPC_R(w, L.yf + bit) = keep ? yn : 0.0;
             newpm |= (nb ? 1 : 0) << bit;
-          } else if (on) {
-            CMPC_R(w, R_YF + bit) = yn;
+          } else if (act) {
+            if (on) CMPC_R(w, L.yf + bit) = yn;
           }
         }
       }
     }
-    if (PMMK && upd) imw[TL] = (pm & ~0xffff) | newpm;
+    if (PMMK) {   // (warp-collective: every lane takes part, also those whose instance does not update)
+      newpm = team_or(I, xs, newpm);
+      if (upd && on) imw[TL] = (pm & ~0xffff) | newpm;
+    }
+    if (CHK) {   // u rows of the stationarity residual: G' delta; norms of P u and A'y
+      team_sync(I);
+#pragma unroll
+      for (int t = 0; t < CT; ++t) {
+        const int j = q + NL * t;
+        if (j < NA) {
+          const int s = j / 3, a = j - 3 * s;
+          double gc[4];
+          CMPC_GCOL(gc, r, s, a);
+          const double rdu = fma(gc[3], sp_ld(xs, X_DX + 4 * s + 3), fma(gc[2], sp_ld(xs, X_DX + 4 * s + 2),
+                                 fma(gc[1], sp_ld(xs, X_DX + 4 * s + 1), gc[0] * sp_ld(xs, X_DX + 4 * s))));
+          const int cid = (s < (mt & 7)) ? ((mt >> (4 + 2 * s)) & 3) : 0;
+          double wsel = pick3(P.Wu[0], P.Wu[1], P.Wu[2], a);
+          if (!FAST) {
+#pragma unroll
+            for (int c = 1; c < MAXC; ++c) wsel = (cid == c) ? pick3(P.Wu[3 * c], P.Wu[3 * c + 1], P.Wu[3 * c + 2], a) : wsel;
+          }
+          const double Pu = wsel * uo[t];
+          R.dua = fmax(R.dua, fabs(rdu));
+          R.ndua = fmax(R.ndua, fmax(fabs(Pu), fabs(rdu - Pu)));
+        }
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) x[i] = xn[i];
+  team_sync(I);   // the exchange words are rewritten by the next knot
 }
 
-// commit: the lane wants the residuals of this sweep (a lane that did not ask for a check may
+// commit: the instance wants the residuals of this sweep (an instance that did not ask for a check may
 // ride along in the CHECK kind when a neighbour did; its iterate update is the same arithmetic)
 template <int KIND, bool FAST>
 CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on, bool commit, bool upd, int* changes) {
@@ -990,26 +1107,24 @@ CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
   const Inst I = I_in;
   Sv S = S_in;
   constexpr bool CHK = KIND == FW_ADMM_CHECK, PMMK = KIND == FW_PMM;
+  constexpr int SK = KIND == FW_PMM ? SK_FWD_PMM : (KIND == FW_COPY ? SK_FWD_COPY : SK_FWD_ADMM);
   const int N = P.N;
-  KnotStream ks;
-  ks.open(T, I, SEG_B | SEG_C | SEG_E | (KIND == FW_PMM ? SEG_F : (KIND == FW_COPY ? 0 : SEG_D)), R_K, 0, N + 1, 1);
+  const ScratchPtr xs = scratch_of(T, I);
+  KnotStream<SK, !FAST> ks;
+  ks.open(T, I, 0, N + 1, 1);
   Res R;
   R.pri = R.dua = R.npri = R.ndua = 0.0;
   int nchg = 0;
   double x[9];
-  if (on) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
-  }
+  for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
   // runs of equal slot count: one specialisation of the knot step per inner loop, x in registers
 #define CMPC_FWD_RUN(NS_)                                                             \
   do {                                                                                \
     const StagedPtr r = ks.acquire();                                                 \
-    if (on) {                                                                         \
-      double* w = rec_of(T, I, k);                                                    \
-      fwd_state<KIND>(P, S, R, r, w, I, k, x);                                        \
-      fwd_knot<NS_, KIND, FAST>(P, S, R, r, w, meta_of(T, I, k), I.lane, gt_of(T, I, k), x, upd, nchg); \
-    }                                                                                 \
+    double* w = rec_of(T, I, k);                                                      \
+    if (on) fwd_state<NS_, KIND, FAST, SK>(P, S, R, r, w, I, k, x);                   \
+    fwd_knot<NS_, KIND, FAST, SK>(P, S, R, r, w, meta_of(T, I, k, lay_of(NS_, !FAST).meta), I, xs, x, on, upd, nchg); \
     ks.release();                                                                     \
     ++k;                                                                              \
   } while (k < N && T.ns(k) == NS_)
@@ -1025,10 +1140,19 @@ CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
 #undef CMPC_FWD_RUN
   {   // terminal knot
     const StagedPtr r = ks.acquire();
-    if (on) fwd_state<KIND>(P, S, R, r, rec_of(T, I, N), I, N, x);
+    if (on) fwd_state<0, KIND, FAST, SK>(P, S, R, r, rec_of(T, I, N), I, N, x);
     ks.release();
   }
-  ks.close(T);
+  if (ks.close(T)) S.lost = 1;
+  if (CHK || PMMK) {   // the lanes of a team hold partial maxima / counts of their own rows
+    R.pri = team_max(I, xs, R.pri);
+    R.npri = team_max(I, xs, R.npri);
+    if (CHK) {
+      R.dua = team_max(I, xs, R.dua);
+      R.ndua = team_max(I, xs, R.ndua);
+    }
+    if (PMMK) nchg = team_sum(I, xs, nchg);
+  }
   if (on && commit && (CHK || PMMK)) {
     S.pri = R.pri;
     S.npri = fmax(R.npri, S.dynrow);
@@ -1039,67 +1163,63 @@ CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
   }
   if (on && changes) *changes = nchg;
   if (on) S_in = S;
+  else if (S.lost) S_in.lost = 1;
 }
 
-// ---------------------------------------------------------------- rho change: keep (w, y), move v
+// ---------------------------------------------------------------- per-knot operations
+// Knots are independent here: lane q of the team takes the knots q, q + NL, ... and works on the
+// global record directly.
+// rho change: keep (w, y), move v
 CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, double rho_new, double rhok_new) {
   const double ratio = S.rho / rho_new;
-  for (int k = 0; k <= P.N; ++k) {
+  for (int k = sub_of(I); k <= P.N; k += NL) {
     double* r = rec_of(T, I, k);
+    const Lay L = lay_of(T.ns(k), T.gen != 0);
     if (k < P.N) {
       const int nr = 4 * T.ns(k);
       for (int j = 0; j < nr; ++j) {
-        const double v = CMPC_R(r, R_VF + j);
-        CMPC_R(r, R_VF + j) = fma(ratio, fmax(v, 0.0), fmin(v, 0.0));
+        const double v = CMPC_R(r, L.vf + j);
+        CMPC_R(r, L.vf + j) = fma(ratio, fmax(v, 0.0), fmin(v, 0.0));
       }
     }
     if (k >= 1) {
-      const double kb[3] = {CMPC_R(r, R_XB + 6), CMPC_R(r, R_XB + 7), CMPC_R(r, R_XB + 8)};
-      const double vk[3] = {CMPC_R(r, R_VK), CMPC_R(r, R_VK + 1), CMPC_R(r, R_VK + 2)};
+      const double kb[3] = {CMPC_R(r, L.xb + 6), CMPC_R(r, L.xb + 7), CMPC_R(r, L.xb + 8)};
+      const double vk[3] = {CMPC_R(r, L.vk), CMPC_R(r, L.vk + 1), CMPC_R(r, L.vk + 2)};
       double w[3];
       prox_kappa(S, vk, kb, w);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = fma(S.rhok / rhok_new, vk[a] - w[a], w[a]);
+      for (int a = 0; a < 3; ++a) CMPC_R(r, L.vk + a) = fma(S.rhok / rhok_new, vk[a] - w[a], w[a]);
     }
   }
 }
 
-// ---------------------------------------------------------------- active set of the polish
-// Friction row active iff its multiplier is positive (OSQP's rule -w < y <=> v > 0); trust-
-// region rows by the branch the prox took.  Sets *kap when some knot has trust-region rows.
-template <bool FAST>
-CMPC_FN void build_active_set_op(const Params& P_in, TileCtx& T, const Inst& I_in, const Sv& S_in, bool on, int* kap_out) {
-  const Params P = P_in;
-  const Inst I = I_in;
-  const Sv S = S_in;
-  constexpr int BASE = R_META;
+// active set of the polish: friction row active iff its multiplier is positive (OSQP's rule
+// -w < y <=> v > 0); trust-region rows by the branch the prox took.  Sets *kap when some knot has
+// trust-region rows.
+CMPC_FN void build_active_set_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, bool on, int* kap_out) {
   const int N = P.N;
   int kap = 0;
-  KnotStream ks;
-  ks.open(T, I, SEG_C | SEG_D, R_META, 0, N + 1, 1);
-  for (int k = 0; k <= N; ++k) {
-    const StagedPtr r = ks.acquire();
-    if (on) {
+  if (on) {
+    for (int k = sub_of(I); k <= N; k += NL) {
       double* w = rec_of(T, I, k);
+      const int ns = T.ns(k);
+      const Lay L = lay_of(ns, T.gen != 0);
       int pm = 0;
       if (k < N) {
-        const int ns = T.ns(k);
-        const double* gt = gt_of(T, I, k);
         for (int s = 0; s < ns; ++s) {
-          Fric<FAST> fr;
-          fr.load(P, gt, s);
 #pragma unroll
           for (int row = 0; row < 4; ++row) {
-            const double v = CMPC_S(r, R_VF + 4 * s + row);
+            const double e2 = T.gen ? CMPC_R(w, L.g + s * GS + 12 + row) : (row < 2 ? P.e2[0] : P.e2[2]);
+            const double v = CMPC_R(w, L.vf + 4 * s + row);
             const bool act = v > 0.0;
             if (act) pm |= 1 << (4 * s + row);
-            CMPC_R(w, R_YF + 4 * s + row) = act ? S.rho * fr.e2(row) * v : 0.0;
+            CMPC_R(w, L.yf + 4 * s + row) = act ? S.rho * e2 * v : 0.0;
           }
         }
       }
       if (k >= 1) {
-        const double kb[3] = {CMPC_S(r, R_XB + 6), CMPC_S(r, R_XB + 7), CMPC_S(r, R_XB + 8)};
-        const double a3[3] = {CMPC_S(r, R_VK), CMPC_S(r, R_VK + 1), CMPC_S(r, R_VK + 2)};
+        const double kb[3] = {CMPC_R(w, L.xb + 6), CMPC_R(w, L.xb + 7), CMPC_R(w, L.xb + 8)};
+        const double a3[3] = {CMPC_R(w, L.vk), CMPC_R(w, L.vk + 1), CMPC_R(w, L.vk + 2)};
         double wk[3], yk4[4] = {0.0, 0.0, 0.0, 0.0};
         const int br = prox_trust(a3, kb, S.radius, S.tau, wk);
         if (br != 0) {
@@ -1119,19 +1239,19 @@ CMPC_FN void build_active_set_op(const Params& P_in, TileCtx& T, const Inst& I_i
           if (br == 2) yk4[3] = nz ? msum / nz : 0.0;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) CMPC_R(w, R_YK + i) = yk4[i];
+        for (int i = 0; i < 4; ++i) CMPC_R(w, L.yk + i) = yk4[i];
       }
-      meta_of(T, I, k)[TL] = pm;
+      meta_of(T, I, k, L.meta)[TL] = pm;
     }
-    ks.release();
   }
-  ks.close(T);
+  kap = team_or(I, scratch_of(T, I), kap);
   if (on) *kap_out = kap;
 }
 
 // ---------------------------------------------------------------- trust test and accuracy ratio
 // sigma_max(X - Xbar) via the 9x9 Gram matrix + cyclic Jacobi (scp_solver.py:151: np.linalg.norm(.,2));
 // rho = sum ||(f(x,u) - lin)[6:9]||^2 / sum ||lin||^2 (scp_solver.py:71-87).
+// (replicated in the lanes of a team: the sums over the horizon are sequential by definition)
 CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, double* snorm, double* num_out, double* den_out) {
   const int N = P.N;
   double A[81];
@@ -1139,14 +1259,15 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
   double num = 0.0, den = 0.0;
   for (int k = 0; k <= N; ++k) {
     const double* r = rec_of(T, I, k);
+    const Lay L = lay_of(T.ns(k), T.gen != 0);
     double x[9], dx[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { x[i] = CMPC_R(r, R_X + i); dx[i] = x[i] - I.Xr[k * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { x[i] = CMPC_R(r, L.x + i); dx[i] = x[i] - I.Xr[k * 9 + i]; }
 #pragma unroll
     for (int i = 0; i < 9; ++i)
       for (int j = i; j < 9; ++j) A[i * 9 + j] = fma(dx[i], dx[j], A[i * 9 + j]);
     if (k == N) break;
-    const int mt = meta_of(T, I, k)[0];
+    const int mt = meta_of(T, I, k, L.meta)[0];
     const int ns = mt & 7;
     double u[MAXU];
 #pragma unroll
@@ -1154,26 +1275,27 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
     double F[3] = {0, 0, 0}, Tq[3] = {0, 0, 0};
     for (int sl = 0; sl < ns; ++sl) {
       const int cid = (mt >> (4 + 2 * sl)) & 3;
-      const double ds[3] = {CMPC_R(r, R_D + 3 * sl), CMPC_R(r, R_D + 3 * sl + 1), CMPC_R(r, R_D + 3 * sl + 2)};
-      const double us[3] = {CMPC_R(r, R_U + 3 * sl), CMPC_R(r, R_U + 3 * sl + 1), CMPC_R(r, R_U + 3 * sl + 2)};
+      const double ds[3] = {CMPC_R(r, L.d + 3 * sl), CMPC_R(r, L.d + 3 * sl + 1), CMPC_R(r, L.d + 3 * sl + 2)};
+      const double us[3] = {CMPC_R(r, L.u + 3 * sl), CMPC_R(r, L.u + 3 * sl + 1), CMPC_R(r, L.u + 3 * sl + 2)};
       double t[3];
       cross3(ds, us, t);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        u[3 * cid + a] = us[a];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) if (c == cid) u[3 * c + a] = us[a];
         F[a] += us[a];
         Tq[a] += t[a];
       }
     }
     // lin = A x + B u + c with the structured A, B
-    const double S3[3] = {CMPC_R(r, R_S), CMPC_R(r, R_S + 1), CMPC_R(r, R_S + 2)};
+    const double S3[3] = {CMPC_R(r, L.s), CMPC_R(r, L.s + 1), CMPC_R(r, L.s + 2)};
     double lin[9], nl[9], Sxc[3];
     cross3(S3, x, Sxc);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       lin[a] = x[a] + P.dt_m * x[3 + a];
       lin[3 + a] = x[3 + a] + P.dt * F[a] + (a == 2 ? P.dtmg : 0.0);
-      lin[6 + a] = x[6 + a] + P.dt * Sxc[a] + P.dt * Tq[a] + CMPC_R(r, R_CK + a);
+      lin[6 + a] = x[6 + a] + P.dt * Sxc[a] + P.dt * Tq[a] + CMPC_R(r, L.ck + a);
     }
     step_knot(P, x, u, I.cpos + (long)k * P.nc * 3, I.cact + (long)k * P.nc, nl);
 #pragma unroll
@@ -1220,47 +1342,56 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
 }
 
 // ---------------------------------------------------------------- per-instance setup
-// K1 for every knot, friction table when not on the fast path, start of the iterate at the
-// linearisation point, constant parts of the residual norms.
-// setup_knots handles the knots k0, k0 + kstep, ... and returns the partial maxima through mq / mc
-// (device: the solver warp takes the even knots, the producer warp the odd ones).
-CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k0, int kstep, double* mq_out, double* mc_out) {
+// Pass 1 (setup_slots): active contacts per knot, so that the tile-uniform slot count (the record
+// layout of the knot) is known.  Pass 2 (setup_knots): K1 for every knot, friction table when not on
+// the fast path, start of the iterate at the linearisation point, constant parts of the residual norms.
+// Lane q of the team takes the knots q, q + NL, ...; the partial maxima come back through mq / mc.
+CMPC_HD int active_slots(const Params& P, const Inst& I, int k) {
+  if (k >= P.N) return 0;
+  int ns = 0;
+  for (int c = 0; c < P.nc; ++c) ns += I.cact[(long)k * P.nc + c] ? 1 : 0;
+  return ns;
+}
+CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool live, double* mq_out, double* mc_out, int* nconv_out) {
   const int N = P.N;
   double mq = 0.0, mc = 0.0;
-  for (int k = k0; k <= N; k += kstep) {
+  int nzx = 0, nzu = 0;
+  for (int k = sub_of(I); live && k <= N; k += NL) {
     double* r = rec_of(T, I, k);
-    int* im = meta_of(T, I, k);
+    const int nst = T.ns(k);
+    const Lay L = lay_of(nst, T.gen != 0);
+    int* im = meta_of(T, I, k, L.meta);
     const int kk = k < N ? k : N - 1;
     const double* xb = I.Xr + k * 9;
-    KnotLin L;
-    linearize_knot(P, xb, I.Ui + kk * P.nu, I.cpos + (long)kk * P.nc * 3, I.cact + (long)kk * P.nc, k == N, L);
+    KnotLin Lk;
+    linearize_knot(P, xb, I.Ui + kk * P.nu, I.cpos + (long)kk * P.nc * 3, I.cact + (long)kk * P.nc, k == N, Lk);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      CMPC_R(r, R_XB + i) = xb[i];
+      CMPC_R(r, L.xb + i) = xb[i];
+      CMPC_R(r, L.x + i) = 0.0;
       mq = fmax(mq, fabs(P.Wx[i] * xb[i]));
+      nzx |= xb[i] != 0.0;
     }
+    if (k < N)
+      for (int j = 0; j < P.nu; ++j) nzu |= I.Ui[k * P.nu + j] != 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { CMPC_R(r, R_S + a) = L.S[a]; CMPC_R(r, R_CK + a) = L.ck[a]; }
+    for (int a = 0; a < 3; ++a) { CMPC_R(r, L.s + a) = Lk.S[a]; CMPC_R(r, L.ck + a) = Lk.ck[a]; }
+    for (int j = 0; j < L.na; ++j) { CMPC_R(r, L.d + j) = Lk.d[j]; CMPC_R(r, L.dv + j) = 0.0; CMPC_R(r, L.u + j) = 0.0; }
+    for (int j = 0; j < 4 * nst; ++j) { CMPC_R(r, L.vf + j) = 0.0; CMPC_R(r, L.yf + j) = 0.0; }
 #pragma unroll
-    for (int j = 0; j < MAXU; ++j) { CMPC_R(r, R_D + j) = L.d[j]; CMPC_R(r, R_DV + j) = 0.0; CMPC_R(r, R_U + j) = 0.0; }
+    for (int j = 0; j < 4; ++j) CMPC_R(r, L.yk + j) = 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { CMPC_R(r, R_VF + j) = 0.0; CMPC_R(r, R_YF + j) = 0.0; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) CMPC_R(r, R_YK + j) = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) CMPC_R(r, R_VK + a) = xb[6 + a];
-    im[0] = L.meta;
+    for (int a = 0; a < 3; ++a) CMPC_R(r, L.vk + a) = xb[6 + a];
+    im[0] = Lk.meta;
     im[TL] = 0;
     if (k < N) {
       mc = fmax(mc, fabs(P.dtmg));
 #pragma unroll
-      for (int a = 0; a < 3; ++a) mc = fmax(mc, fabs(L.ck[a]));
-      const int ns = L.meta & 7;
-      double* gt = gt_of(T, I, k);
-#pragma unroll
-      for (int sl = 0; sl < MAXC; ++sl) {
-        if (sl >= ns && !gt) continue;   // padded slot on the fast path: nothing to write
-        const int cid = sl < ns ? ((L.meta >> (4 + 2 * sl)) & 3) : 0;
+      for (int a = 0; a < 3; ++a) mc = fmax(mc, fabs(Lk.ck[a]));
+      const int ns = Lk.meta & 7;
+      for (int sl = 0; sl < nst; ++sl) {
+        if (sl >= ns && !T.gen) continue;   // padded slot on the fast path: nothing to write
+        const int cid = sl < ns ? ((Lk.meta >> (4 + 2 * sl)) & 3) : 0;
         double G[12];
 #pragma unroll
         for (int row = 0; row < 4; ++row) {
@@ -1275,13 +1406,13 @@ CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k
               for (int b2 = 0; b2 < 3; ++b2) g += pyr4(P, row, b2) * Rm[a * 3 + b2];
             }
             G[row * 3 + a] = g;
-            if (gt) mx = fmax(mx, fabs(g) / sqrt(P.Wu[3 * cid + a]));
+            if (T.gen) mx = fmax(mx, fabs(g) / sqrt(P.Wu[3 * cid + a]));
           }
-          if (gt) {
+          if (T.gen) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) CMPC_R(gt, sl * GS + row * 3 + a) = G[row * 3 + a];
-            CMPC_R(gt, sl * GS + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
-            CMPC_R(gt, sl * GS + 16 + row) = (sl < ns && I.fub) ? I.fub[((long)k * P.nc + cid) * 4 + row] : 0.0;
+            for (int a = 0; a < 3; ++a) CMPC_R(r, L.g + sl * GS + row * 3 + a) = G[row * 3 + a];
+            CMPC_R(r, L.g + sl * GS + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
+            CMPC_R(r, L.g + sl * GS + 16 + row) = (sl < ns && I.fub) ? I.fub[((long)k * P.nc + cid) * 4 + row] : 0.0;
           }
         }
         if (sl < ns) {
@@ -1292,17 +1423,21 @@ CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, int k
 #pragma unroll
             for (int a = 0; a < 3; ++a) cf += G[row * 3 + a] * ub[a];
             if (I.fub) cf -= I.fub[((long)k * P.nc + cid) * 4 + row];
-            CMPC_R(r, R_VF + 4 * sl + row) = fmin(cf, 0.0);
+            CMPC_R(r, L.vf + 4 * sl + row) = fmin(cf, 0.0);
           }
         }
       }
     }
   }
-  *mq_out = mq;
-  *mc_out = mc;
+  const ScratchPtr xs = scratch_of(T, I);
+  *mq_out = team_max(I, xs, mq);
+  *mc_out = team_max(I, xs, mc);
+  const int nz = team_or(I, xs, nzx | (nzu << 1));
+  *nconv_out = nz != 3;
 }
-CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc) {
+CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc, int nconv) {
   S.nq = mq;
+  S.nconv = nconv;
   double mi = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) mi = fmax(mi, fabs(I.xi[i]));
@@ -1311,34 +1446,35 @@ CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc) {
   for (int i = 0; i < 9; ++i) S.ye[i] = 0.0;
   S.kap = 0;
   S.fail = 0;
+  S.lost = 0;
   S.n_pmm = S.n_polish = 0;
   S.pri = S.dua = S.npri = S.ndua = 0.0;
 }
 
-// knots k0, k0 + kstep, ... (device: even knots on the solver warp, odd ones on the producer warp)
-CMPC_FN void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out, int k0, int kstep) {
+CMPC_FN void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out) {
   const int N = P.N;
   double* Xo = X_out + (long)I.b * (N + 1) * 9;
   double* Uo = U_out + (long)I.b * N * P.nu;
-  for (int k = k0; k <= N; k += kstep) {
+  for (int k = sub_of(I); k <= N; k += NL) {
     const double* r = rec_of(T, I, k);
+    const Lay L = lay_of(T.ns(k), T.gen != 0);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Xo[k * 9 + i] = CMPC_R(r, R_X + i);
+    for (int i = 0; i < 9; ++i) Xo[k * 9 + i] = CMPC_R(r, L.x + i);
     if (k == N) break;
-    const int mt = meta_of(T, I, k)[0];
+    const int mt = meta_of(T, I, k, L.meta)[0];
     const int ns = mt & 7;
     for (int j = 0; j < P.nu; ++j) Uo[k * P.nu + j] = 0.0;
     for (int sl = 0; sl < ns; ++sl) {
       const int cid = (mt >> (4 + 2 * sl)) & 3;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) Uo[k * P.nu + 3 * cid + a] = CMPC_R(r, R_U + 3 * sl + a);
+      for (int a = 0; a < 3; ++a) Uo[k * P.nu + 3 * cid + a] = CMPC_R(r, L.u + 3 * sl + a);
     }
   }
 }
 
-// ---------------------------------------------------------------- the per-lane driver
+// ---------------------------------------------------------------- the per-instance driver
 // scp_solver.py:118-179 with the QP solve (ADMM interleaved with certified active-set polishes)
-// flattened into a state machine: advance() runs the scalar decisions of a lane until the lane
+// flattened into a state machine: advance() runs the scalar decisions of an instance until it
 // needs a whole-horizon operation and returns its code; the caller executes it and calls
 // advance() again.  The linearisation point never moves (:129-130), so the stage data are built
 // once; each SCP iteration re-solves the QP for the current (radius, weight).
@@ -1391,9 +1527,15 @@ CMPC_HD void drv_init(const Params& P, Sv& S, Drv& D) {
 
 CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
   for (;;) {
+    if (S.lost) {   // a bulk copy of this tile never landed: report it per instance and stop
+      D.status = ST_DEVICE;
+      return OP_DONE;
+    }
     switch (D.pc) {
       case PC_SCP_TOP:
-        if (!(D.it_scp < P.max_scp && D.weight < P.omega_max && !(D.it_scp != 0 && D.success && 0.0 < P.conv_thresh))) {
+        // convergence() compares the warm start with itself (scp_solver.py:90-93): 0 < threshold whenever
+        // both norms are nonzero, 0/0 = NaN (never converged) when one of them vanishes (S.nconv)
+        if (!(D.it_scp < P.max_scp && D.weight < P.omega_max && !(D.it_scp != 0 && D.success && !S.nconv && 0.0 < P.conv_thresh))) {
           D.pc = PC_FINISH;
           break;
         }
@@ -1588,8 +1730,8 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
 }
 
 // Executes one operation of the tile.  Every lane of the warp calls it with the same op (the
-// streamed operations are warp-collective); `on` says whether this lane takes part.
-// anycheck: some participating lane wants residuals from this ADMM sweep.
+// streamed operations are warp-collective); `on` says whether this lane's instance takes part.
+// anycheck: some participating instance wants residuals from this ADMM sweep.
 template <bool FAST>
 CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const Batch& bt, Sv& S, Drv& D, bool on, bool anycheck) {
   switch (op) {
@@ -1599,7 +1741,7 @@ CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const B
       if (anycheck) forward_op<FW_ADMM_CHECK, FAST>(P, T, I, S, on, on && D.check, false, nullptr);
       else forward_op<FW_ADMM, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
-    case OP_BUILD_AS: build_active_set_op<FAST>(P, T, I, S, on, &S.kap); break;
+    case OP_BUILD_AS: build_active_set_op(P, T, I, S, on, &S.kap); break;
     case OP_FACTOR_PMM: factor_op<MODE_PMM, FAST>(P, T, I, S, on); break;
     case OP_SWEEP_PMM:
       backward_op<MODE_PMM, FAST>(P, T, I, S, on);
@@ -1611,20 +1753,14 @@ CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const B
       forward_op<FW_COPY, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
     case OP_EVAL: if (on) evaluate_op(P, T, I, &D.snorm, &D.num, &D.den); break;
-    case OP_WRITE:
-#if defined(__CUDACC__)
-      helper_fork(T, CMD_WRITE, __ballot_sync(0xffffffffu, on));
-      if (on) write_solution_knots(P, T, I, bt.X_out, bt.U_out, 0, 2);
-      helper_join();
-#else
-      if (on) write_solution_knots(P, T, I, bt.X_out, bt.U_out, 0, 1);
-#endif
-      break;
+    case OP_WRITE: if (on) write_solution_knots(P, T, I, bt.X_out, bt.U_out); break;
     default: break;
   }
+  team_sync(I);
 }
 
 CMPC_FN void write_stats(const Batch& bt, const Inst& I, const Sv& S, const Drv& D) {
+  if (sub_of(I) != 0) return;
   bt.scp_iters[I.b] = D.it_scp;
   bt.status[I.b] = D.status;
   bt.n_accepted[I.b] = D.n_acc;
@@ -1651,22 +1787,13 @@ CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b) {
   I.xi = bt.x_init + (long)b * 9;
   I.xf = bt.x_final + (long)b * 9;
 }
-#if defined(__CUDACC__)
-CMPC_HD void helper_fork(const TileCtx& T, int cmd, unsigned mask) {
-  asm volatile("fence.proxy.async;" ::: "memory");
-  __syncwarp();
-  if ((threadIdx.x & 31u) == 0)
-    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(T.bars_sa + 48u), "r"(T.tile), "r"((int)mask), "r"(0), "r"(cmd) : "memory");
-  asm volatile("bar.arrive 1, 64;" ::: "memory");
-}
-#endif
 CMPC_HD void bind_tile(TileCtx& T, const Params& P, const Batch& bt, int tile) {
-  T.prm = &P;
 #if defined(__CUDACC__)
   T.tile = tile;
 #endif
-  T.ws = bt.ws + (long)tile * (P.N + 1) * (REC * TL);
-  T.gt = bt.gtab ? bt.gtab + (long)tile * P.N * (GT * TL) : nullptr;
+  T.gen = P.fast ? 0 : 1;
+  T.rstride = (long)bt.rfields * TL;
+  T.ws = bt.ws + (long)tile * (P.N + 1) * T.rstride;
   T.nst = bt.nst + (long)tile * (P.N + 1);
 }
 

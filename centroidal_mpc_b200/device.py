@@ -23,7 +23,9 @@ def _ptr(t):
 # QP settings used when friction upper bounds are bound (stochastic mode) unless the caller overrides
 # them: the multiplier iteration of a polish round needs more sweeps to reach the 1e-9 certificate with
 # back-offs (bound gait: 3 sweeps leave a quarter of the instances uncertified for several attempts),
-# and the active set needs up to 13 correction rounds at N = 100.
+# and the active set needs up to 13 correction rounds at N = 100.  The library
+# applies the same values by itself when it is called with qp = NULL and upper bounds are bound
+# (cmpc_api.cu: launch_tiles), so a C caller gets them without knowing this table.
 STOCHASTIC_QP_DEFAULTS = dict(polish_refine_iter=10, polish_active_set_rounds=19)
 
 
@@ -43,8 +45,9 @@ class BatchSolver:
             L.check(self.lib.cmpc_create(C.byref(self.dims), C.byref(self.handle)), self.lib)
         B, N, nu = batch.B, batch.N, batch.nu
         f64 = torch.float64
-        self.X = torch.empty((B, N + 1, 9), dtype=f64, device=self.device)
-        self.U = torch.empty((B, N, nu), dtype=f64, device=self.device)
+        self.X = torch.zeros((B, N + 1, 9), dtype=f64, device=self.device)   # zeros: nothing is written for an
+        self.U = torch.zeros((B, N, nu), dtype=f64, device=self.device)      # instance whose QP fails
+        self._stream = None
         self.ints = torch.zeros((5, B), dtype=torch.int32, device=self.device)
         self.info = torch.zeros((B, 12), dtype=f64, device=self.device)
         self.d = {}
@@ -54,6 +57,14 @@ class BatchSolver:
     def upload(self, batch):
         """Host -> device copy of the problem data and (re)binding of the pointers."""
         torch = _torch_cuda()
+        if (batch.B, batch.N, batch.nc, 1 if batch.shared_plan else 0) != \
+                (self.dims.batch, self.dims.N, self.dims.nc, self.dims.shared_plan):
+            raise L.CmpcError("upload(): batch dims (B=%d, N=%d, nc=%d, shared_plan=%s) differ from the handle's "
+                              "(B=%d, N=%d, nc=%d, shared_plan=%d)" % (batch.B, batch.N, batch.nc, batch.shared_plan,
+                                                                       self.dims.batch, self.dims.N, self.dims.nc,
+                                                                       self.dims.shared_plan))
+        self.batch = batch
+        self.model = L.make_model_struct(batch.proto)
         for name in ("x_init", "x_final", "X_ref", "U_init", "contact_pos", "contact_R", "contact_active"):
             a = getattr(batch, name)
             self.d[name] = None if a is None else torch.from_numpy(a).to(self.device, non_blocking=True)
@@ -77,6 +88,7 @@ class BatchSolver:
         scp = L.make_scp_struct(scp_params)
         qp = L.make_qp_struct(self._qp(qp_overrides), self.lib)
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._stream = None if stream is None else torch.cuda.ExternalStream(stream, device=self.device)
         with torch.cuda.device(self.device):
             L.check(self.lib.cmpc_solve_scp(self.handle, C.byref(scp), C.byref(qp), _ptr(self.X), _ptr(self.U),
                                             _ptr(self.ints[0]), _ptr(self.ints[1]), _ptr(self.ints[2]),
@@ -88,14 +100,25 @@ class BatchSolver:
             return overrides
         return dict(STOCHASTIC_QP_DEFAULTS, **(overrides or {}))
 
+    def _wait_for_solve(self):
+        """Orders torch's current stream after the stream the last solve() ran on (a raw stream handed in
+        by the caller is not ordered with torch's streams by itself)."""
+        if self._stream is not None:
+            torch = _torch_cuda()
+            torch.cuda.current_stream(self.device).wait_stream(self._stream)
+
     def stats(self):
-        L.check(self.lib.cmpc_get_stats(self.handle, _ptr(self.ints[3]), _ptr(self.ints[4]), _ptr(self.info)),
-                self.lib)
+        torch = _torch_cuda()
+        self._wait_for_solve()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.cmpc_get_stats(self.handle, _ptr(self.ints[3]), _ptr(self.ints[4]), _ptr(self.info),
+                                        C.c_void_p(st)), self.lib)
         return dict(qp_iters=self.ints[3].cpu().numpy(), n_factor=self.ints[4].cpu().numpy(),
                     info=self.info.cpu().numpy())
 
     def results(self):
         """Device -> host: dict of numpy arrays."""
+        self._wait_for_solve()
         ints = self.ints.cpu().numpy()
         return dict(X=self.X.cpu().numpy(), U=self.U.cpu().numpy(), scp_iters=ints[0], status=ints[1],
                     n_accepted=ints[2])

@@ -72,7 +72,8 @@ typedef struct {
 } cmpc_qp_settings;
 
 /* status[] values */
-enum { CMPC_OK = 0, CMPC_QP_MAX_ITER = 1, CMPC_QP_NUMERIC = 2 };
+enum { CMPC_OK = 0, CMPC_QP_MAX_ITER = 1, CMPC_QP_NUMERIC = 2,
+       CMPC_DEVICE_ERROR = 3 /* a staged copy of the instance's tile never completed; the other tiles are unaffected */ };
 
 void cmpc_default_qp_settings(cmpc_qp_settings* s);
 
@@ -117,8 +118,9 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
 /* Per-instance statistics of the last solve (device pointers, each nullable):
  * qp_iters[B] total ADMM iterations, n_factor[B] Riccati factorisations, info[B][12] =
  * {sigma_max(X-Xbar), accuracy ratio, primal res, dual res, rho, radius, weight, polished,
- *  multiplier-method sweeps, polish attempts, 0, 0}. */
-int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info);
+ *  multiplier-method sweeps, polish attempts, 0, 0}.  Asynchronous copies on `stream` (pass the stream
+ * of the solve, so that they are ordered after it). */
+int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info, void* stream);
 
 /* compute_trajectory_data (src/centroidal_model.py:257-291): f, A=df/dx, B=df/du along (X,U).
  * X [B][N+1][9], U [B][N][nu] -> f [B][N][9], fx [B][N][9][9], fu [B][N][9][nu]. */

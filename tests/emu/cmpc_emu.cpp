@@ -9,7 +9,11 @@
 // It is NOT part of libcmpc_b200.so, exports different symbol names (cmpc_emu_*), and nothing
 // in the product package loads it: the product path fails loudly without CUDA.
 #include <stdlib.h>
+#include <stdio.h>
 #include <vector>
+#if defined(CMPC_NL) && CMPC_NL > 1
+#include <ucontext.h>
+#endif
 
 #include "../../centroidal_mpc_b200/csrc/cmpc_params.h"
 #include "../../centroidal_mpc_b200/csrc/cmpc_tile.cuh"
@@ -17,35 +21,92 @@
 
 using namespace cmpc;
 
+// one lane (t = instance lane of the tile, q = lane of the instance's team): what a CUDA thread of
+// run_tile (cmpc_api.cu) does for its instance
 template <bool FAST>
-static void run_tile_host(const Params& prm, const Batch& bt, int tile) {
+static void run_lane(const Params& prm, const Batch& bt, TileCtx T, int tile, int t, int q) {
+  Inst I;
+  Sv S;
+  Drv D;
+  bind_instance(I, prm, bt, tile * TL + t);
+  I.sub = q;
+  double mq = 0.0, mc = 0.0;
+  int nconv = 0;
+  setup_knots(prm, T, I, true, &mq, &mc, &nconv);
+  setup_finish(I, S, mq, mc, nconv);
+  team_sync(I);
+  drv_init(prm, S, D);
+  for (int op = advance(prm, S, D); op != OP_DONE; op = advance(prm, S, D))
+    execute<FAST>(op, prm, T, I, bt, S, D, true, D.check != 0);
+  write_stats(bt, I, S, D);
+}
+
+#if CMPC_NL > 1
+// lock-step build: the NL lanes of a team are coroutines that switch at every team_sync
+namespace {
+ucontext_t g_main, g_ctx[NL];
+int g_cur = 0;
+bool g_done[NL];
+struct LaneArgs { const Params* prm; const Batch* bt; const TileCtx* T; int tile, t, fast; } g_args;
+void lane_entry(int q) {
+  if (g_args.fast) run_lane<true>(*g_args.prm, *g_args.bt, *g_args.T, g_args.tile, g_args.t, q);
+  else run_lane<false>(*g_args.prm, *g_args.bt, *g_args.T, g_args.tile, g_args.t, q);
+  g_done[q] = true;
+  swapcontext(&g_ctx[q], &g_main);
+}
+}  // namespace
+void cmpc::cmpc_emu_yield() { swapcontext(&g_ctx[g_cur], &g_main); }
+static int run_team(const Params& prm, const Batch& bt, const TileCtx& T, int tile, int t, bool fast) {
+  static std::vector<char> stacks((size_t)NL << 20);
+  g_args = LaneArgs{&prm, &bt, &T, tile, t, fast ? 1 : 0};
+  for (int q = 0; q < NL; ++q) {
+    getcontext(&g_ctx[q]);
+    g_ctx[q].uc_stack.ss_sp = stacks.data() + ((size_t)q << 20);
+    g_ctx[q].uc_stack.ss_size = (size_t)1 << 20;
+    g_ctx[q].uc_link = &g_main;
+    g_done[q] = false;
+    makecontext(&g_ctx[q], (void (*)())lane_entry, 1, q);
+  }
+  for (;;) {   // one round = every lane runs up to its next team_sync
+    int ndone = 0;
+    for (int q = 0; q < NL; ++q) {
+      g_cur = q;
+      swapcontext(&g_main, &g_ctx[q]);
+      ndone += g_done[q] ? 1 : 0;
+    }
+    if (ndone == NL) return 0;
+    if (ndone != 0) { fprintf(stderr, "cmpc_emu: the lanes of a team disagree on the number of team_sync calls\n"); return -9; }
+  }
+}
+#else
+static int run_team(const Params& prm, const Batch& bt, const TileCtx& T, int tile, int t, bool fast) {
+  if (fast) run_lane<true>(prm, bt, T, tile, t, 0);
+  else run_lane<false>(prm, bt, T, tile, t, 0);
+  return 0;
+}
+#endif
+
+static int run_tile_host(const Params& prm, const Batch& bt, int tile, std::vector<double>& scratch) {
   TileCtx T;
   bind_tile(T, prm, bt, tile);
-  Inst I[TL];
-  Sv S[TL];
-  Drv D[TL];
-  int live[TL];
+  T.scratch = scratch.data();
   for (int k = 0; k <= prm.N; ++k) T.nst[k] = 0;
-  for (int l = 0; l < TL; ++l) {
-    const int b = tile * TL + l;
-    live[l] = b < bt.B;
-    if (!live[l]) continue;
-    bind_instance(I[l], prm, bt, b);
-    double mq = 0.0, mc = 0.0;
-    setup_knots(prm, T, I[l], 0, 1, &mq, &mc);
-    setup_finish(I[l], S[l], mq, mc);
-    for (int k = 0; k <= prm.N; ++k) {
-      const int ns = meta_of(T, I[l], k)[0] & 7;
+  for (int t = 0; t < TL; ++t) {   // slots per knot of the tile: the record layout of the knot
+    const int b = tile * TL + t;
+    if (b >= bt.B) continue;
+    Inst I;
+    bind_instance(I, prm, bt, b);
+    for (int k = 0; k < prm.N; ++k) {
+      const int ns = active_slots(prm, I, k);
       if (ns > T.nst[k]) T.nst[k] = ns;
     }
   }
-  for (int l = 0; l < TL; ++l) {
-    if (!live[l]) continue;
-    drv_init(prm, S[l], D[l]);
-    for (int op = advance(prm, S[l], D[l]); op != OP_DONE; op = advance(prm, S[l], D[l]))
-      execute<FAST>(op, prm, T, I[l], bt, S[l], D[l], true, D[l].check != 0);
-    write_stats(bt, I[l], S[l], D[l]);
+  for (int t = 0; t < TL; ++t) {
+    if (tile * TL + t >= bt.B) continue;
+    int rc = run_team(prm, bt, T, tile, t, prm.fast != 0);
+    if (rc) return rc;
   }
+  return 0;
 }
 
 // stochastic mode: friction-row upper bounds [B][N][nc][4] used by the following solves (null = nominal)
@@ -63,9 +124,11 @@ extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model
   if (rc) return rc;
   if (g_fub) prm.fast = 0;
   const int B = dims->batch, N = dims->N;
-  WsSizes w1 = ws_sizes(TL, N);   // tiles run one after the other: one tile of workspace
-  WsSizes wb = ws_sizes(B, N);
-  std::vector<double> ws(w1.ws), gtab(w1.gtab);
+  WsSizes w1 = ws_sizes(TL, N, dims->nc);   // tiles run one after the other: one tile of workspace
+  WsSizes wb = ws_sizes(B, N, dims->nc);
+  const int rfields = rec_fields(dims->nc, !prm.fast);
+  const long tile_ws = (long)(N + 1) * rfields * TL;
+  std::vector<double> ws(w1.ws), scratch((size_t)X_FAC_END * TL);
   std::vector<int> nst(w1.nst);
   for (int tile = 0; tile < wb.tiles; ++tile) {
     Batch bt;
@@ -74,20 +137,21 @@ extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model
     bt.cpos = contact_pos; bt.cR = contact_R; bt.cact = contact_active;
     bt.plan_stride = dims->shared_plan ? 0 : 1;
     bt.fub = g_fub;
+    bt.rfields = rfields;
     // workspace views shifted so that this tile lands on the single-tile buffers
-    bt.ws = ws.data() - (long)tile * w1.ws;
-    bt.gtab = prm.fast ? nullptr : gtab.data() - (long)tile * w1.gtab;
+    bt.ws = ws.data() - (long)tile * tile_ws;
     bt.nst = nst.data() - (long)tile * w1.nst;
     bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = scp_iters; bt.status = status;
     bt.n_accepted = n_accepted; bt.qp_iters = qp_iters; bt.n_factor = n_factor; bt.info = info;
     std::fill(ws.begin(), ws.end(), 0.0);
-    if (prm.fast) run_tile_host<true>(prm, bt, tile);
-    else run_tile_host<false>(prm, bt, tile);
+    rc = run_tile_host(prm, bt, tile, scratch);
+    if (rc) return rc;
   }
   return 0;
 }
 
-extern "C" int cmpc_emu_record_doubles(void) { return REC; }
+extern "C" int cmpc_emu_team_lanes(void) { return NL; }
+extern "C" int cmpc_emu_record_doubles(void) { return REC_MAX; }
 
 // host run of csrc/cmpc_lqr.cuh with the loop structure of cmpc_lqr_gains_kernel / cmpc_covs_kernel
 extern "C" int cmpc_emu_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w,

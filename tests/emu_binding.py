@@ -14,31 +14,37 @@ _SRC = os.path.join(_HERE, "emu", "cmpc_emu.cpp")
 _SO = os.path.join(_HERE, "emu", "libcmpc_emu.so")
 _DEPS = [os.path.join(_HERE, "..", "centroidal_mpc_b200", "csrc", f)
          for f in ("cmpc_core.cuh", "cmpc_tile.cuh", "cmpc_lqr.cuh", "cmpc_params.h")] + [_SRC]
-_lib = None
+_libs = {}
 
 
-def build(force=False):
+def build(force=False, team_lanes=1):
+    """team_lanes = 1: one host thread of control per instance.  team_lanes = 8: the lock-step build, in
+    which the 8 lanes of an instance's team run as coroutines that switch at every team_sync, i.e. the
+    work split, the shared-memory exchanges and the synchronisation points of the CUDA kernel."""
+    so = _SO if team_lanes == 1 else _SO.replace(".so", "_nl%d.so" % team_lanes)
     newest = max(os.path.getmtime(f) for f in _DEPS)
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-x", "c++", "-o", _SO, _SRC])
-    return _SO
+    if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC",
+                               "-DCMPC_NL=%d" % team_lanes, "-x", "c++", "-o", so + ".tmp", _SRC])
+        os.replace(so + ".tmp", so)
+    return so
 
 
-def load():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-    return _lib
+def load(team_lanes=1):
+    if team_lanes not in _libs:
+        _libs[team_lanes] = C.CDLL(build(team_lanes=team_lanes))
+        assert _libs[team_lanes].cmpc_emu_team_lanes() == team_lanes
+    return _libs[team_lanes]
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def solve_scp(batch, scp_params, qp_overrides=None, friction_ub=None):
+def solve_scp(batch, scp_params, qp_overrides=None, friction_ub=None, team_lanes=1):
     """Run the host build of the device solver on a ProblemBatch; returns a dict of arrays.
     ``friction_ub`` [B,N,nc,4]: stochastic mode (upper bounds of the friction rows)."""
-    lib = load()
+    lib = load(team_lanes)
     lib.cmpc_emu_set_friction_ub.argtypes = [C.c_void_p]
     lib.cmpc_emu_set_friction_ub.restype = None
     fub = None if friction_ub is None else np.ascontiguousarray(friction_ub, dtype=np.float64)

@@ -369,3 +369,33 @@ def test_stochastic_headline_horizon_certifies_at_the_first_attempt():
     assert (tuned["status"] == 0).all() and (tuned["qp_iters"] == 20).all() and (tuned["info"][:, 9] == 1).all()
     assert plain["qp_iters"].max() > 20
     assert relerr(tuned["X"], plain["X"]) < TOL and relerr(tuned["U"], plain["U"]) < TOL
+
+
+# ---- the team work split of the CUDA kernel (8 lanes per instance), run in lock step on the host ----
+def _assert_same(a, b):
+    for key in ("X", "U", "scp_iters", "status", "n_accepted", "qp_iters", "n_factor", "info"):
+        np.testing.assert_array_equal(a[key], b[key], err_msg=key)
+
+
+@pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
+def test_team_of_8_lanes_is_bitwise_equal_to_one_lane(cases, name):
+    """Owner-computes work split + shared-memory exchanges + team_sync points of the kernel (NL = 8,
+    coroutines in lock step) against the single-lane host build: every output bit, every count."""
+    conf, models = cases[name]
+    batch = ProblemBatch(models[:3])
+    _assert_same(E.solve_scp(batch, conf.scp_params, team_lanes=8), E.solve_scp(batch, conf.scp_params))
+
+
+def test_team_of_8_lanes_trust_region_and_general_friction_paths(cases):
+    conf, models = cases["solo12_trot"]
+    sp = dict(conf.scp_params, trust_region_radius0=0.05, max_iterations=3)     # kappa rows of the polish bind
+    batch = ProblemBatch(models[:2])
+    _assert_same(E.solve_scp(batch, sp, team_lanes=8), E.solve_scp(batch, sp))
+    # general friction path: upper bounds on the friction rows (stochastic mode)
+    fub = -0.05 * np.abs(np.random.default_rng(3).normal(size=(batch.B, batch.N, batch.nc, 4)))
+    a = E.solve_scp(batch, conf.scp_params, friction_ub=fub, team_lanes=8)
+    b = E.solve_scp(batch, conf.scp_params, friction_ub=fub)
+    _assert_same(a, b)
+    # no early polish: ADMM runs to OSQP's termination test (CHECK sweeps, rho adaptation, rescale)
+    qp = dict(active_set_start=0)
+    _assert_same(E.solve_scp(batch, conf.scp_params, qp_overrides=qp, team_lanes=8), E.solve_scp(batch, conf.scp_params, qp_overrides=qp))
