@@ -40,11 +40,24 @@ constexpr int THREADS = 32;
 constexpr int BAR_BYTES = 64;   // 4 mbarriers ("full" per ring slot) + padding
 inline long scp_smem_bytes(int N, bool gen) { return (long)tile_smem_fields(gen) * TL * 8 + BAR_BYTES + ((N + 1 + 15) & ~15); }
 
+#if defined(CMPC_PROFILE)
+// profiling build: cycles per operation kind summed over all warps (lane 0 of each warp)
+// [0..9] per Op code (sweeps: whole op), [10] backward part of ADMM sweeps, [11] of PMM sweeps,
+// [12] setup, [13] whole tile, [14] cycles waiting for bulk copies, [15] number of waits
+__device__ unsigned long long g_prof[16];
+#endif
+
 template <bool FAST>
 __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& T, unsigned char* nst_s) {
   const int lane = (int)(threadIdx.x & 31u);
   const int t = lane & (TL - 1), q = lane / TL;
   bind_tile(T, prm, bt, tile);
+#if defined(CMPC_PROFILE)
+  long long prof[16];
+  for (int i = 0; i < 16; ++i) prof[i] = 0;
+  T.prof = prof;
+  const long long tile_t0 = clock64();
+#endif
   const int b = tile * TL + t;
   const bool live = b < bt.B;
   Inst I;
@@ -69,6 +82,9 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
     setup_finish(I, S, mq, mc, nconv);
   }
   __syncwarp();
+#if defined(CMPC_PROFILE)
+  prof[12] += clock64() - tile_t0;
+#endif
   int op = OP_DONE;
   if (live) {
     drv_init(prm, S, D);
@@ -84,6 +100,11 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
     __syncwarp();
   }
   if (live) write_stats(bt, I, S, D);
+#if defined(CMPC_PROFILE)
+  prof[13] += clock64() - tile_t0;
+  if (lane == 0)
+    for (int i = 0; i < 16; ++i) atomicAdd(&g_prof[i], (unsigned long long)prof[i]);
+#endif
 }
 
 template <bool FAST>
@@ -541,6 +562,20 @@ int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, doubl
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+// profiling build only (-DCMPC_PROFILE): reads and clears the cycle counters; returns -1 in a normal build
+int cmpc_debug_profile(double* out16) {
+#if defined(CMPC_PROFILE)
+  unsigned long long h[16], z[16] = {0};
+  CUDA_TRY(cudaMemcpyFromSymbol(h, g_prof, sizeof(h)));
+  CUDA_TRY(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
+  for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
+  return 0;
+#else
+  (void)out16;
+  return -1;
+#endif
 }
 
 int cmpc_fp64_peak(double* tflops, double* ms_out) {

@@ -60,7 +60,7 @@ constexpr int TL = CMPC_TL;   // instances per tile
 // uniform: the maximum over the tile's instances, an instance with fewer active contacts pads with
 // slots whose B columns are zero) and on whether the general friction table is present (gen):
 //   A  Pc[9]                       factor -> backward sweep            P_{k+1} c_k
-//   M  Hn[na*na], Kt[9*na]         factor -> sweeps     Hn = -Huu^-1 (full square), Kt[i*na+j] = K[j][i]
+//   M  Hn[na][nap], Kt[9][nap]     factor -> sweeps     Hn = -Huu^-1 (full square), Kt[i][j] = -K[j][i]; nap = na | 1
 //   C  meta, xbar[9], S[3], ck[3], d[na]     stage data, constant during a solve
 //   G  per slot G[12] e2[4] ub[4]            general friction rows (rotated contacts / stochastic mode)
 //   D  vk[3], vf[4 ns]             ADMM iterate
@@ -69,15 +69,16 @@ constexpr int TL = CMPC_TL;   // instances per tile
 //   -  x[9], u[na]                 solution
 // The order makes the fields of the ADMM sweeps contiguous: backward = [A .. D], forward = [Kt .. E].
 struct Lay {
-  int na, pc, hn, kt, meta, xb, s, ck, d, g, vk, vf, dv, yk, yf, x, u, end;
+  int na, nap, pc, hn, kt, meta, xb, s, ck, d, g, vk, vf, dv, yk, yf, x, u, end;
 };
 CMPC_CX Lay lay_of(int ns, bool gen) {
   Lay L{};
   L.na = 3 * ns;
+  L.nap = ns > 0 ? (L.na | 1) : 0;   // row stride of [Hn; Kt]: odd, so that the rows of the lanes of a team fall into different banks
   L.pc = 0;
   L.hn = 9;
-  L.kt = L.hn + L.na * L.na;
-  L.meta = L.kt + 9 * L.na;   // one field = 2*TL int32: [t] meta (bits 0..2 slots, 4..11 contact id per slot), [TL+t] active set
+  L.kt = L.hn + L.na * L.nap;
+  L.meta = L.kt + 9 * L.nap;   // one field = 2*TL int32: [t] meta (bits 0..2 slots, 4..11 contact id per slot), [TL+t] active set
   L.xb = L.meta + 1;          // xbar[9]: linearisation point, q = -Wx xbar (cost.py:21-29), kbar = xbar[6:9]
   L.s = L.xb + 9;             // S[3]: sum of active fbar, A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
   L.ck = L.s + 3;             // ck[3]: affine term rows 6..8, -dt S x cbar (row 5 is dt m g)

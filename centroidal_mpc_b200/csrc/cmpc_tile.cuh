@@ -162,6 +162,15 @@ CMPC_HD int team_sum(const Inst& I, ScratchPtr xs, int v) {
 }
 #endif
 CMPC_HD int sub_of(const Inst& I) { return NL == 1 ? 0 : I.sub; }
+// true when the predicate holds for every instance of the tile (device: the whole warp; host build: the
+// instances of a tile run one after the other, each for itself)
+CMPC_HD bool tile_all(bool v) {
+#if defined(__CUDACC__)
+  return __all_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
 
 struct TileCtx {
   double* ws;      // tile workspace [N+1][rfields][TL]
@@ -171,6 +180,9 @@ struct TileCtx {
 #if defined(__CUDACC__)
   unsigned smem_sa, bars_sa, phases;   // the warp's shared memory (scratch, ring), its mbarriers; warp-uniform
   int tile;
+#if defined(CMPC_PROFILE)
+  long long* prof;                     // cycle counters of a profiling build (scripts/prof_cycles.py)
+#endif
   const unsigned char* nst_s;          // shared copy of nst
   CMPC_HD int ns(int k) const { return nst_s[k]; }
 #else
@@ -219,11 +231,14 @@ template <int SK, bool GEN>
 struct KnotStream {
   static constexpr int DEPTH = ring_depth(SK, GEN);
   static constexpr int SLOTF = slot_fields(SK, GEN);
-  unsigned ring_sa, bars_sa, phases;
+  unsigned ring_sa, bars_sa, phases, pre;
   int lane, s_wait, k_issue, n_left, dir, s_issue, lost;
   const double* ws;
   long rstride;
   const unsigned char* nst_s;
+#if defined(CMPC_PROFILE)
+  long long* prof;
+#endif
 
   CMPC_HD void issue() {   // lane 0: knot k_issue into slot s_issue
     const int k = k_issue;
@@ -254,8 +269,11 @@ struct KnotStream {
   CMPC_HD void open(TileCtx& Tc, const Inst& I, int k_first, int count, int direction) {
     ring_sa = Tc.smem_sa + (unsigned)ring_base(SK) * (TL * 8u);
     bars_sa = Tc.bars_sa; phases = Tc.phases;
-    lane = I.lane; s_wait = 0; s_issue = 0; k_issue = k_first; n_left = count; dir = direction; lost = 0;
+    lane = I.lane; s_wait = 0; s_issue = 0; k_issue = k_first; n_left = count; dir = direction; lost = 0; pre = 0;
     ws = Tc.ws; rstride = Tc.rstride; nst_s = Tc.nst_s;
+#if defined(CMPC_PROFILE)
+    prof = Tc.prof;
+#endif
     // earlier generic-proxy writes of this warp (records written by the previous operation) must be
     // visible to the async proxy before the bulk copies read them
     asm volatile("fence.proxy.async;" ::: "memory");
@@ -272,9 +290,28 @@ struct KnotStream {
       for (int i = 0; i < DEPTH && n_left > 0; ++i) issue();
     }
   }
+  // non-blocking look at the NEXT slot's barrier (call between acquire and release): its latency hides behind
+  // the arithmetic of the current knot, and the next acquire does not have to ask again when the copy is there
+  CMPC_HD void peek() {
+    const int s_next = (s_wait + 1 == DEPTH) ? 0 : s_wait + 1;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(pre) : "r"(bars_sa + 8u * s_next), "r"((phases >> s_next) & 1u) : "memory");
+  }
   CMPC_HD StagedPtr acquire() {
     const unsigned bar = bars_sa + 8u * s_wait;
-    if (!mbar_wait(bar, (phases >> s_wait) & 1u)) lost = 1;
+#if defined(CMPC_PROFILE)
+    const long long t0_ = clock64();
+#endif
+    if (!pre && !mbar_wait(bar, (phases >> s_wait) & 1u)) lost = 1;
+    pre = 0;
+#if defined(CMPC_PROFILE)
+    prof[14] += clock64() - t0_;
+    prof[15] += 1;
+#endif
     phases ^= 1u << s_wait;
     return ring_sa + (unsigned)((s_wait * SLOTF) * TL + lane) * 8u;
   }
@@ -299,6 +336,7 @@ struct KnotStream {
   CMPC_HD void open(TileCtx& T, const Inst& I, int k_first, int, int direction) {
     ws = T.ws; rstride = T.rstride; lane = I.lane; dir = direction; k = k_first;
   }
+  CMPC_HD void peek() {}
   CMPC_HD StagedPtr acquire() const { return ws + (long)k * rstride + lane; }
   CMPC_HD void release() { k += dir; }
   CMPC_HD int close(TileCtx&) { return 0; }
@@ -466,16 +504,16 @@ CMPC_HD double pick3(double a, double b, double c, int i) { return i == 0 ? a : 
 // Backward over k.  The symmetric tableau  T = [[Huu, Hux],[Hux', Q + A'PA]]  (Huu = R + B'PB, Hux = B'PA;
 // n = na + 9 rows, controls first) is swept on its na control pivots (SPD, no pivoting):
 //   T -> [[-Huu^-1, Huu^-1 Hux],[Hux' Huu^-1, Q + A'PA - Hux' Huu^-1 Hux]],
-// which delivers Hn = -Huu^-1, K' = -Hux' Huu^-1 and P_k in one pass.  Pc = P c.
+// which delivers Hn = -Huu^-1, Kt = Hux' Huu^-1 = -K' and P_k in one pass.  Pc = P c.
 // ADMM mode: R = W_u + rho G'E2G, Q = W_x + rho_k I (kappa); multiplier mode: active friction rows and
 // kappa rows carry the penalty 1/delta.
-// Team work split: lane q owns the tableau rows q, q + NL, ... as FULL rows in registers.  P (square,
-// symmetric) and Y = P [B A] go through the scratch; per pivot the owners publish their entry of the
-// pivot column (double-buffered), everybody reads the column and updates its own rows.
+// Team work split: lane q owns the tableau rows q, q + NL, ... in registers: the control columns of every
+// row (they are the factor record [Hn; Kt]) and the state columns of the state rows; the state columns of
+// the control rows are the mirror image of the control columns of the state rows and are never formed.
 template <int NS, int MODE, bool FAST, int SK>
 CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const Inst& I, int k, ScratchPtr xs, bool on) {
   constexpr Lay L = lay_of(NS, !FAST);
-  constexpr int NA = 3 * NS, n = NA + 9;
+  constexpr int NA = 3 * NS, n = NA + 9, NAP = L.nap;
   constexpr int RT = (n + NL - 1) / NL;   // tableau rows per lane
   constexpr int ST = (9 + NL - 1) / NL;   // state rows per lane
   const int q = sub_of(I);
@@ -531,18 +569,19 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
     }
   }
   team_sync(I);
-  // ---- phase 2: the lane's tableau rows, full rows in registers
-  double T[RT][n];
+  // ---- phase 2: the lane's tableau rows in registers: control columns by slot, state columns
+  double Tc[RT][NS > 0 ? NS : 1][3], Ts[RT][9];
 #pragma unroll
   for (int t = 0; t < RT; ++t) {
     const int rr = q + NL * t;
-    if (rr < NA) {   // control row (s, a):  B' Y  + R block
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Ts[t][c] = 0.0;
+#pragma unroll
+    for (int e = 0; e < NA; ++e) Tc[t][e / 3][e % 3] = 0.0;
+    if (rr < NA) {   // control row (s, a):  B' (P B)  + R block
       const int s = rr / 3, a = rr - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
       const double dtr = s < nsl ? P.dt : 0.0;
       const double dA = CMPC_SO(r, L.d, 3 * s + a2), dB = CMPC_SO(r, L.d, 3 * s + a1);
-#pragma unroll
-      for (int e = 0; e < n; ++e)
-        T[t][e] = dtr * fma(sp_ld(xs, X_Y + (6 + a1) * n + e), dA, fma(-sp_ld(xs, X_Y + (6 + a2) * n + e), dB, sp_ld(xs, X_Y + (3 + a) * n + e)));
       // R block of the slot: W_u + G' diag(rr) G, columns 3s .. 3s+2
       double gc[3][4], rw[4];
 #pragma unroll
@@ -573,11 +612,10 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
         radd[b2] = v;
       }
 #pragma unroll
-      for (int s2 = 0; s2 < NS; ++s2) {
-        if (s2 == s) {
-#pragma unroll
-          for (int b2 = 0; b2 < 3; ++b2) T[t][3 * s2 + b2] += radd[b2];
-        }
+      for (int e = 0; e < NA; ++e) {
+        double v = dtr * fma(sp_ld(xs, X_Y + (6 + a1) * n + e), dA, fma(-sp_ld(xs, X_Y + (6 + a2) * n + e), dB, sp_ld(xs, X_Y + (3 + a) * n + e)));
+        if (e / 3 == s) v += radd[e % 3];
+        Tc[t][e / 3][e % 3] = v;
       }
     } else if (rr < n) {   // state row i:  Hux' | Q + A'(P A)
       const int i = rr - NA;
@@ -585,10 +623,10 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
 #pragma unroll
-        for (int b2 = 0; b2 < 3; ++b2) {   // Hux[(s,b2)][i], the expression of the control row's owner
+        for (int b2 = 0; b2 < 3; ++b2) {   // Hux[(s,b2)][i]
           const int b1 = nxt3(b2), bp = prv3(b2);
-          T[t][3 * s + b2] = dts[s] * fma(sp_ld(xs, X_Y + (6 + b1) * n + NA + i), ds[s][bp],
-                                          fma(-sp_ld(xs, X_Y + (6 + bp) * n + NA + i), ds[s][b1], sp_ld(xs, X_Y + (3 + b2) * n + NA + i)));
+          Tc[t][s][b2] = dts[s] * fma(sp_ld(xs, X_Y + (6 + b1) * n + NA + i), ds[s][bp],
+                                      fma(-sp_ld(xs, X_Y + (6 + bp) * n + NA + i), ds[s][b1], sp_ld(xs, X_Y + (3 + b2) * n + NA + i)));
         }
       }
       // (A'X)[i][c] = X[i][c] + mul (X[rA][c] sA - X[rB][c] sB):  rows 0..2: dt [S]x', rows 3..5: dt/m, rows 6..8: -
@@ -605,56 +643,86 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
           if (MODE == MODE_ADMM && k >= 1 && i >= 6) v += S.rhok;
         }
         if (MODE == MODE_PMM && c >= 6 && kap && i >= 6) v += sp_ld(xs, X_KX + 3 + 3 * (i - 6) + (c - 6));
-        T[t][NA + c] = v;
+        Ts[t][c] = v;
       }
     }
   }
-  // ---- phase 3: sweep the control pivots
+  // ---- phase 3: sweep the control pivots, slot by slot.  The pivot columns of the current slot are always
+  // the first block of the row registers: after its three pivots the blocks are rotated by one (a loop
+  // over the slots with compile-time register indices; after NS rotations the order is the original one).
+  // Per pivot the owners publish their entry of the pivot column (double-buffered), everybody reads the
+  // column -- it is the pivot row as well -- and updates its rows.
+#pragma unroll 1
+  for (int sc = 0; sc < NS; ++sc) {
 #pragma unroll
-  for (int pv = 0; pv < NA; ++pv) {
-    const int cb = X_CX + (pv & 1) * 21;
+    for (int a = 0; a < 3; ++a) {
+      const int pv = 3 * sc + a;
+      const int cb = X_CX + (pv & 1) * 21;
 #pragma unroll
-    for (int t = 0; t < RT; ++t) {
-      const int rr = q + NL * t;
-      if (rr < n) sp_st(xs, cb + rr, T[t][pv]);
-    }
-    team_sync(I);
-    double c[n];
+      for (int t = 0; t < RT; ++t) {
+        const int rr = q + NL * t;
+        if (rr < n) sp_st(xs, cb + rr, Tc[t][0][a]);
+      }
+      team_sync(I);
+      double c[NS > 0 ? NS : 1][3], c9[9];
 #pragma unroll
-    for (int e = 0; e < n; ++e) c[e] = sp_ld(xs, cb + e);
-    const double piv = c[pv];
-    if (!(piv > 0.0) && on) S.fail = 1;
-    const double ip = 1.0 / piv;
+      for (int sj = 0; sj < NS; ++sj) {
+        const int so = sj + sc >= NS ? sj + sc - NS : sj + sc;   // the slot that sits in block sj now
 #pragma unroll
-    for (int t = 0; t < RT; ++t) {
-      const int rr = q + NL * t;
-      if (rr == pv) {            // the pivot row: scaled column, -1/pivot on the diagonal
+        for (int aj = 0; aj < 3; ++aj) c[sj][aj] = sp_ld(xs, cb + 3 * so + aj);
+      }
 #pragma unroll
-        for (int e = 0; e < n; ++e) T[t][e] = (e == pv) ? -ip : c[e] * ip;
-      } else {
-        const double bc = T[t][pv] * ip;
+      for (int cc = 0; cc < 9; ++cc) c9[cc] = sp_ld(xs, cb + NA + cc);
+      const double piv = c[0][a];
+      if (!(piv > 0.0) && on) S.fail = 1;
+      const double ip = 1.0 / piv;
 #pragma unroll
-        for (int e = 0; e < n; ++e) T[t][e] = (e == pv) ? bc : fma(-bc, c[e], T[t][e]);
+      for (int t = 0; t < RT; ++t) {
+        const int rr = q + NL * t;
+        const double bc = Tc[t][0][a] * ip;
+        if (rr == pv) {   // the pivot row: scaled column, -1/pivot on the diagonal
+#pragma unroll
+          for (int sj = 0; sj < NS; ++sj)
+#pragma unroll
+            for (int aj = 0; aj < 3; ++aj) Tc[t][sj][aj] = (sj == 0 && aj == a) ? -ip : c[sj][aj] * ip;
+        } else {
+#pragma unroll
+          for (int sj = 0; sj < NS; ++sj)
+#pragma unroll
+            for (int aj = 0; aj < 3; ++aj) Tc[t][sj][aj] = (sj == 0 && aj == a) ? bc : fma(-bc, c[sj][aj], Tc[t][sj][aj]);
+          if (NL * t + NL - 1 >= NA) {   // state columns (state rows only)
+#pragma unroll
+            for (int cc = 0; cc < 9; ++cc) Ts[t][cc] = fma(-bc, c9[cc], Ts[t][cc]);
+          }
+        }
       }
     }
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {   // rotate the slot blocks
+      const double t0 = Tc[t][0][0], t1 = Tc[t][0][1], t2 = Tc[t][0][2];
+#pragma unroll
+      for (int sj = 0; sj + 1 < NS; ++sj) {
+        Tc[t][sj][0] = Tc[t][sj + 1][0]; Tc[t][sj][1] = Tc[t][sj + 1][1]; Tc[t][sj][2] = Tc[t][sj + 1][2];
+      }
+      Tc[t][NS > 0 ? NS - 1 : 0][0] = t0; Tc[t][NS > 0 ? NS - 1 : 0][1] = t1; Tc[t][NS > 0 ? NS - 1 : 0][2] = t2;
+    }
   }
-  // ---- factor record M = [Hn; K'] and P_k (lower triangle, mirrored: P stays exactly symmetric)
+  // ---- factor record [Hn; Kt] and P_k (lower triangle, mirrored: P stays exactly symmetric)
 #pragma unroll
   for (int t = 0; t < RT; ++t) {
     const int rr = q + NL * t;
     if (rr < n) {
-      const double sg = rr < NA ? 1.0 : -1.0;
       if (on) {
 #pragma unroll
-        for (int l = 0; l < NA; ++l) CMPC_R(w, L.hn + rr * NA + l) = sg * T[t][l];
+        for (int l = 0; l < NA; ++l) CMPC_R(w, L.hn + rr * NAP + l) = Tc[t][l / 3][l % 3];
       }
       if (rr >= NA) {
         const int i = rr - NA;
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
           if (c <= i) {
-            sp_st(xs, X_PS + i * 9 + c, T[t][NA + c]);
-            sp_st(xs, X_PS + c * 9 + i, T[t][NA + c]);
+            sp_st(xs, X_PS + i * 9 + c, Ts[t][c]);
+            sp_st(xs, X_PS + c * 9 + i, Ts[t][c]);
           }
         }
       }
@@ -707,6 +775,7 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
 #define CMPC_FAC_RUN(NS_)                                                             \
   do {                                                                                \
     const StagedPtr r = ks.acquire();                                                 \
+    ks.peek();                                                                        \
     factor_knot<NS_, MODE, FAST, SK>(P, S, r, rec_of(T, I, k), I, k, xs, on);         \
     ks.release();                                                                     \
     --k;                                                                              \
@@ -726,7 +795,7 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
 }
 
 // ---------------------------------------------------------------- backward sweep (linear term)
-// p_N = qx_N;  g = p + Pc;  hu = ru + B'g;  d = Hn hu;  p = qx + A'g + K'hu.
+// p_N = qx_N;  g = p + Pc;  hu = ru + B'g;  d = Hn hu;  p = qx + A'g + K'hu  (the record holds Kt = -K').
 // qx = -Wx xbar (+ kappa / terminal penalty terms), ru = friction penalty terms.
 // Team work split: phase 1 the owners of the control rows publish hu; phase 2 the rows of [Hn; K'] hu
 // (na + 9 row tasks) by their owners, who write d to the record and the new p to the scratch.
@@ -750,79 +819,135 @@ CMPC_HD void kappa_linear_term(const Params& P, const Sv& S, StagedPtr r, const 
   }
 }
 
-template <int NS, int MODE, bool FAST, int SK>
-CMPC_HD void bwd_knot(const Params& P, const Sv& S, StagedPtr r, double* w, const Inst& I, int k, ScratchPtr xs, int buf, bool on) {
+// One run of knots with the same slot count.  Everything that depends only on the lane (which rows it
+// owns, their kind, their friction constants) is formed once, before the knots; the knot step itself is
+// branch-free: rows past the end are clamped to a valid row and only their stores are predicated, so that
+// the independent dot-product chains of the lane's rows interleave.
+template <int NS, int MODE, bool FAST, int SK, class KS>
+CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst& I, KS& ks, ScratchPtr xs, int& k_io, int& buf_io, bool on) {
   constexpr Lay L = lay_of(NS, !FAST);
-  constexpr int NA = 3 * NS, n = NA + 9;
+  constexpr int NA = 3 * NS, n = NA + 9, NAP = L.nap;
   constexpr int CT = (NA + NL - 1) / NL, RT = (n + NL - 1) / NL;
   const int q = sub_of(I);
-  const int nsl = CMPC_SI(r, L.meta, 0) & 7;
-  const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
-  const int pin = X_PX + buf * 9, pout = X_PX + (buf ^ 1) * 9;
-  if (k >= 1) {
-    double kl[3];
-    kappa_linear_term<NS, MODE, FAST, SK>(P, S, r, I, pm, kl);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) sp_st(xs, X_KX + a, kl[a]);
-  }
-  // ---- phase 1: hu of the lane's control rows
+  // the lane's control rows j = q + NL t  (hu_j)
+  int cj[CT > 0 ? CT : 1], cs[CT > 0 ? CT : 1], ca[CT > 0 ? CT : 1], ca1[CT > 0 ? CT : 1], ca2[CT > 0 ? CT : 1];
+  bool cok[CT > 0 ? CT : 1];
+  double cg[CT > 0 ? CT : 1][4];
 #pragma unroll
   for (int t = 0; t < CT; ++t) {
     const int j = q + NL * t;
-    if (j < NA) {
-      const int s = j / 3, a = j - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
-      const double dtr = s < nsl ? P.dt : 0.0;
-      double tt[4], gc[4];
-      CMPC_GCOL(gc, r, s, a);
-#pragma unroll
-      for (int row = 0; row < 4; ++row) {
-        FRow fr;
-        CMPC_FROW(fr, r, s, row);
-        if (MODE == MODE_ADMM) {
-          tt[row] = S.rho * fr.e2 * fabs(CMPC_SO(r, L.vf, 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
-          if (!FAST) tt[row] = fma(-S.rho * fr.e2, fr.ub, tt[row]);         // unshifted w = min(v, 0) + ub
-        } else {
-          const double y = CMPC_SO(r, L.yf, 4 * s + row);
-          tt[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? y : fma(-P.inv_delta, fr.ub, y)) : 0.0;
-        }
-      }
-      const double o = fma(gc[3], tt[3], fma(gc[2], tt[2], fma(gc[1], tt[1], gc[0] * tt[0])));
-      const double g0 = sp_ld(xs, pin + 3 + a) + CMPC_SO(r, L.pc, 3 + a);
-      const double gA = sp_ld(xs, pin + 6 + a1) + CMPC_SO(r, L.pc, 6 + a1);
-      const double gB = sp_ld(xs, pin + 6 + a2) + CMPC_SO(r, L.pc, 6 + a2);
-      sp_st(xs, X_UX + j, dtr * fma(gA, CMPC_SO(r, L.d, 3 * s + a2), fma(-gB, CMPC_SO(r, L.d, 3 * s + a1), g0)) + o);
-    }
+    cok[t] = j < NA;
+    cj[t] = cok[t] ? j : 0;
+    cs[t] = cj[t] / 3;
+    ca[t] = cj[t] - 3 * cs[t];
+    ca1[t] = ca[t] == 2 ? 0 : ca[t] + 1;
+    ca2[t] = ca[t] == 0 ? 2 : ca[t] - 1;
+    cg[t][0] = ca[t] == 0 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][1] = ca[t] == 0 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
+    cg[t][2] = ca[t] == 1 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][3] = ca[t] == 1 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
   }
-  team_sync(I);
-  // ---- phase 2: rows of [Hn; K'] hu
-  double hu[NA > 0 ? NA : 1];
-#pragma unroll
-  for (int l = 0; l < NA; ++l) hu[l] = sp_ld(xs, X_UX + l);
+  // the lane's rows rr = q + NL t of [Hn; Kt] hu: control rows give d, state rows the new p
+  int rrow[RT], ri[RT], rA[RT], rB[RT], roA[RT], roB[RT];
+  bool rok[RT], rst[RT], rg0[RT], rkx[RT];
+  double rmul[RT], rwx[RT];
 #pragma unroll
   for (int t = 0; t < RT; ++t) {
     const int rr = q + NL * t;
-    if (rr < n) {
-      double acc = 0.0;
+    rok[t] = rr < n;
+    rrow[t] = rok[t] ? rr : n - 1;
+    rst[t] = rrow[t] >= NA;
+    const int i = rst[t] ? rrow[t] - NA : 0;
+    const int g3 = i / 3, a = i - 3 * g3, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
+    ri[t] = i;
+    rg0[t] = g3 == 0;
+    rkx[t] = i >= 6;
+    rmul[t] = g3 == 0 ? P.dt : (g3 == 1 ? P.dt_m : 0.0);   // (A'g)_i = g_i + mul (g[rA] sA - g[rB] sB)
+    rA[t] = g3 == 0 ? 6 + a1 : a;
+    rB[t] = g3 == 0 ? 6 + a2 : a;
+    roA[t] = a2;
+    roB[t] = a1;
+    rwx[t] = pick9(P.Wx, i);
+  }
+  int k = k_io, buf = buf_io;
+  do {
+    const StagedPtr r = ks.acquire();
+    ks.peek();
+    double* w = rec_of(T, I, k);
+    const int nsl = CMPC_SI(r, L.meta, 0) & 7;
+    const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
+    const int pin = X_PX + buf * 9, pout = X_PX + (buf ^ 1) * 9;
+    if (k >= 1) {
+      double kl[3];
+      kappa_linear_term<NS, MODE, FAST, SK>(P, S, r, I, pm, kl);
 #pragma unroll
-      for (int l = 0; l < NA; ++l) acc = fma(CMPC_SO(r, L.hn, rr * NA + l), hu[l], acc);
-      if (rr < NA) {
-        if (on) CMPC_R(w, L.dv + rr) = acc;
-      } else {   // p_i = qx_i + (A'g)_i + (K'hu)_i
-        const int i = rr - NA;
-        const int g3 = i / 3, a = i - 3 * g3, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
-        const double mul = g3 == 0 ? P.dt : (g3 == 1 ? P.dt_m : 0.0);
-        const int rA = g3 == 0 ? 6 + a1 : a, rB = g3 == 0 ? 6 + a2 : a;
-        const double sA = g3 == 0 ? CMPC_SO(r, L.s, a2) : 1.0, sB = g3 == 0 ? CMPC_SO(r, L.s, a1) : 0.0;
+      for (int a = 0; a < 3; ++a) sp_st(xs, X_KX + a, kl[a]);
+    }
+    // ---- phase 1: hu of the lane's control rows
+#pragma unroll
+    for (int t = 0; t < CT; ++t) {
+      const int s = cs[t];
+      const double dtr = s < nsl ? P.dt : 0.0;
+      double tt[4], gc[4];
+#pragma unroll
+      for (int row = 0; row < 4; ++row) {
+        double e2 = row < 2 ? P.e2[0] : P.e2[2], ub = 0.0;
+        gc[row] = cg[t][row];
+        if (!FAST) {
+          gc[row] = CMPC_SO(r, L.g, s * GS + row * 3 + ca[t]);
+          e2 = CMPC_SO(r, L.g, s * GS + 12 + row);
+          ub = CMPC_SO(r, L.g, s * GS + 16 + row);
+        }
+        if (MODE == MODE_ADMM) {
+          tt[row] = S.rho * e2 * fabs(CMPC_SO(r, L.vf, 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
+          if (!FAST) tt[row] = fma(-S.rho * e2, ub, tt[row]);            // unshifted w = min(v, 0) + ub
+        } else {
+          const double y = CMPC_SO(r, L.yf, 4 * s + row);
+          tt[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? y : fma(-P.inv_delta, ub, y)) : 0.0;
+        }
+      }
+      const double o = fma(gc[3], tt[3], fma(gc[2], tt[2], fma(gc[1], tt[1], gc[0] * tt[0])));
+      const double g0 = sp_ld(xs, pin + 3 + ca[t]) + CMPC_SO(r, L.pc, 3 + ca[t]);
+      const double gA = sp_ld(xs, pin + 6 + ca1[t]) + CMPC_SO(r, L.pc, 6 + ca1[t]);
+      const double gB = sp_ld(xs, pin + 6 + ca2[t]) + CMPC_SO(r, L.pc, 6 + ca2[t]);
+      const double hu = dtr * fma(gA, CMPC_SO(r, L.d, 3 * s + ca2[t]), fma(-gB, CMPC_SO(r, L.d, 3 * s + ca1[t]), g0)) + o;
+      if (cok[t]) sp_st(xs, X_UX + cj[t], hu);
+    }
+    team_sync(I);
+    // ---- phase 2: rows of [Hn; Kt] hu (two partial sums per row: shorter dependent chains)
+    double hu[NA > 0 ? NA : 1];
+#pragma unroll
+    for (int l = 0; l < NA; ++l) hu[l] = sp_ld(xs, X_UX + l);
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < NA; l += 2) {
+        acc0 = fma(CMPC_SO(r, L.hn, rrow[t] * NAP + l), hu[l], acc0);
+        if (l + 1 < NA) acc1 = fma(CMPC_SO(r, L.hn, rrow[t] * NAP + l + 1), hu[l + 1], acc1);
+      }
+      const double acc = acc0 + acc1;
+      if (NL * t < NA) {             // this row can be a control row: d_j
+        if (rok[t] && !rst[t] && on) CMPC_R(w, L.dv + rrow[t]) = acc;
+      }
+      if (NL * t + NL - 1 >= NA) {   // this row can be a state row: p_i = qx_i + (A'g)_i + (K'hu)_i, Kt = -K'
+        const int i = ri[t];
+        const double sA = rg0[t] ? CMPC_SO(r, L.s, roA[t]) : 1.0, sB = rg0[t] ? CMPC_SO(r, L.s, roB[t]) : 0.0;
         const double gi = sp_ld(xs, pin + i) + CMPC_SO(r, L.pc, i);
-        const double gA = sp_ld(xs, pin + rA) + CMPC_SO(r, L.pc, rA);
-        const double gB = sp_ld(xs, pin + rB) + CMPC_SO(r, L.pc, rB);
-        double pi = fma(mul, fma(gA, sA, -(gB * sB)), gi) + acc - pick9(P.Wx, i) * CMPC_SO(r, L.xb, i);
-        if (k >= 1 && i >= 6) pi += sp_ld(xs, X_KX + (i - 6));
-        sp_st(xs, pout + i, pi);
+        const double gA = sp_ld(xs, pin + rA[t]) + CMPC_SO(r, L.pc, rA[t]);
+        const double gB = sp_ld(xs, pin + rB[t]) + CMPC_SO(r, L.pc, rB[t]);
+        double pi = fma(rmul[t], fma(gA, sA, -(gB * sB)), gi) - acc - rwx[t] * CMPC_SO(r, L.xb, i);
+        if (k >= 1 && rkx[t]) pi += sp_ld(xs, X_KX + (i - 6));
+        if (rok[t] && rst[t]) sp_st(xs, pout + i, pi);
       }
     }
-  }
-  team_sync(I);
+    team_sync(I);
+    buf ^= 1;
+    ks.release();
+    --k;
+  } while (k >= 0 && T.ns(k) == NS);
+  k_io = k;
+  buf_io = buf;
 }
 
 template <int MODE, bool FAST>
@@ -852,24 +977,15 @@ CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S
     ks.release();
     team_sync(I);
   }
-#define CMPC_BWD_RUN(NS_)                                                             \
-  do {                                                                                \
-    const StagedPtr r = ks.acquire();                                                 \
-    bwd_knot<NS_, MODE, FAST, SK>(P, S, r, rec_of(T, I, k), I, k, xs, buf, on);       \
-    buf ^= 1;                                                                         \
-    ks.release();                                                                     \
-    --k;                                                                              \
-  } while (k >= 0 && T.ns(k) == NS_)
-  for (int k = N - 1; k >= 0;) {
+  for (int k = N - 1; k >= 0;) {   // runs of equal slot count: one specialisation of the knot step per run
     switch (T.ns(k)) {
-      case 0: CMPC_BWD_RUN(0); break;
-      case 1: CMPC_BWD_RUN(1); break;
-      case 2: CMPC_BWD_RUN(2); break;
-      case 3: CMPC_BWD_RUN(3); break;
-      default: CMPC_BWD_RUN(4); break;
+      case 0: bwd_run<0, MODE, FAST, SK>(P, S, T, I, ks, xs, k, buf, on); break;
+      case 1: bwd_run<1, MODE, FAST, SK>(P, S, T, I, ks, xs, k, buf, on); break;
+      case 2: bwd_run<2, MODE, FAST, SK>(P, S, T, I, ks, xs, k, buf, on); break;
+      case 3: bwd_run<3, MODE, FAST, SK>(P, S, T, I, ks, xs, k, buf, on); break;
+      default: bwd_run<4, MODE, FAST, SK>(P, S, T, I, ks, xs, k, buf, on); break;
     }
   }
-#undef CMPC_BWD_RUN
   if (ks.close(T)) S_in.lost = 1;
 }
 
@@ -969,90 +1085,131 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
   }
 }
 
-template <int NS, int KIND, bool FAST, int SK>
-CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double* w, int* imw, const Inst& I,
-                      ScratchPtr xs, double* x, bool on, bool upd, int& nchg) {
+template <int NS, int KIND, bool FAST, int SK, class KS>
+CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Inst& I, KS& ks, ScratchPtr xs, double* x,
+                     int& k_io, bool on, bool upd, int& nchg) {
   constexpr Lay L = lay_of(NS, !FAST);
-  constexpr int NA = 3 * NS;
+  constexpr int NA = 3 * NS, NAP = L.nap;
   constexpr int CT = (NA + NL - 1) / NL, FT = (4 * NS + NL - 1) / NL;
   constexpr bool ADMM = KIND == FW_ADMM || KIND == FW_ADMM_CHECK, CHK = KIND == FW_ADMM_CHECK;
   constexpr bool PMMK = KIND == FW_PMM, COPY = KIND == FW_COPY;
   const int q = sub_of(I);
+  const int N = P.N;
   const double al = ADMM ? P.alpha : 1.0;
   const double inv = P.inv_delta;
-  const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
-  // ---- phase 1: controls u~ = K x + d of the lane's rows
-  double uo[CT > 0 ? CT : 1];
+  // the lane's control rows j = q + NL t (u_j) and friction rows bit = q + NL t (4 per slot)
+  int cj[CT > 0 ? CT : 1], cs[CT > 0 ? CT : 1], ca[CT > 0 ? CT : 1];
+  bool cok[CT > 0 ? CT : 1];
+  double cg[CT > 0 ? CT : 1][4];
 #pragma unroll
   for (int t = 0; t < CT; ++t) {
     const int j = q + NL * t;
-    uo[t] = 0.0;
-    if (j < NA) {
-      double v = CMPC_SO(r, L.dv, j);
+    cok[t] = j < NA;
+    cj[t] = cok[t] ? j : 0;
+    cs[t] = cj[t] / 3;
+    ca[t] = cj[t] - 3 * cs[t];
+    cg[t][0] = ca[t] == 0 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][1] = ca[t] == 0 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
+    cg[t][2] = ca[t] == 1 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][3] = ca[t] == 1 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
+  }
+  int fb[FT > 0 ? FT : 1], fs[FT > 0 ? FT : 1], frow[FT > 0 ? FT : 1];
+  bool fok[FT > 0 ? FT : 1];
+  double fgx[FT > 0 ? FT : 1], fgy[FT > 0 ? FT : 1], fe2[FT > 0 ? FT : 1];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) v = fma(CMPC_SO(r, L.kt, i * NA + j), x[i], v);
+  for (int t = 0; t < FT; ++t) {
+    const int bit = q + NL * t;
+    fok[t] = bit < 4 * NS;
+    fb[t] = fok[t] ? bit : 0;
+    fs[t] = fb[t] >> 2;
+    frow[t] = fb[t] & 3;
+    fgx[t] = frow[t] == 0 ? 1.0 : (frow[t] == 1 ? -1.0 : 0.0);
+    fgy[t] = frow[t] == 2 ? 1.0 : (frow[t] == 3 ? -1.0 : 0.0);
+    fe2[t] = frow[t] < 2 ? P.e2[0] : P.e2[2];
+  }
+  int k = k_io;
+  do {
+    const StagedPtr r = ks.acquire();
+    ks.peek();
+    double* w = rec_of(T, I, k);
+    int* imw = meta_of(T, I, k, L.meta);
+    if (on) fwd_state<NS, KIND, FAST, SK>(P, S, R, r, w, I, k, x);
+    const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
+    // ---- phase 1: controls u~ = K x + d of the lane's rows (Kt = -K'; two partial sums per row)
+    double uo[CT > 0 ? CT : 1];
+#pragma unroll
+    for (int t = 0; t < CT; ++t) {
+      const int j = cj[t];
+      double v0 = CMPC_SO(r, L.dv, j), v1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; i += 2) {
+        v0 = fma(-CMPC_SO(r, L.kt, i * NAP + j), x[i], v0);
+        if (i + 1 < 9) v1 = fma(-CMPC_SO(r, L.kt, (i + 1) * NAP + j), x[i + 1], v1);
+      }
+      const double v = v0 + v1;
       uo[t] = v;
-      sp_st(xs, X_UX + j, v);
-      if ((PMMK || COPY) && on) CMPC_R(w, L.u + j) = v;
+      if (cok[t]) {
+        sp_st(xs, X_UX + j, v);
+        if ((PMMK || COPY) && on) CMPC_R(w, L.u + j) = v;
+      }
     }
-  }
-  team_sync(I);
-  // ---- phase 2: next state (replicated), friction rows of the lane
-  double u[NA > 0 ? NA : 1];
+    team_sync(I);
+    // ---- phase 2: next state (replicated), friction rows of the lane
+    double u[NA > 0 ? NA : 1];
 #pragma unroll
-  for (int j = 0; j < NA; ++j) u[j] = sp_ld(xs, X_UX + j);
-  double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < NA; ++j) u[j] = sp_ld(xs, X_UX + j);
+    double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    const double ds[3] = {CMPC_S(r, L.d + 3 * s), CMPC_S(r, L.d + 3 * s + 1), CMPC_S(r, L.d + 3 * s + 2)};
+    for (int s = 0; s < NS; ++s) {
+      const double ds[3] = {CMPC_S(r, L.d + 3 * s), CMPC_S(r, L.d + 3 * s + 1), CMPC_S(r, L.d + 3 * s + 2)};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int a1 = nxt3(a), a2 = prv3(a);
-      sF[a] = sF[a] + u[3 * s + a];
-      sT[a] = sT[a] + fma(ds[a1], u[3 * s + a2], -(ds[a2] * u[3 * s + a1]));
+      for (int a = 0; a < 3; ++a) {
+        const int a1 = nxt3(a), a2 = prv3(a);
+        sF[a] = sF[a] + u[3 * s + a];
+        sT[a] = sT[a] + fma(ds[a1], u[3 * s + a2], -(ds[a2] * u[3 * s + a1]));
+      }
     }
-  }
-  double xn[9];
-  {
-    const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
+    double xn[9];
+    {
+      const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int a1 = nxt3(a), a2 = prv3(a);
-      xn[a] = fma(P.dt_m, x[3 + a], x[a]);
-      xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
-      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_S(r, L.ck + a));
+      for (int a = 0; a < 3; ++a) {
+        const int a1 = nxt3(a), a2 = prv3(a);
+        xn[a] = fma(P.dt_m, x[3 + a], x[a]);
+        xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
+        xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_S(r, L.ck + a));
+      }
     }
-  }
-  if (!COPY) {
-    const int mt = CMPC_SI(r, L.meta, 0);
-    const int pm = PMMK ? CMPC_SI(r, L.meta, 1) : 0;
-    int newpm = 0;
+    if (!COPY) {
+      const int mt = CMPC_SI(r, L.meta, 0);
+      const int pm = PMMK ? CMPC_SI(r, L.meta, 1) : 0;
+      int newpm = 0;
 #pragma unroll
-    for (int t = 0; t < FT; ++t) {
-      const int bit = q + NL * t;   // friction row 4 s + row
-      if (bit < 4 * NS) {
-        const int s = bit >> 2, row = bit & 3;
-        FRow fr;
-        CMPC_FROW(fr, r, s, row);
+      for (int t = 0; t < FT; ++t) {
+        const int bit = fb[t], s = fs[t];
+        double gx = fgx[t], gy = fgy[t], gz = -P.kf, e2 = fe2[t], ub = 0.0;
+        if (!FAST) {
+          gx = CMPC_SO(r, L.g, s * GS + frow[t] * 3); gy = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 1);
+          gz = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 2);
+          e2 = CMPC_SO(r, L.g, s * GS + 12 + frow[t]); ub = CMPC_SO(r, L.g, s * GS + 16 + frow[t]);
+        }
         const double u0 = sp_ld(xs, X_UX + 3 * s), u1 = sp_ld(xs, X_UX + 3 * s + 1), u2 = sp_ld(xs, X_UX + 3 * s + 2);
-        double cf = fma(fr.gz, u2, fma(fr.gy, u1, fr.gx * u0));
-        if (!FAST) cf -= fr.ub;
+        double cf = fma(gz, u2, fma(gy, u1, gx * u0));
+        if (!FAST) cf -= ub;
         if (ADMM) {
           const double v = CMPC_SO(r, L.vf, bit);
           const double w0 = fmin(v, 0.0), y0 = fmax(v, 0.0);
           const double vn = fma(al, cf, fma(1.0 - al, w0, y0));
-          if (on) CMPC_R(w, L.vf + bit) = vn;
-          if (CHK) {
+          if (fok[t] && on) CMPC_R(w, L.vf + bit) = vn;
+          if (CHK && fok[t]) {
             const double wn = fmin(vn, 0.0);
             R.pri = fmax(R.pri, fabs(cf - wn));
-            R.npri = fmax(R.npri, FAST ? fmax(fabs(cf), fabs(wn)) : fmax(fabs(cf + fr.ub), fabs(wn + fr.ub)));
-            sp_st(xs, X_DX + bit, S.rho * fr.e2 * (fmax(vn, 0.0) - y0 - cf + w0));
+            R.npri = fmax(R.npri, FAST ? fmax(fabs(cf), fabs(wn)) : fmax(fabs(cf + ub), fabs(wn + ub)));
+            sp_st(xs, X_DX + bit, S.rho * e2 * (fmax(vn, 0.0) - y0 - cf + w0));
           }
-        } else {
+        } else if (fok[t]) {
           const bool act = (pm >> bit) & 1;
           const double yn = fma(inv, cf, act ? CMPC_SO(r, L.yf, bit) : 0.0);
           R.pri = fmax(R.pri, act ? fabs(cf) : fmax(cf, 0.0));
-          R.npri = fmax(R.npri, FAST ? fabs(cf) : fabs(cf + fr.ub));
+          R.npri = fmax(R.npri, FAST ? fabs(cf) : fabs(cf + ub));
           if (upd) {
             const bool keep = act && !(yn < 0.0);
             const bool join = !act && (cf > tolc);
@@ -1065,38 +1222,41 @@ CMPC_HD void fwd_knot(const Params& P, const Sv& S, Res& R, StagedPtr r, double*
           }
         }
       }
-    }
-    if (PMMK) {   // (warp-collective: every lane takes part, also those whose instance does not update)
-      newpm = team_or(I, xs, newpm);
-      if (upd && on) imw[TL] = (pm & ~0xffff) | newpm;
-    }
-    if (CHK) {   // u rows of the stationarity residual: G' delta; norms of P u and A'y
-      team_sync(I);
+      if (PMMK) {   // (warp-collective: every lane takes part, also those whose instance does not update)
+        newpm = team_or(I, xs, newpm);
+        if (upd && on) imw[TL] = (pm & ~0xffff) | newpm;
+      }
+      if (CHK) {   // u rows of the stationarity residual: G' delta; norms of P u and A'y
+        team_sync(I);
 #pragma unroll
-      for (int t = 0; t < CT; ++t) {
-        const int j = q + NL * t;
-        if (j < NA) {
-          const int s = j / 3, a = j - 3 * s;
-          double gc[4];
-          CMPC_GCOL(gc, r, s, a);
-          const double rdu = fma(gc[3], sp_ld(xs, X_DX + 4 * s + 3), fma(gc[2], sp_ld(xs, X_DX + 4 * s + 2),
-                                 fma(gc[1], sp_ld(xs, X_DX + 4 * s + 1), gc[0] * sp_ld(xs, X_DX + 4 * s))));
-          const int cid = (s < (mt & 7)) ? ((mt >> (4 + 2 * s)) & 3) : 0;
-          double wsel = pick3(P.Wu[0], P.Wu[1], P.Wu[2], a);
-          if (!FAST) {
+        for (int t = 0; t < CT; ++t) {
+          if (cok[t]) {
+            const int s = cs[t], a = ca[t];
+            double gc[4];
 #pragma unroll
-            for (int c = 1; c < MAXC; ++c) wsel = (cid == c) ? pick3(P.Wu[3 * c], P.Wu[3 * c + 1], P.Wu[3 * c + 2], a) : wsel;
+            for (int row = 0; row < 4; ++row) gc[row] = FAST ? cg[t][row] : CMPC_SO(r, L.g, s * GS + row * 3 + a);
+            const double rdu = fma(gc[3], sp_ld(xs, X_DX + 4 * s + 3), fma(gc[2], sp_ld(xs, X_DX + 4 * s + 2),
+                                   fma(gc[1], sp_ld(xs, X_DX + 4 * s + 1), gc[0] * sp_ld(xs, X_DX + 4 * s))));
+            const int cid = (s < (mt & 7)) ? ((mt >> (4 + 2 * s)) & 3) : 0;
+            double wsel = pick3(P.Wu[0], P.Wu[1], P.Wu[2], a);
+            if (!FAST) {
+#pragma unroll
+              for (int c = 1; c < MAXC; ++c) wsel = (cid == c) ? pick3(P.Wu[3 * c], P.Wu[3 * c + 1], P.Wu[3 * c + 2], a) : wsel;
+            }
+            const double Pu = wsel * uo[t];
+            R.dua = fmax(R.dua, fabs(rdu));
+            R.ndua = fmax(R.ndua, fmax(fabs(Pu), fabs(rdu - Pu)));
           }
-          const double Pu = wsel * uo[t];
-          R.dua = fmax(R.dua, fabs(rdu));
-          R.ndua = fmax(R.ndua, fmax(fabs(Pu), fabs(rdu - Pu)));
         }
       }
     }
-  }
 #pragma unroll
-  for (int i = 0; i < 9; ++i) x[i] = xn[i];
-  team_sync(I);   // the exchange words are rewritten by the next knot
+    for (int i = 0; i < 9; ++i) x[i] = xn[i];
+    team_sync(I);   // the exchange words are rewritten by the next knot
+    ks.release();
+    ++k;
+  } while (k < N && T.ns(k) == NS);
+  k_io = k;
 }
 
 // commit: the instance wants the residuals of this sweep (an instance that did not ask for a check may
@@ -1118,26 +1278,15 @@ CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
   double x[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) x[i] = I.xi[i];
-  // runs of equal slot count: one specialisation of the knot step per inner loop, x in registers
-#define CMPC_FWD_RUN(NS_)                                                             \
-  do {                                                                                \
-    const StagedPtr r = ks.acquire();                                                 \
-    double* w = rec_of(T, I, k);                                                      \
-    if (on) fwd_state<NS_, KIND, FAST, SK>(P, S, R, r, w, I, k, x);                   \
-    fwd_knot<NS_, KIND, FAST, SK>(P, S, R, r, w, meta_of(T, I, k, lay_of(NS_, !FAST).meta), I, xs, x, on, upd, nchg); \
-    ks.release();                                                                     \
-    ++k;                                                                              \
-  } while (k < N && T.ns(k) == NS_)
-  for (int k = 0; k < N;) {
+  for (int k = 0; k < N;) {   // runs of equal slot count: one specialisation of the knot step per run, x in registers
     switch (T.ns(k)) {
-      case 0: CMPC_FWD_RUN(0); break;
-      case 1: CMPC_FWD_RUN(1); break;
-      case 2: CMPC_FWD_RUN(2); break;
-      case 3: CMPC_FWD_RUN(3); break;
-      default: CMPC_FWD_RUN(4); break;
+      case 0: fwd_run<0, KIND, FAST, SK>(P, S, R, T, I, ks, xs, x, k, on, upd, nchg); break;
+      case 1: fwd_run<1, KIND, FAST, SK>(P, S, R, T, I, ks, xs, x, k, on, upd, nchg); break;
+      case 2: fwd_run<2, KIND, FAST, SK>(P, S, R, T, I, ks, xs, x, k, on, upd, nchg); break;
+      case 3: fwd_run<3, KIND, FAST, SK>(P, S, R, T, I, ks, xs, x, k, on, upd, nchg); break;
+      default: fwd_run<4, KIND, FAST, SK>(P, S, R, T, I, ks, xs, x, k, on, upd, nchg); break;
     }
   }
-#undef CMPC_FWD_RUN
   {   // terminal knot
     const StagedPtr r = ks.acquire();
     if (on) fwd_state<0, KIND, FAST, SK>(P, S, R, r, rec_of(T, I, N), I, N, x);
@@ -1250,23 +1399,21 @@ CMPC_FN void build_active_set_op(const Params& P, const TileCtx& T, const Inst& 
 
 // ---------------------------------------------------------------- trust test and accuracy ratio
 // sigma_max(X - Xbar) via the 9x9 Gram matrix + cyclic Jacobi (scp_solver.py:151: np.linalg.norm(.,2));
-// rho = sum ||(f(x,u) - lin)[6:9]||^2 / sum ||lin||^2 (scp_solver.py:71-87).
-// (replicated in the lanes of a team: the sums over the horizon are sequential by definition)
-CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, double* snorm, double* num_out, double* den_out) {
+// rho = sum_k ||(f(x,u) - lin)[6:9]||^2 / sum_k ||lin||^2 (scp_solver.py:71-87).
+// Team work split: the per-knot terms of the two sums by the lanes q, q + NL, ... (parked in the knot
+// records, then added up in knot order by every lane); the Gram matrix by rows (a lane walks the whole
+// horizon for its rows); the Jacobi rotations on the matrix in the scratch, rows / columns by their owners.
+CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, bool on, double* snorm, double* num_out, double* den_out) {
   const int N = P.N;
-  double A[81];
-  for (int i = 0; i < 81; ++i) A[i] = 0.0;
-  double num = 0.0, den = 0.0;
-  for (int k = 0; k <= N; ++k) {
-    const double* r = rec_of(T, I, k);
+  const int q = sub_of(I);
+  const ScratchPtr xs = scratch_of(T, I);
+  constexpr int GT_ = (9 + NL - 1) / NL;
+  for (int k = q; on && k < N; k += NL) {   // accuracy-ratio terms of the knots q, q + NL, ...
+    double* r = rec_of(T, I, k);
     const Lay L = lay_of(T.ns(k), T.gen != 0);
-    double x[9], dx[9];
+    double x[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { x[i] = CMPC_R(r, L.x + i); dx[i] = x[i] - I.Xr[k * 9 + i]; }
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-      for (int j = i; j < 9; ++j) A[i * 9 + j] = fma(dx[i], dx[j], A[i * 9 + j]);
-    if (k == N) break;
+    for (int i = 0; i < 9; ++i) x[i] = CMPC_R(r, L.x + i);
     const int mt = meta_of(T, I, k, L.meta)[0];
     const int ns = mt & 7;
     double u[MAXU];
@@ -1298,47 +1445,100 @@ CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, doubl
       lin[6 + a] = x[6 + a] + P.dt * Sxc[a] + P.dt * Tq[a] + CMPC_R(r, L.ck + a);
     }
     step_knot(P, x, u, I.cpos + (long)k * P.nc * 3, I.cact + (long)k * P.nc, nl);
+    double nk = 0.0, dk = 0.0;
 #pragma unroll
-    for (int i = 6; i < 9; ++i) num += (nl[i] - lin[i]) * (nl[i] - lin[i]);
+    for (int i = 6; i < 9; ++i) nk += (nl[i] - lin[i]) * (nl[i] - lin[i]);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) den += lin[i] * lin[i];
+    for (int i = 0; i < 9; ++i) dk += lin[i] * lin[i];
+    CMPC_R(r, L.yk) = nk;        // (the multiplier fields are free here: every polish starts by rebuilding them)
+    CMPC_R(r, L.yk + 1) = dk;
+  }
+  // Gram matrix of X - Xbar: the lane's rows i = q + NL t, the whole horizon
+  double G[GT_][9];
+#pragma unroll
+  for (int t = 0; t < GT_; ++t)
+#pragma unroll
+    for (int j = 0; j < 9; ++j) G[t][j] = 0.0;
+  for (int k = 0; on && k <= N; ++k) {
+    const double* r = rec_of(T, I, k);
+    const Lay L = lay_of(T.ns(k), T.gen != 0);
+    double dx[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dx[j] = CMPC_R(r, L.x + j) - I.Xr[k * 9 + j];
+#pragma unroll
+    for (int t = 0; t < GT_; ++t) {
+      const int i = q + NL * t < 9 ? q + NL * t : 8;
+      const double di = CMPC_R(r, L.x + i) - I.Xr[k * 9 + i];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) G[t][j] = fma(di, dx[j], G[t][j]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < GT_; ++t) {
+    const int i = q + NL * t;
+    if (i < 9) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) sp_st(xs, X_PS + i * 9 + j, G[t][j]);
+    }
+  }
+  team_sync(I);
+  double num = 0.0, den = 0.0;
+  for (int k = 0; on && k < N; ++k) {   // the two sums in knot order
+    const double* r = rec_of(T, I, k);
+    const Lay L = lay_of(T.ns(k), T.gen != 0);
+    num += CMPC_R(r, L.yk);
+    den += CMPC_R(r, L.yk + 1);
   }
   *num_out = num;
   *den_out = den;
-#pragma unroll
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < i; ++j) A[i * 9 + j] = A[j * 9 + i];
-  // largest eigenvalue of the Gram matrix: cyclic Jacobi
+  // largest eigenvalue of the Gram matrix: cyclic Jacobi on the scratch copy.  The team_sync points must be
+  // the same for every instance of the tile: an instance that has converged (or meets a zero off-diagonal
+  // entry) goes through the remaining rotations with the identity, which leaves its matrix bit for bit.
+  bool conv = !on;   // an instance that does not take part only keeps the synchronisation points
   for (int sweep = 0; sweep < 12; ++sweep) {
-    double off = 0.0;
-    for (int i = 0; i < 9; ++i)
-      for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
-    double dg = 0.0;
-    for (int i = 0; i < 9; ++i) dg += A[i * 9 + i] * A[i * 9 + i];
-    if (off <= 1e-30 * dg || off == 0.0) break;
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      for (int j = i + 1; j < 9; ++j) { const double v = sp_ld(xs, X_PS + i * 9 + j); off += v * v; }
+      const double d = sp_ld(xs, X_PS + i * 10);
+      dg += d * d;
+    }
+    if (off <= 1e-30 * dg || off == 0.0 || !(off == off)) conv = true;
+    if (tile_all(conv)) break;
     for (int p = 0; p < 8; ++p) {
-      for (int q = p + 1; q < 9; ++q) {
-        double apq = A[p * 9 + q];
-        if (apq == 0.0) continue;
-        double th = (A[q * 9 + q] - A[p * 9 + p]) / (2.0 * apq);
-        double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-        double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
-        for (int rr = 0; rr < 9; ++rr) {
-          double arp = A[rr * 9 + p], arq = A[rr * 9 + q];
-          A[rr * 9 + p] = cs * arp - sn * arq;
-          A[rr * 9 + q] = sn * arp + cs * arq;
+      for (int qq = p + 1; qq < 9; ++qq) {
+        const double apq = sp_ld(xs, X_PS + p * 9 + qq);
+        const bool skip = conv || apq == 0.0 || !(apq == apq);
+        const double th = (sp_ld(xs, X_PS + qq * 10) - sp_ld(xs, X_PS + p * 10)) / (2.0 * (skip ? 1.0 : apq));
+        const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+        const double cs = skip ? 1.0 : 1.0 / sqrt(t * t + 1.0), sn = skip ? 0.0 : t * cs;
+        team_sync(I);   // everybody has read the pivot entries before rows p, q change
+#pragma unroll
+        for (int tt = 0; tt < GT_; ++tt) {   // columns p, q of the lane's rows
+          const int rr = q + NL * tt;
+          if (rr < 9 && !skip) {
+            const double arp = sp_ld(xs, X_PS + rr * 9 + p), arq = sp_ld(xs, X_PS + rr * 9 + qq);
+            sp_st(xs, X_PS + rr * 9 + p, cs * arp - sn * arq);
+            sp_st(xs, X_PS + rr * 9 + qq, sn * arp + cs * arq);
+          }
         }
-        for (int rr = 0; rr < 9; ++rr) {
-          double apr = A[p * 9 + rr], aqr = A[q * 9 + rr];
-          A[p * 9 + rr] = cs * apr - sn * aqr;
-          A[q * 9 + rr] = sn * apr + cs * aqr;
+        team_sync(I);
+#pragma unroll
+        for (int tt = 0; tt < GT_; ++tt) {   // rows p, q of the lane's columns
+          const int rr = q + NL * tt;
+          if (rr < 9 && !skip) {
+            const double apr = sp_ld(xs, X_PS + p * 9 + rr), aqr = sp_ld(xs, X_PS + qq * 9 + rr);
+            sp_st(xs, X_PS + p * 9 + rr, cs * apr - sn * aqr);
+            sp_st(xs, X_PS + qq * 9 + rr, sn * apr + cs * aqr);
+          }
         }
+        team_sync(I);
       }
     }
   }
   double mx = 0.0;
-  for (int i = 0; i < 9; ++i) mx = fmax(mx, A[i * 9 + i]);
+  for (int i = 0; i < 9; ++i) mx = fmax(mx, sp_ld(xs, X_PS + i * 10));
   *snorm = sqrt(mx);
+  team_sync(I);
 }
 
 // ---------------------------------------------------------------- per-instance setup
@@ -1734,10 +1934,16 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
 // anycheck: some participating instance wants residuals from this ADMM sweep.
 template <bool FAST>
 CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const Batch& bt, Sv& S, Drv& D, bool on, bool anycheck) {
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+  const long long t0_ = clock64();
+#endif
   switch (op) {
     case OP_FACTOR_ADMM: factor_op<MODE_ADMM, FAST>(P, T, I, S, on); break;
     case OP_SWEEP_ADMM:
       backward_op<MODE_ADMM, FAST>(P, T, I, S, on);
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+      T.prof[10] += clock64() - t0_;
+#endif
       if (anycheck) forward_op<FW_ADMM_CHECK, FAST>(P, T, I, S, on, on && D.check, false, nullptr);
       else forward_op<FW_ADMM, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
@@ -1745,6 +1951,9 @@ CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const B
     case OP_FACTOR_PMM: factor_op<MODE_PMM, FAST>(P, T, I, S, on); break;
     case OP_SWEEP_PMM:
       backward_op<MODE_PMM, FAST>(P, T, I, S, on);
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+      T.prof[11] += clock64() - t0_;
+#endif
       forward_op<FW_PMM, FAST>(P, T, I, S, on, true, on && D.upd, &D.chg);
       break;
     case OP_RESCALE: if (on) rescale_op(P, T, I, S, D.rho_new, D.rhok_new); break;
@@ -1752,11 +1961,19 @@ CMPC_FN void execute(int op, const Params& P, TileCtx& T, const Inst& I, const B
       backward_op<MODE_ADMM, FAST>(P, T, I, S, on);
       forward_op<FW_COPY, FAST>(P, T, I, S, on, false, false, nullptr);
       break;
-    case OP_EVAL: if (on) evaluate_op(P, T, I, &D.snorm, &D.num, &D.den); break;
+    case OP_EVAL: {
+      double sn_ = 0.0, nu_ = 0.0, de_ = 1.0;
+      evaluate_op(P, T, I, on, &sn_, &nu_, &de_);
+      if (on) { D.snorm = sn_; D.num = nu_; D.den = de_; }
+      break;
+    }
     case OP_WRITE: if (on) write_solution_knots(P, T, I, bt.X_out, bt.U_out); break;
     default: break;
   }
   team_sync(I);
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+  T.prof[op] += clock64() - t0_;
+#endif
 }
 
 CMPC_FN void write_stats(const Batch& bt, const Inst& I, const Sv& S, const Drv& D) {
