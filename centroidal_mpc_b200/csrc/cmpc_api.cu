@@ -37,14 +37,14 @@ int fail(int code, const std::string& msg) {
 // tile does those together.  Warps never synchronise with each other.
 // ------------------------------------------------------------------------------------------
 constexpr int THREADS = 32;
-constexpr int BAR_BYTES = 64;   // 4 mbarriers ("full" per ring slot) + padding
+constexpr int BAR_BYTES = 128;  // 4 mbarriers ("full" per ring slot), then the byte-range table of the open stream (5 x 16 bytes)
 inline long scp_smem_bytes(int N, bool gen) { return (long)tile_smem_fields(gen) * TL * 8 + BAR_BYTES + ((N + 1 + 15) & ~15); }
 
 #if defined(CMPC_PROFILE)
 // profiling build: cycles per operation kind summed over all warps (lane 0 of each warp)
 // [0..9] per Op code (sweeps: whole op), [10] backward part of ADMM sweeps, [11] of PMM sweeps,
 // [12] setup, [13] whole tile, [14] cycles waiting for bulk copies, [15] number of waits
-__device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_prof[32];
 #endif
 
 template <bool FAST>
@@ -53,8 +53,8 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
   const int t = lane & (TL - 1), q = lane / TL;
   bind_tile(T, prm, bt, tile);
 #if defined(CMPC_PROFILE)
-  long long prof[16];
-  for (int i = 0; i < 16; ++i) prof[i] = 0;
+  long long prof[32];
+  for (int i = 0; i < 32; ++i) prof[i] = 0;
   T.prof = prof;
   const long long tile_t0 = clock64();
 #endif
@@ -103,7 +103,7 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
 #if defined(CMPC_PROFILE)
   prof[13] += clock64() - tile_t0;
   if (lane == 0)
-    for (int i = 0; i < 16; ++i) atomicAdd(&g_prof[i], (unsigned long long)prof[i]);
+    for (int i = 0; i < 32; ++i) atomicAdd(&g_prof[i], (unsigned long long)prof[i]);
 #endif
 }
 
@@ -119,7 +119,7 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
   T.bars_sa = T.smem_sa + (unsigned)SCR_BYTES;
   T.phases = 0;
   unsigned char* nst_s = smem_raw + SCR_BYTES + BAR_BYTES;
-  T.nst_s = nst_s;
+  T.nst_sa = smem_addr(nst_s);
   if (lane == 0) {
     for (int d = 0; d < 4; ++d)   // "full" barriers of the ring slots (bulk-copy completion)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(T.bars_sa + 8u * d) : "memory");
@@ -567,10 +567,10 @@ int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, doubl
 // profiling build only (-DCMPC_PROFILE): reads and clears the cycle counters; returns -1 in a normal build
 int cmpc_debug_profile(double* out16) {
 #if defined(CMPC_PROFILE)
-  unsigned long long h[16], z[16] = {0};
+  unsigned long long h[32], z[32] = {0};
   CUDA_TRY(cudaMemcpyFromSymbol(h, g_prof, sizeof(h)));
   CUDA_TRY(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
-  for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
+  for (int i = 0; i < 32; ++i) out16[i] = (double)h[i];
   return 0;
 #else
   (void)out16;

@@ -18,10 +18,16 @@
 #if defined(__CUDACC__)   // the solver is device code in the CUDA build, host code in the test build (g++)
 #define CMPC_HD __device__ __forceinline__
 #define CMPC_FN __device__ __forceinline__
+#if defined(CMPC_INLINE_OPS)
+#define CMPC_OP __device__ __forceinline__
+#else
+#define CMPC_OP __device__ __noinline__   // whole-horizon operations: real calls, so that each gets its own register allocation
+#endif
 #define CMPC_CX __host__ __device__ constexpr inline
 #else
 #define CMPC_HD inline
 #define CMPC_FN
+#define CMPC_OP
 #define CMPC_CX constexpr inline
 #endif
 

@@ -68,8 +68,10 @@ CMPC_CX int tile_smem_fields(bool gen) { return X_COMMON + ring_fields(gen); }
 static_assert(X_FAC_END - X_COMMON + 2 * slot_fields(SK_FAC_PMM, true) <= ring_fields(true), "factor scratch");
 static_assert(X_FAC_END - X_COMMON + 2 * slot_fields(SK_FAC_PMM, false) <= ring_fields(false), "factor scratch");
 
-#ifndef CMPC_PF
-#define CMPC_PF 4   // knots of L2 prefetch ahead of the ring
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+#define CMPC_PROF_PTR(T) (T).prof
+#else
+#define CMPC_PROF_PTR(T) nullptr
 #endif
 
 // ---------------------------------------------------------------- memory spaces
@@ -178,13 +180,17 @@ struct TileCtx {
   int* nst;        // [N+1] slots per knot (tile maximum; 0 at the terminal knot), global memory
   int gen;         // general friction table present
 #if defined(__CUDACC__)
-  unsigned smem_sa, bars_sa, phases;   // the warp's shared memory (scratch, ring), its mbarriers; warp-uniform
+  unsigned smem_sa, bars_sa, phases;   // the warp's shared memory (scratch, ring), the stream's range table; warp-uniform
   int tile;
 #if defined(CMPC_PROFILE)
   long long* prof;                     // cycle counters of a profiling build (scripts/prof_cycles.py)
 #endif
-  const unsigned char* nst_s;          // shared copy of nst
-  CMPC_HD int ns(int k) const { return nst_s[k]; }
+  unsigned nst_sa;                     // shared copy of nst (bytes), shared-space address
+  CMPC_HD int ns(int k) const {
+    int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(nst_sa + (unsigned)k));
+    return v;
+  }
 #else
   double* scratch;                     // [X_FAC_END][TL]
   CMPC_HD int ns(int k) const { return nst[k]; }
@@ -205,13 +211,12 @@ CMPC_HD ScratchPtr scratch_of(const TileCtx& T, const Inst& I) {
 
 // ---------------------------------------------------------------- knot stream
 // Walks the knots of a tile in one direction and hands out a pointer through which the staged fields of
-// the current knot can be read.  Device: a ring of DEPTH shared-memory slots filled by cp.async.bulk
-// (lane 0 of the warp issues the copy of knot k + DEPTH when it releases knot k; completion on an
-// mbarrier) plus an L2 prefetch CMPC_PF knots further ahead, so that the HBM latency hides behind
-// the arithmetic of the knots in between and every operand read is a shared-memory read.
-// Host build: the pointer is the global record itself.
+// the current knot can be read.  Device: a ring of DEPTH shared-memory slots filled asynchronously, so that
+// the HBM latency hides behind the arithmetic of the knots in between and every operand read is a
+// shared-memory read.  Host build: the pointer is the global record itself.
 #if defined(__CUDACC__)
 CMPC_HD unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 // bounded wait on an mbarrier phase: returns false when the bulk copy never lands
 CMPC_HD bool mbar_wait(unsigned bar, unsigned parity) {
   unsigned done = 0;
@@ -227,40 +232,43 @@ CMPC_HD bool mbar_wait(unsigned bar, unsigned parity) {
   return true;
 }
 
+// Device: a ring of DEPTH shared-memory slots filled by cp.async.bulk: lane 0 of the warp issues the copy
+// of knot k + DEPTH (one bulk copy per field range, byte ranges from a small table per slot count) when the
+// warp releases knot k; completion on the slot's mbarrier.
+// Measured alternatives (B200, 4096 x N=100): an L2 prefetch (cp.async.bulk.prefetch.L2) four
+// knots ahead of the ring: 14.0 instead of 11.7 ms per batch; a non-blocking mbarrier.test_wait of the next
+// slot early in the knot: the instruction holds the warp for its whole latency; all 32 lanes copying with
+// cp.async (16 bytes per lane) instead of the bulk copy: 13.8 instead of 12.0 ms.
 template <int SK, bool GEN>
 struct KnotStream {
   static constexpr int DEPTH = ring_depth(SK, GEN);
   static constexpr int SLOTF = slot_fields(SK, GEN);
-  unsigned ring_sa, bars_sa, phases, pre;
+  unsigned ring_sa, bars_sa, phases, nst_sa, tab_sa;
   int lane, s_wait, k_issue, n_left, dir, s_issue, lost;
   const double* ws;
   long rstride;
-  const unsigned char* nst_s;
 #if defined(CMPC_PROFILE)
   long long* prof;
 #endif
 
+  CMPC_HD int ns_at(int k) const {
+    int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(nst_sa + (unsigned)k));
+    return v;
+  }
   CMPC_HD void issue() {   // lane 0: knot k_issue into slot s_issue
     const int k = k_issue;
-    const Ranges R = ranges_of(SK, nst_s[k], GEN);
-    const unsigned b1 = (unsigned)(R.e1 - R.s1) * (TL * 8u), b2 = (unsigned)(R.e2 - R.s2) * (TL * 8u);
+    unsigned o1, b1, o2, b2;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o1), "=r"(b1), "=r"(o2), "=r"(b2) : "r"(tab_sa + 16u * (unsigned)ns_at(k)));
     const unsigned bar = bars_sa + 8u * s_issue;
     const unsigned dst = ring_sa + (unsigned)(s_issue * SLOTF) * (TL * 8u);
-    const double* src = ws + (long)k * rstride;
+    const char* src = reinterpret_cast<const char*>(ws + (long)k * rstride);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b1 + b2) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src + (long)R.s1 * TL), "r"(b1), "r"(bar) : "memory");
+                 ::"r"(dst), "l"(src + o1), "r"(b1), "r"(bar) : "memory");
     if (b2)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst + b1), "l"(src + (long)R.s2 * TL), "r"(b2), "r"(bar) : "memory");
-    if (CMPC_PF > 0 && n_left > CMPC_PF) {   // L2 prefetch of the knot CMPC_PF further along
-      const int kp = k + CMPC_PF * dir;
-      const Ranges Q = ranges_of(SK, nst_s[kp], GEN);
-      const double* sp = ws + (long)kp * rstride;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp + (long)Q.s1 * TL), "r"((unsigned)(Q.e1 - Q.s1) * (TL * 8u)) : "memory");
-      if (Q.e2 > Q.s2)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp + (long)Q.s2 * TL), "r"((unsigned)(Q.e2 - Q.s2) * (TL * 8u)) : "memory");
-    }
+                   ::"r"(dst + b1), "l"(src + o2), "r"(b2), "r"(bar) : "memory");
     k_issue += dir;
     --n_left;
     s_issue = (s_issue + 1 == DEPTH) ? 0 : s_issue + 1;
@@ -269,45 +277,31 @@ struct KnotStream {
   CMPC_HD void open(TileCtx& Tc, const Inst& I, int k_first, int count, int direction) {
     ring_sa = Tc.smem_sa + (unsigned)ring_base(SK) * (TL * 8u);
     bars_sa = Tc.bars_sa; phases = Tc.phases;
-    lane = I.lane; s_wait = 0; s_issue = 0; k_issue = k_first; n_left = count; dir = direction; lost = 0; pre = 0;
-    ws = Tc.ws; rstride = Tc.rstride; nst_s = Tc.nst_s;
+    lane = I.lane; s_wait = 0; s_issue = 0; k_issue = k_first; n_left = count; dir = direction; lost = 0;
+    ws = Tc.ws; rstride = Tc.rstride; nst_sa = Tc.nst_sa; tab_sa = Tc.bars_sa + 32u;
 #if defined(CMPC_PROFILE)
     prof = Tc.prof;
 #endif
     // earlier generic-proxy writes of this warp (records written by the previous operation) must be
     // visible to the async proxy before the bulk copies read them
     asm volatile("fence.proxy.async;" ::: "memory");
-    __syncwarp();
-    if ((threadIdx.x & 31u) == 0) {
-      if (CMPC_PF > 0) {   // warm the L2 for the first knots
-        for (int i = DEPTH; i < DEPTH + CMPC_PF && i < count; ++i) {
-          const int kp = k_first + i * direction;
-          const Ranges Q = ranges_of(SK, nst_s[kp], GEN);
-          const double* sp = ws + (long)kp * rstride;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp + (long)Q.s1 * TL), "r"((unsigned)(Q.e1 - Q.s1) * (TL * 8u)) : "memory");
-        }
-      }
-      for (int i = 0; i < DEPTH && n_left > 0; ++i) issue();
+    const unsigned wl = threadIdx.x & 31u;
+    if (wl <= MAXC) {   // byte ranges of this operation per slot count: {offset 1, bytes 1, offset 2, bytes 2}
+      const Ranges R = ranges_of(SK, (int)wl, GEN);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_sa + 16u * wl), "r"((unsigned)R.s1 * (TL * 8u)),
+                   "r"((unsigned)(R.e1 - R.s1) * (TL * 8u)), "r"((unsigned)R.s2 * (TL * 8u)), "r"((unsigned)(R.e2 - R.s2) * (TL * 8u)) : "memory");
     }
+    __syncwarp();
+    if (wl == 0)
+      for (int i = 0; i < DEPTH && n_left > 0; ++i) issue();
   }
-  // non-blocking look at the NEXT slot's barrier (call between acquire and release): its latency hides behind
-  // the arithmetic of the current knot, and the next acquire does not have to ask again when the copy is there
-  CMPC_HD void peek() {
-    const int s_next = (s_wait + 1 == DEPTH) ? 0 : s_wait + 1;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}" : "=r"(pre) : "r"(bars_sa + 8u * s_next), "r"((phases >> s_next) & 1u) : "memory");
-  }
+  CMPC_HD void peek() {}
   CMPC_HD StagedPtr acquire() {
     const unsigned bar = bars_sa + 8u * s_wait;
 #if defined(CMPC_PROFILE)
     const long long t0_ = clock64();
 #endif
-    if (!pre && !mbar_wait(bar, (phases >> s_wait) & 1u)) lost = 1;
-    pre = 0;
+    if (!mbar_wait(bar, (phases >> s_wait) & 1u)) lost = 1;
 #if defined(CMPC_PROFILE)
     prof[14] += clock64() - t0_;
     prof[15] += 1;
@@ -511,7 +505,7 @@ CMPC_HD double pick3(double a, double b, double c, int i) { return i == 0 ? a : 
 // row (they are the factor record [Hn; Kt]) and the state columns of the state rows; the state columns of
 // the control rows are the mirror image of the control columns of the state rows and are never formed.
 template <int NS, int MODE, bool FAST, int SK>
-CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const Inst& I, int k, ScratchPtr xs, bool on) {
+CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const Inst& I, int k, ScratchPtr xs, bool on, long long* prof_) {
   constexpr Lay L = lay_of(NS, !FAST);
   constexpr int NA = 3 * NS, n = NA + 9, NAP = L.nap;
   constexpr int RT = (n + NL - 1) / NL;   // tableau rows per lane
@@ -538,6 +532,12 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
 #pragma unroll
     for (int i = 0; i < 9; ++i) sp_st(xs, X_KX + 3 + i, kM[i]);
   }
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+#define CMPC_FK(i) do { const long long t_ = clock64(); prof_[22 + (i)] += t_ - ck_; ck_ = t_; } while (0)
+  long long ck_ = clock64();
+#else
+#define CMPC_FK(i)
+#endif
   // ---- phase 1: rows of Y = P [B A] and Pc = P c, by the owners of the state rows
 #pragma unroll
   for (int t = 0; t < ST; ++t) {
@@ -569,6 +569,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
     }
   }
   team_sync(I);
+  CMPC_FK(0);
   // ---- phase 2: the lane's tableau rows in registers: control columns by slot, state columns
   double Tc[RT][NS > 0 ? NS : 1][3], Ts[RT][9];
 #pragma unroll
@@ -647,6 +648,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
       }
     }
   }
+  CMPC_FK(1);
   // ---- phase 3: sweep the control pivots, slot by slot.  The pivot columns of the current slot are always
   // the first block of the row registers: after its three pivots the blocks are rotated by one (a loop
   // over the slots with compile-time register indices; after NS rotations the order is the original one).
@@ -707,6 +709,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
       Tc[t][NS > 0 ? NS - 1 : 0][0] = t0; Tc[t][NS > 0 ? NS - 1 : 0][1] = t1; Tc[t][NS > 0 ? NS - 1 : 0][2] = t2;
     }
   }
+  CMPC_FK(2);
   // ---- factor record [Hn; Kt] and P_k (lower triangle, mirrored: P stays exactly symmetric)
 #pragma unroll
   for (int t = 0; t < RT; ++t) {
@@ -729,10 +732,12 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
     }
   }
   team_sync(I);
+  CMPC_FK(3);
+#undef CMPC_FK
 }
 
 template <int MODE, bool FAST>
-CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on) {
+CMPC_OP void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on) {
   // local copies: the reference arguments live in the caller's frame, which every generic store
   // of the operation could alias (the compiler would reload them after each one)
   const Params P = P_in;
@@ -776,7 +781,7 @@ CMPC_FN void factor_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_i
   do {                                                                                \
     const StagedPtr r = ks.acquire();                                                 \
     ks.peek();                                                                        \
-    factor_knot<NS_, MODE, FAST, SK>(P, S, r, rec_of(T, I, k), I, k, xs, on);         \
+    factor_knot<NS_, MODE, FAST, SK>(P, S, r, rec_of(T, I, k), I, k, xs, on, CMPC_PROF_PTR(T)); \
     ks.release();                                                                     \
     --k;                                                                              \
   } while (k >= 0 && T.ns(k) == NS_)
@@ -868,90 +873,165 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     rwx[t] = pick9(P.Wx, i);
   }
   int k = k_io, buf = buf_io;
+#if defined(CMPC_PROFILE) && defined(__CUDACC__)
+#define CMPC_CK(i) do { const long long t_ = clock64(); T.prof[16 + (i)] += t_ - ck_; ck_ = t_; } while (0)
+  long long ck_ = clock64();
+#else
+#define CMPC_CK(i)
+#endif
+  // Every phase is written loads -> arithmetic -> stores: the shared-memory accesses keep their program
+  // order (a store may alias a later load as far as the compiler can tell), so a store in the middle of a
+  // phase would serialise the rows of the lane.
   do {
     const StagedPtr r = ks.acquire();
     ks.peek();
+    CMPC_CK(0);
     double* w = rec_of(T, I, k);
+    const int pin = X_PX + buf * 9, pout = X_PX + (buf ^ 1) * 9;
+    // ---- phase 1 loads
     const int nsl = CMPC_SI(r, L.meta, 0) & 7;
     const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
-    const int pin = X_PX + buf * 9, pout = X_PX + (buf ^ 1) * 9;
-    if (k >= 1) {
-      double kl[3];
-      kappa_linear_term<NS, MODE, FAST, SK>(P, S, r, I, pm, kl);
+    const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
+    double kin[4] = {0.0, 0.0, 0.0, 0.0};   // ADMM: vk[3]; multiplier mode: yk[4]
+    if (MODE == MODE_ADMM) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) sp_st(xs, X_KX + a, kl[a]);
+      for (int a = 0; a < 3; ++a) kin[a] = CMPC_S(r, L.vk + a);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) kin[a] = CMPC_S(r, L.yk + a);
     }
-    // ---- phase 1: hu of the lane's control rows
+    double fv[CT > 0 ? CT : 1][4], fg[CT > 0 ? CT : 1][4], fe[CT > 0 ? CT : 1][4], fu[CT > 0 ? CT : 1][4];
+    double p0[CT > 0 ? CT : 1], pA[CT > 0 ? CT : 1], pB[CT > 0 ? CT : 1], c0[CT > 0 ? CT : 1], cA[CT > 0 ? CT : 1], cB[CT > 0 ? CT : 1];
+    double dA[CT > 0 ? CT : 1], dB[CT > 0 ? CT : 1];
+#pragma unroll
+    for (int t = 0; t < CT; ++t) {
+      const int s = cs[t];
+#pragma unroll
+      for (int row = 0; row < 4; ++row) {
+        fv[t][row] = (MODE == MODE_ADMM) ? CMPC_SO(r, L.vf, 4 * s + row) : CMPC_SO(r, L.yf, 4 * s + row);
+        fg[t][row] = cg[t][row];
+        fe[t][row] = row < 2 ? P.e2[0] : P.e2[2];
+        fu[t][row] = 0.0;
+        if (!FAST) {
+          fg[t][row] = CMPC_SO(r, L.g, s * GS + row * 3 + ca[t]);
+          fe[t][row] = CMPC_SO(r, L.g, s * GS + 12 + row);
+          fu[t][row] = CMPC_SO(r, L.g, s * GS + 16 + row);
+        }
+      }
+      p0[t] = sp_ld(xs, pin + 3 + ca[t]);  c0[t] = CMPC_SO(r, L.pc, 3 + ca[t]);
+      pA[t] = sp_ld(xs, pin + 6 + ca1[t]); cA[t] = CMPC_SO(r, L.pc, 6 + ca1[t]);
+      pB[t] = sp_ld(xs, pin + 6 + ca2[t]); cB[t] = CMPC_SO(r, L.pc, 6 + ca2[t]);
+      dA[t] = CMPC_SO(r, L.d, 3 * s + ca2[t]);
+      dB[t] = CMPC_SO(r, L.d, 3 * s + ca1[t]);
+    }
+    // ---- phase 1 arithmetic: linear term of the kappa rows (replicated), hu of the lane's control rows
+    double kl[3] = {0.0, 0.0, 0.0};
+    if (k >= 1) {
+      if (MODE == MODE_ADMM) {
+        double wv[3];
+        prox_kappa(S, kin, kb, wv);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) kl[a] = -S.rhok * (wv[a] + wv[a] - kin[a]);
+      } else if (S.kap) {
+        double kM[9];
+        pmm_kappa_terms(P, S, pm, kb, kin, kM, kl);
+      }
+    }
+    double huo[CT > 0 ? CT : 1];
 #pragma unroll
     for (int t = 0; t < CT; ++t) {
       const int s = cs[t];
       const double dtr = s < nsl ? P.dt : 0.0;
-      double tt[4], gc[4];
+      double tt[4];
 #pragma unroll
       for (int row = 0; row < 4; ++row) {
-        double e2 = row < 2 ? P.e2[0] : P.e2[2], ub = 0.0;
-        gc[row] = cg[t][row];
-        if (!FAST) {
-          gc[row] = CMPC_SO(r, L.g, s * GS + row * 3 + ca[t]);
-          e2 = CMPC_SO(r, L.g, s * GS + 12 + row);
-          ub = CMPC_SO(r, L.g, s * GS + 16 + row);
-        }
         if (MODE == MODE_ADMM) {
-          tt[row] = S.rho * e2 * fabs(CMPC_SO(r, L.vf, 4 * s + row));   // -(rho e2 w - y) = rho e2 |v|
-          if (!FAST) tt[row] = fma(-S.rho * e2, ub, tt[row]);            // unshifted w = min(v, 0) + ub
+          tt[row] = S.rho * fe[t][row] * fabs(fv[t][row]);                      // -(rho e2 w - y) = rho e2 |v|
+          if (!FAST) tt[row] = fma(-S.rho * fe[t][row], fu[t][row], tt[row]);   // unshifted w = min(v, 0) + ub
         } else {
-          const double y = CMPC_SO(r, L.yf, 4 * s + row);
-          tt[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? y : fma(-P.inv_delta, ub, y)) : 0.0;
+          tt[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? fv[t][row] : fma(-P.inv_delta, fu[t][row], fv[t][row])) : 0.0;
         }
       }
-      const double o = fma(gc[3], tt[3], fma(gc[2], tt[2], fma(gc[1], tt[1], gc[0] * tt[0])));
-      const double g0 = sp_ld(xs, pin + 3 + ca[t]) + CMPC_SO(r, L.pc, 3 + ca[t]);
-      const double gA = sp_ld(xs, pin + 6 + ca1[t]) + CMPC_SO(r, L.pc, 6 + ca1[t]);
-      const double gB = sp_ld(xs, pin + 6 + ca2[t]) + CMPC_SO(r, L.pc, 6 + ca2[t]);
-      const double hu = dtr * fma(gA, CMPC_SO(r, L.d, 3 * s + ca2[t]), fma(-gB, CMPC_SO(r, L.d, 3 * s + ca1[t]), g0)) + o;
-      if (cok[t]) sp_st(xs, X_UX + cj[t], hu);
+      const double o = fma(fg[t][3], tt[3], fma(fg[t][2], tt[2], fma(fg[t][1], tt[1], fg[t][0] * tt[0])));
+      const double g0 = p0[t] + c0[t], gA = pA[t] + cA[t], gB = pB[t] + cB[t];
+      huo[t] = dtr * fma(gA, dA[t], fma(-gB, dB[t], g0)) + o;
     }
+    CMPC_CK(1);
+    // ---- phase 1 stores
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sp_st(xs, X_KX + a, kl[a]);
+#pragma unroll
+    for (int t = 0; t < CT; ++t)
+      if (cok[t]) sp_st(xs, X_UX + cj[t], huo[t]);
     team_sync(I);
-    // ---- phase 2: rows of [Hn; Kt] hu (two partial sums per row: shorter dependent chains)
-    double hu[NA > 0 ? NA : 1];
+    CMPC_CK(2);
+    // ---- phase 2 loads: hu, the lane's rows of [Hn; Kt], the operands of the state rows
+    double hu[NA > 0 ? NA : 1], Mr[RT][NA > 0 ? NA : 1];
 #pragma unroll
     for (int l = 0; l < NA; ++l) hu[l] = sp_ld(xs, X_UX + l);
 #pragma unroll
+    for (int t = 0; t < RT; ++t)
+#pragma unroll
+      for (int l = 0; l < NA; ++l) Mr[t][l] = CMPC_SO(r, L.hn, rrow[t] * NAP + l);
+    double qi[RT], qA[RT], qB[RT], ei[RT], eA[RT], eB[RT], sA[RT], sB[RT], xbi[RT], kx[RT];
+#pragma unroll
     for (int t = 0; t < RT; ++t) {
-      constexpr int dummy = 0;
-      (void)dummy;
+      if (NL * t + NL - 1 >= NA) {   // this row can be a state row
+        const int i = ri[t];
+        qi[t] = sp_ld(xs, pin + i);     ei[t] = CMPC_SO(r, L.pc, i);
+        qA[t] = sp_ld(xs, pin + rA[t]); eA[t] = CMPC_SO(r, L.pc, rA[t]);
+        qB[t] = sp_ld(xs, pin + rB[t]); eB[t] = CMPC_SO(r, L.pc, rB[t]);
+        sA[t] = CMPC_SO(r, L.s, roA[t]);
+        sB[t] = CMPC_SO(r, L.s, roB[t]);
+        xbi[t] = CMPC_SO(r, L.xb, i);
+        kx[t] = sp_ld(xs, X_KX + (rkx[t] ? i - 6 : 0));
+      }
+    }
+    // ---- phase 2 arithmetic (two partial sums per row: shorter dependent chains)
+    double acc[RT], pn[RT];
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int l = 0; l < NA; l += 2) {
-        acc0 = fma(CMPC_SO(r, L.hn, rrow[t] * NAP + l), hu[l], acc0);
-        if (l + 1 < NA) acc1 = fma(CMPC_SO(r, L.hn, rrow[t] * NAP + l + 1), hu[l + 1], acc1);
+        acc0 = fma(Mr[t][l], hu[l], acc0);
+        if (l + 1 < NA) acc1 = fma(Mr[t][l + 1], hu[l + 1], acc1);
       }
-      const double acc = acc0 + acc1;
+      acc[t] = acc0 + acc1;
+      pn[t] = 0.0;
+      if (NL * t + NL - 1 >= NA) {   // p_i = qx_i + (A'g)_i + (K'hu)_i, Kt = -K'
+        const double gi = qi[t] + ei[t], gA = qA[t] + eA[t], gB = qB[t] + eB[t];
+        const double a_ = rg0[t] ? sA[t] : 1.0, b_ = rg0[t] ? sB[t] : 0.0;
+        double pi = fma(rmul[t], fma(gA, a_, -(gB * b_)), gi) - acc[t] - rwx[t] * xbi[t];
+        if (k >= 1 && rkx[t]) pi += kx[t];
+        pn[t] = pi;
+      }
+    }
+    // ---- phase 2 stores
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
       if (NL * t < NA) {             // this row can be a control row: d_j
-        if (rok[t] && !rst[t] && on) CMPC_R(w, L.dv + rrow[t]) = acc;
+        if (rok[t] && !rst[t] && on) CMPC_R(w, L.dv + rrow[t]) = acc[t];
       }
-      if (NL * t + NL - 1 >= NA) {   // this row can be a state row: p_i = qx_i + (A'g)_i + (K'hu)_i, Kt = -K'
-        const int i = ri[t];
-        const double sA = rg0[t] ? CMPC_SO(r, L.s, roA[t]) : 1.0, sB = rg0[t] ? CMPC_SO(r, L.s, roB[t]) : 0.0;
-        const double gi = sp_ld(xs, pin + i) + CMPC_SO(r, L.pc, i);
-        const double gA = sp_ld(xs, pin + rA[t]) + CMPC_SO(r, L.pc, rA[t]);
-        const double gB = sp_ld(xs, pin + rB[t]) + CMPC_SO(r, L.pc, rB[t]);
-        double pi = fma(rmul[t], fma(gA, sA, -(gB * sB)), gi) - acc - rwx[t] * CMPC_SO(r, L.xb, i);
-        if (k >= 1 && rkx[t]) pi += sp_ld(xs, X_KX + (i - 6));
-        if (rok[t] && rst[t]) sp_st(xs, pout + i, pi);
+      if (NL * t + NL - 1 >= NA) {
+        if (rok[t] && rst[t]) sp_st(xs, pout + ri[t], pn[t]);
       }
     }
     team_sync(I);
+    CMPC_CK(3);
     buf ^= 1;
     ks.release();
     --k;
+    CMPC_CK(4);
   } while (k >= 0 && T.ns(k) == NS);
+  CMPC_CK(5);
+#undef CMPC_CK
   k_io = k;
   buf_io = buf;
 }
 
 template <int MODE, bool FAST>
-CMPC_FN void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on) {
+CMPC_OP void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on) {
   const Params P = P_in;
   const Inst I = I_in;
   const Sv S = S_in;
@@ -1131,52 +1211,80 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
     ks.peek();
     double* w = rec_of(T, I, k);
     int* imw = meta_of(T, I, k, L.meta);
+    // ---- phase 1 loads (issued before the state part, whose latency they overlap)
+    double dvj[CT > 0 ? CT : 1], ktc[CT > 0 ? CT : 1][9];
+#pragma unroll
+    for (int t = 0; t < CT; ++t) {
+      dvj[t] = CMPC_SO(r, L.dv, cj[t]);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) ktc[t][i] = CMPC_SO(r, L.kt, i * NAP + cj[t]);
+    }
     if (on) fwd_state<NS, KIND, FAST, SK>(P, S, R, r, w, I, k, x);
     const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
     // ---- phase 1: controls u~ = K x + d of the lane's rows (Kt = -K'; two partial sums per row)
     double uo[CT > 0 ? CT : 1];
 #pragma unroll
     for (int t = 0; t < CT; ++t) {
-      const int j = cj[t];
-      double v0 = CMPC_SO(r, L.dv, j), v1 = 0.0;
+      double v0 = dvj[t], v1 = 0.0;
 #pragma unroll
       for (int i = 0; i < 9; i += 2) {
-        v0 = fma(-CMPC_SO(r, L.kt, i * NAP + j), x[i], v0);
-        if (i + 1 < 9) v1 = fma(-CMPC_SO(r, L.kt, (i + 1) * NAP + j), x[i + 1], v1);
+        v0 = fma(-ktc[t][i], x[i], v0);
+        if (i + 1 < 9) v1 = fma(-ktc[t][i + 1], x[i + 1], v1);
       }
-      const double v = v0 + v1;
-      uo[t] = v;
+      uo[t] = v0 + v1;
+    }
+#pragma unroll
+    for (int t = 0; t < CT; ++t) {
       if (cok[t]) {
-        sp_st(xs, X_UX + j, v);
-        if ((PMMK || COPY) && on) CMPC_R(w, L.u + j) = v;
+        sp_st(xs, X_UX + cj[t], uo[t]);
+        if ((PMMK || COPY) && on) CMPC_R(w, L.u + cj[t]) = uo[t];
       }
     }
     team_sync(I);
-    // ---- phase 2: next state (replicated), friction rows of the lane
-    double u[NA > 0 ? NA : 1];
+    // ---- phase 2 loads: u~, stage data, the lane's friction rows
+    double u[NA > 0 ? NA : 1], dsl[NS > 0 ? NS : 1][3];
 #pragma unroll
     for (int j = 0; j < NA; ++j) u[j] = sp_ld(xs, X_UX + j);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) dsl[s][a] = CMPC_S(r, L.d + 3 * s + a);
+    const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
+    const double ckv[3] = {CMPC_S(r, L.ck), CMPC_S(r, L.ck + 1), CMPC_S(r, L.ck + 2)};
+    double fvv[FT > 0 ? FT : 1], fu0[FT > 0 ? FT : 1], fu1[FT > 0 ? FT : 1], fu2[FT > 0 ? FT : 1];
+    double tgx[FT > 0 ? FT : 1], tgy[FT > 0 ? FT : 1], tgz[FT > 0 ? FT : 1], te2[FT > 0 ? FT : 1], tub[FT > 0 ? FT : 1];
+    if (!COPY) {
+#pragma unroll
+      for (int t = 0; t < FT; ++t) {
+        const int s = fs[t];
+        fvv[t] = ADMM ? CMPC_SO(r, L.vf, fb[t]) : CMPC_SO(r, L.yf, fb[t]);
+        fu0[t] = sp_ld(xs, X_UX + 3 * s); fu1[t] = sp_ld(xs, X_UX + 3 * s + 1); fu2[t] = sp_ld(xs, X_UX + 3 * s + 2);
+        tgx[t] = fgx[t]; tgy[t] = fgy[t]; tgz[t] = -P.kf; te2[t] = fe2[t]; tub[t] = 0.0;
+        if (!FAST) {
+          tgx[t] = CMPC_SO(r, L.g, s * GS + frow[t] * 3); tgy[t] = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 1);
+          tgz[t] = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 2);
+          te2[t] = CMPC_SO(r, L.g, s * GS + 12 + frow[t]); tub[t] = CMPC_SO(r, L.g, s * GS + 16 + frow[t]);
+        }
+      }
+    }
+    // ---- phase 2: next state (replicated), friction rows of the lane
     double sF[3] = {0.0, 0.0, 0.0}, sT[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      const double ds[3] = {CMPC_S(r, L.d + 3 * s), CMPC_S(r, L.d + 3 * s + 1), CMPC_S(r, L.d + 3 * s + 2)};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const int a1 = nxt3(a), a2 = prv3(a);
         sF[a] = sF[a] + u[3 * s + a];
-        sT[a] = sT[a] + fma(ds[a1], u[3 * s + a2], -(ds[a2] * u[3 * s + a1]));
+        sT[a] = sT[a] + fma(dsl[s][a1], u[3 * s + a2], -(dsl[s][a2] * u[3 * s + a1]));
       }
     }
     double xn[9];
-    {
-      const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const int a1 = nxt3(a), a2 = prv3(a);
-        xn[a] = fma(P.dt_m, x[3 + a], x[a]);
-        xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
-        xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], CMPC_S(r, L.ck + a));
-      }
+    for (int a = 0; a < 3; ++a) {
+      const int a1 = nxt3(a), a2 = prv3(a);
+      xn[a] = fma(P.dt_m, x[3 + a], x[a]);
+      xn[3 + a] = x[3 + a] + fma(P.dt, sF[a], a == 2 ? P.dtmg : 0.0);
+      xn[6 + a] = fma(P.dt * S3[a1], x[a2], fma(-P.dt * S3[a2], x[a1], x[6 + a])) + fma(P.dt, sT[a], ckv[a]);
     }
     if (!COPY) {
       const int mt = CMPC_SI(r, L.meta, 0);
@@ -1184,18 +1292,12 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
       int newpm = 0;
 #pragma unroll
       for (int t = 0; t < FT; ++t) {
-        const int bit = fb[t], s = fs[t];
-        double gx = fgx[t], gy = fgy[t], gz = -P.kf, e2 = fe2[t], ub = 0.0;
-        if (!FAST) {
-          gx = CMPC_SO(r, L.g, s * GS + frow[t] * 3); gy = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 1);
-          gz = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 2);
-          e2 = CMPC_SO(r, L.g, s * GS + 12 + frow[t]); ub = CMPC_SO(r, L.g, s * GS + 16 + frow[t]);
-        }
-        const double u0 = sp_ld(xs, X_UX + 3 * s), u1 = sp_ld(xs, X_UX + 3 * s + 1), u2 = sp_ld(xs, X_UX + 3 * s + 2);
-        double cf = fma(gz, u2, fma(gy, u1, gx * u0));
+        const int bit = fb[t];
+        const double e2 = te2[t], ub = tub[t];
+        double cf = fma(tgz[t], fu2[t], fma(tgy[t], fu1[t], tgx[t] * fu0[t]));
         if (!FAST) cf -= ub;
         if (ADMM) {
-          const double v = CMPC_SO(r, L.vf, bit);
+          const double v = fvv[t];
           const double w0 = fmin(v, 0.0), y0 = fmax(v, 0.0);
           const double vn = fma(al, cf, fma(1.0 - al, w0, y0));
           if (fok[t] && on) CMPC_R(w, L.vf + bit) = vn;
@@ -1207,7 +1309,7 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
           }
         } else if (fok[t]) {
           const bool act = (pm >> bit) & 1;
-          const double yn = fma(inv, cf, act ? CMPC_SO(r, L.yf, bit) : 0.0);
+          const double yn = fma(inv, cf, act ? fvv[t] : 0.0);
           R.pri = fmax(R.pri, act ? fabs(cf) : fmax(cf, 0.0));
           R.npri = fmax(R.npri, FAST ? fabs(cf) : fabs(cf + ub));
           if (upd) {
@@ -1262,7 +1364,7 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
 // commit: the instance wants the residuals of this sweep (an instance that did not ask for a check may
 // ride along in the CHECK kind when a neighbour did; its iterate update is the same arithmetic)
 template <int KIND, bool FAST>
-CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on, bool commit, bool upd, int* changes) {
+CMPC_OP void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_in, bool on, bool commit, bool upd, int* changes) {
   const Params P = P_in;
   const Inst I = I_in;
   Sv S = S_in;
@@ -1319,7 +1421,7 @@ CMPC_FN void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
 // Knots are independent here: lane q of the team takes the knots q, q + NL, ... and works on the
 // global record directly.
 // rho change: keep (w, y), move v
-CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, double rho_new, double rhok_new) {
+CMPC_OP void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, double rho_new, double rhok_new) {
   const double ratio = S.rho / rho_new;
   for (int k = sub_of(I); k <= P.N; k += NL) {
     double* r = rec_of(T, I, k);
@@ -1345,7 +1447,7 @@ CMPC_FN void rescale_op(const Params& P, const TileCtx& T, const Inst& I, const 
 // active set of the polish: friction row active iff its multiplier is positive (OSQP's rule
 // -w < y <=> v > 0); trust-region rows by the branch the prox took.  Sets *kap when some knot has
 // trust-region rows.
-CMPC_FN void build_active_set_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, bool on, int* kap_out) {
+CMPC_OP void build_active_set_op(const Params& P, const TileCtx& T, const Inst& I, const Sv& S, bool on, int* kap_out) {
   const int N = P.N;
   int kap = 0;
   if (on) {
@@ -1403,7 +1505,7 @@ CMPC_FN void build_active_set_op(const Params& P, const TileCtx& T, const Inst& 
 // Team work split: the per-knot terms of the two sums by the lanes q, q + NL, ... (parked in the knot
 // records, then added up in knot order by every lane); the Gram matrix by rows (a lane walks the whole
 // horizon for its rows); the Jacobi rotations on the matrix in the scratch, rows / columns by their owners.
-CMPC_FN void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, bool on, double* snorm, double* num_out, double* den_out) {
+CMPC_OP void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, bool on, double* snorm, double* num_out, double* den_out) {
   const int N = P.N;
   const int q = sub_of(I);
   const ScratchPtr xs = scratch_of(T, I);
@@ -1552,7 +1654,7 @@ CMPC_HD int active_slots(const Params& P, const Inst& I, int k) {
   for (int c = 0; c < P.nc; ++c) ns += I.cact[(long)k * P.nc + c] ? 1 : 0;
   return ns;
 }
-CMPC_FN void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool live, double* mq_out, double* mc_out, int* nconv_out) {
+CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool live, double* mq_out, double* mc_out, int* nconv_out) {
   const int N = P.N;
   double mq = 0.0, mc = 0.0;
   int nzx = 0, nzu = 0;
@@ -1651,7 +1753,7 @@ CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc, int nconv)
   S.pri = S.dua = S.npri = S.ndua = 0.0;
 }
 
-CMPC_FN void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out) {
+CMPC_OP void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out) {
   const int N = P.N;
   double* Xo = X_out + (long)I.b * (N + 1) * 9;
   double* Uo = U_out + (long)I.b * N * P.nu;

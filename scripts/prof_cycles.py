@@ -13,7 +13,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 conf = synthetic.load_conf(name, N=100)
 solver = BatchSolver(synthetic.make_batch(conf, B))
 lib = L.load()
-out = (C.c_double * 16)()
+out = (C.c_double * 32)()
 for _ in range(2):
     solver.solve(conf.scp_params)
 torch.cuda.synchronize()
@@ -28,6 +28,10 @@ names = ["factor_admm", "sweep_admm", "build_as", "factor_pmm", "sweep_pmm", "re
 print("rc", rc, "ms", e0.elapsed_time(e1), "tiles", tiles, "mean tile cycles %.0f (%.2f ms @1.965 GHz)" % (v[13] / tiles, v[13] / tiles / 1.965e6))
 for n, x in zip(names, v):
     print("%-14s %12.0f cycles/tile  %5.1f%%" % (n, x / tiles, 100 * x / v[13]))
+for n, x in zip(["bwd: acquire+peek", "bwd: kappa term", "bwd: phase 1 + sync", "bwd: phase 2 + sync", "bwd: release/issue/--k", "bwd: loop exit"], v[16:22]):
+    print("%-24s %12.0f cycles/tile  %5.1f%%" % (n, x / tiles, 100 * x / v[13]))
+for n, x in zip(["fac: phase 1 (Y rows)", "fac: phase 2 (build rows)", "fac: phase 3 (pivots)", "fac: output"], v[22:26]):
+    print("%-24s %12.0f cycles/tile  %5.1f%%" % (n, x / tiles, 100 * x / v[13]))
 print("wait per acquire %.0f cycles" % (v[14] / max(v[15], 1)))
 st = solver.stats()
 print("admm its mean", st["qp_iters"].mean(), "factor mean", st["n_factor"].mean(), "max", st["n_factor"].max(), "pmm sweeps mean", st["info"][:, 8].mean(), "max", st["info"][:, 8].max())
