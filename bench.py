@@ -6,7 +6,11 @@
 
 A "step" is one batched solve_scp over a synthetic batch: solo12 trot, horizon N=100, 4096
 independent MPC instances per GPU (weak scaling; instances are independent, so ranks share
-nothing on the solve path and one gather collects the solutions).
+nothing on the solve path and one gather collects the solutions; the gather of step i runs on a side
+stream under the solve of step i+1).  Other BASELINE.json configurations:
+  --workload {solo12_trot,solo12_pace,solo12_bound,bolt}  --mode {A,B}  --batch B  --scaling {weak,strong}
+(strong: --batch is the GLOBAL batch, split contiguously over the ranks; e.g. the bolt configuration is
+--workload bolt --batch 8192 --scaling strong --gpus 8, the pace one --workload solo12_pace --mode A --batch 1024).
 
   value   whole-job solves/s with the problem data resident in HBM (CUDA events, max over ranks)
   e2e     the same through the C-ABI host entry point cmpc_solve_scp_host: pinned host buffers,
@@ -39,7 +43,8 @@ METRIC = "SCP-MPC solves/sec (solo12 trot N=100, batch 4096)"
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def _oracle_one(b):
+def _oracle_one(arg):
+    b, WORKLOAD = arg
     import numpy as np  # noqa: F401
     from centroidal_mpc_b200 import synthetic
     from centroidal_mpc_b200.src.centroidal_model import Centroidal_model
@@ -53,7 +58,7 @@ def _oracle_one(b):
     return 0 if sol is False else sol["iterations"]
 
 
-def cpu_oracle_throughput(n_instances, workers):
+def cpu_oracle_throughput(n_instances, workers, workload=WORKLOAD):
     """solves/s of the CPU oracle on ``n_instances`` instances of the workload with a process
     pool of ``workers`` (one single-threaded solve per process)."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -62,9 +67,9 @@ def cpu_oracle_throughput(n_instances, workers):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        pool.map(_oracle_one, range(workers))          # warm-up: imports, first-touch
+        pool.map(_oracle_one, [(b, workload) for b in range(workers)])          # warm-up: imports, first-touch
         t0 = time.time()
-        pool.map(_oracle_one, range(n_instances))
+        pool.map(_oracle_one, [(b, workload) for b in range(n_instances)])
         dt = time.time() - t0
     return n_instances / dt, dt
 
@@ -84,10 +89,10 @@ def run_reference_arm(args):
     workers = max(1, min(cores, 64))
     per_step = workers * 16
     for _ in range(args.warmup and 1):
-        cpu_oracle_throughput(workers, workers)
+        cpu_oracle_throughput(workers, workers, args.workload)
     vals, times = [], []
     for _ in range(args.steps):
-        v, dt = cpu_oracle_throughput(per_step, workers)
+        v, dt = cpu_oracle_throughput(per_step, workers, args.workload)
         vals.append(v)
         times.append(dt)
     value = float(sum(vals) / len(vals))
@@ -95,7 +100,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s N=%d" % (WORKLOAD, HORIZON), "batch_per_step": per_step,
+        "config": {"workload": "%s N=%d" % (args.workload, HORIZON), "batch_per_step": per_step,
                    "note": "CPU restatement of the reference (jax/osqp/pinocchio unavailable offline)"},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": workers, "kind": "port",
                          "sample": "%d instances per step, one single-threaded oracle solve per process" % per_step},
@@ -213,10 +218,14 @@ def run_gpu_arm(args):
     g.build()
     lib = L.load()
 
-    conf = synthetic.load_conf(WORKLOAD, N=HORIZON)
-    B = args.batch
-    # weak scaling: every rank owns B instances; instance ids are global so ranks differ
-    batch = synthetic.make_batch(conf, B, mode="B", first=rank * B)
+    workload = args.workload
+    conf = synthetic.load_conf(workload, N=HORIZON)
+    if args.scaling == "strong":   # --batch is the global batch: contiguous split, ragged shards allowed
+        lo, hi = parallel.shard_range(args.batch, rank, world)
+        B, first, Bglobal = hi - lo, lo, args.batch
+    else:                          # weak scaling: every rank owns --batch instances; instance ids are global
+        B, first, Bglobal = args.batch, rank * args.batch, args.batch * world
+    batch = synthetic.make_batch(conf, B, mode=args.mode, first=first)
     for name in ("x_init", "x_final", "X_ref", "U_init", "contact_pos", "contact_active"):
         t = torch.from_numpy(getattr(batch, name)).pin_memory()
         setattr(batch, name, t.numpy())
@@ -234,15 +243,35 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The single end-of-batch collective runs on a side stream: the gather of step i overlaps the solve of
+    # step i+1 (the solver writes into alternating result buffers, so the gather reads a finished one).
+    side = torch.cuda.Stream() if world > 1 else None
+    gathered = [None]
+    res_bufs = [(solver.X, solver.U, solver.ints), (torch.zeros_like(solver.X), torch.zeros_like(solver.U), torch.zeros_like(solver.ints))]
+    parity = [0]
+
     def step_device():
+        if world > 1:
+            solver.X, solver.U, solver.ints = res_bufs[parity[0]]
         solver.solve(conf.scp_params)
-        if world > 1:   # the single end-of-batch collective
-            parallel.gather_solutions(dict(X=solver.X, U=solver.U, ints=solver.ints[:3]), B * world, dist, dst=0)
+        if world > 1:
+            done = torch.cuda.Event()
+            done.record()
+            X, U, ints = res_bufs[parity[0]]
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                gathered[0] = parallel.gather_solutions(dict(X=X, U=U, ints=ints[:3]), Bglobal, dist, dst=0)
+            parity[0] ^= 1
+
+    def drain():
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(side)
 
     sampler = ClockSampler(local_rank)
     sampler.start()                    # nvidia-smi needs ~100 ms to deliver its first sample
     for _ in range(max(args.warmup, 3)):
         step_device()
+    drain()
     barrier()
     launches0 = lib.cmpc_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -255,6 +284,7 @@ def run_gpu_arm(args):
         e0.record()
         step_device()
         e1.record()
+    drain()          # the last gather belongs to the timed region
     t_all1.record()
     barrier()
     clocks = sampler.stop(t_host0, time.time())
@@ -284,8 +314,8 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    value = B * world * args.steps / (total_ms * 1e-3)
-    e2e = B * world * args.steps / (e2e_ms * 1e-3)
+    value = Bglobal * args.steps / (total_ms * 1e-3)
+    e2e = Bglobal * args.steps / (e2e_ms * 1e-3)
     kernel_ms = float(np.mean(step_ms))            # the step is one launch of cmpc_scp_kernel (+ gather)
     alg_bytes, flops, per_iter_bytes = algorithmic_work(batch, stats)
     peaks = {}
@@ -294,9 +324,16 @@ def run_gpu_arm(args):
     except OSError:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None   # DRAM bytes of one launch from the committed ncu --set full capture of this kernel
+    # DRAM bytes of one launch from the committed ncu --set full capture of this kernel; the file is stamped
+    # with the hash of the library it was captured with and is ignored for any other build or workload
+    traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        import hashlib
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        sha = hashlib.sha256(open(L.LIB_PATH, "rb").read()).hexdigest()
+        if traffic.get("lib_sha256") != sha or traffic.get("workload") != "%s N=%d B=%d" % (workload, HORIZON, B):
+            traffic = {"dram_bytes_per_launch": None,
+                       "source": "profiles/r2_traffic.json was captured with another build or workload (%s); not used" % traffic.get("workload")}
     except (OSError, ValueError):
         pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
@@ -305,16 +342,20 @@ def run_gpu_arm(args):
 
     cores = host_cores()
     workers = max(1, min(cores, 64))
-    cpu_v, cpu_dt = cpu_oracle_throughput(workers * 48, workers) if not args.no_cpu_baseline else (None, None)
+    cpu_v, cpu_dt = cpu_oracle_throughput(workers * 48, workers, workload) if not args.no_cpu_baseline else (None, None)
 
     srt = sorted(step_ms)
     line = {
-        "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if (workload == WORKLOAD and args.batch == BATCH_PER_GPU and args.scaling == "weak")
+                  else "SCP-MPC solves/sec (%s N=%d, batch %d %s)" % (workload, HORIZON, args.batch, args.scaling),
+        "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s N=%d" % (WORKLOAD, HORIZON), "batch_per_gpu": B, "global_batch": B * world,
-                   "mode": "B (independent reference trajectories, rng(1000+b))",
-                   "parallelism": "instances sharded across %d GPU(s), no collective on the solve path, one gather" % world,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s N=%d" % (workload, HORIZON), "batch_per_gpu": B, "global_batch": Bglobal,
+                   "mode": "B (independent reference trajectories, rng(1000+b))" if args.mode == "B"
+                           else "A (one shared reference, perturbed initial states, rng(1000+b))",
+                   "parallelism": "instances sharded across %d GPU(s), no collective on the solve path, one gather "
+                                  "(side stream, under the next step's solve)" % world,
                    "l2": "solver workspace %.2f GB per GPU (>> 126 MB L2) is streamed by every sweep; no flush needed"
                          % (lib.cmpc_workspace_bytes(solver.handle) / 1e9)},
         "latency_ms_p50": srt[len(srt) // 2],
@@ -329,7 +370,7 @@ def run_gpu_arm(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "kernel": "cmpc_scp_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_sweep_pair_per_solve": per_iter_bytes,
-                     "note": "one tile (32 instances) per SM: the dependent chain of a knot step, not HBM or the FP64 pipe, sets the time (DESIGN.md section 6)",
+                     "note": "teams of 8 lanes per instance, 4 instances per warp, 7 warps per SM at batch 4096: latency-bound on the per-knot dependent chain (DESIGN.md section 6)",
                      "fp64": {"achieved_tflops": flops / (kernel_ms * 1e-3) / 1e12, "measured_peak_tflops": tf.value,
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / max(tf.value, 1e-9)}},
         "solver_stats": {"admm_iters_mean": float(stats["qp_iters"].mean()), "admm_iters_max": int(stats["qp_iters"].max()),
@@ -352,7 +393,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU (weak) or in total (strong)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
+    ap.add_argument("--mode", default="B", choices=["A", "B"], help="B: independent references; A: perturbed initial states")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -23,9 +23,18 @@ class ProblemBatch:
         for p in probs[1:]:
             if int(p["N"]) != self.N or p["contact_active"].shape[1] != self.nc:
                 raise ValueError("all instances of a batch must share N and the number of contacts")
-            for key in ("m", "g", "dt", "mu"):
+            for key in ("m", "g", "dt", "mu", "robot"):
                 if p[key] != p0[key]:
                     raise ValueError("all instances of a batch must share %s" % key)
+            # the batch is solved with ONE model struct (weights) and one mode (nominal / stochastic)
+            for key in ("state_cost_weights", "control_cost_weights"):
+                if not np.array_equal(np.asarray(p[key]), np.asarray(p0[key])):
+                    raise ValueError("all instances of a batch must share %s" % key)
+            s0, s1 = p0.get("stochastic"), p.get("stochastic")
+            if (s0 is None) != (s1 is None):
+                raise ValueError("a batch cannot mix nominal and STOCHASTIC_OCP models")
+            if s0 is not None and any(not np.array_equal(np.asarray(s0[k]), np.asarray(s1[k])) for k in s0):
+                raise ValueError("all instances of a stochastic batch must share beta_u, Q, R, cov_w, cov_eta")
         if shared_plan is None:
             shared_plan = all(p["contact_active"] is p0["contact_active"] or
                               (np.array_equal(p["contact_active"], p0["contact_active"])

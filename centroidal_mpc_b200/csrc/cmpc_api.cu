@@ -463,8 +463,25 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   double* oX = (double*)h->d_out;
   double* oU = oX + n_X;
   int* oi = (int*)(oU + n_U);
-  // Chunks of whole tiles: the trajectories of chunk c+1 are uploaded and the results of chunk c-1 are
-  // downloaded while chunk c is being solved.
+  int *oit = oi, *ost = oi + B, *ona = oi + 2 * B;
+  // Page-locked (mapped) result buffers: the kernel writes the solution straight into host memory at a
+  // tile's write-back, so that the transfer of the tiles that finish early hides behind the slower ones
+  // and no device-to-host copy is left at the end.  Pageable buffers go through the staging buffer.
+  auto mapped = [](const void* p, void** dev) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dev = at.devicePointer;
+    return true;
+  };
+  void *mX = nullptr, *mU = nullptr, *mi = nullptr, *ms = nullptr, *mn = nullptr;
+  const bool zero_copy = mapped(X_out, &mX) && mapped(U_out, &mU) && mapped(scp_iters, &mi) && mapped(status, &ms) &&
+                         (!n_accepted || mapped(n_accepted, &mn));
+  if (zero_copy) {
+    oX = (double*)mX; oU = (double*)mU; oit = (int*)mi; ost = (int*)ms; ona = n_accepted ? (int*)mn : oi + 2 * B;
+  }
+  // Chunks of whole tiles: the trajectories of chunk c+1 are uploaded (and, without mapped buffers, the
+  // results of chunk c-1 downloaded) while chunk c is being solved.
   const int tiles = h->tiles;
   int chunks = tiles >= 4 * MAX_CHUNKS ? MAX_CHUNKS : (tiles >= 8 ? 4 : 1);
   const int per = (tiles + chunks - 1) / chunks;
@@ -478,13 +495,14 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
     const long xo = b0 * (N + 1) * 9, uo = b0 * N * nu;
     CUDA_TRY(cudaMemcpyAsync(dX + xo, X_ref + xo, nb * (N + 1) * 9 * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dU + uo, U_init + uo, nb * N * nu * 8, cudaMemcpyHostToDevice, st));
-    rc = launch_tiles(h, bt, model, scp, qp, oX, oU, oi, oi + B, oi + 2 * B, t0, t1, c, st);
+    rc = launch_tiles(h, bt, model, scp, qp, oX, oU, oit, ost, ona, t0, t1, c, st);
     if (rc) break;
+    if (zero_copy) continue;
     CUDA_TRY(cudaMemcpyAsync(X_out + xo, oX + xo, nb * (N + 1) * 9 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(U_out + uo, oU + uo, nb * N * nu * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(scp_iters + b0, oi + b0, nb * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(status + b0, oi + B + b0, nb * 4, cudaMemcpyDeviceToHost, st));
-    if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted + b0, oi + 2 * B + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(scp_iters + b0, oit + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status + b0, ost + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+    if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted + b0, ona + b0, nb * 4, cudaMemcpyDeviceToHost, st));
   }
   for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(h->cs[c]));
   return rc;

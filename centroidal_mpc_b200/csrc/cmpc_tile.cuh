@@ -1754,23 +1754,27 @@ CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc, int nconv)
 }
 
 CMPC_OP void write_solution_knots(const Params& P, const TileCtx& T, const Inst& I, double* X_out, double* U_out) {
-  const int N = P.N;
+  // The lanes of a team write consecutive elements of the instance's output arrays (8 consecutive doubles
+  // per store instruction and instance): the outputs may be mapped host memory (cmpc_solve_scp_host with
+  // page-locked buffers), where scattered 8-byte writes would be one PCIe transaction each.
+  const int N = P.N, nu = P.nu;
   double* Xo = X_out + (long)I.b * (N + 1) * 9;
-  double* Uo = U_out + (long)I.b * N * P.nu;
-  for (int k = sub_of(I); k <= N; k += NL) {
-    const double* r = rec_of(T, I, k);
+  double* Uo = U_out + (long)I.b * N * nu;
+  for (int e = sub_of(I); e < (N + 1) * 9; e += NL) {
+    const int k = e / 9, i = e - 9 * k;
     const Lay L = lay_of(T.ns(k), T.gen != 0);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Xo[k * 9 + i] = CMPC_R(r, L.x + i);
-    if (k == N) break;
+    Xo[e] = CMPC_R(rec_of(T, I, k), L.x + i);
+  }
+  for (int e = sub_of(I); e < N * nu; e += NL) {
+    const int k = e / nu, j = e - k * nu, c = j / 3, a = j - 3 * c;
+    const Lay L = lay_of(T.ns(k), T.gen != 0);
+    const double* r = rec_of(T, I, k);
     const int mt = meta_of(T, I, k, L.meta)[0];
     const int ns = mt & 7;
-    for (int j = 0; j < P.nu; ++j) Uo[k * P.nu + j] = 0.0;
-    for (int sl = 0; sl < ns; ++sl) {
-      const int cid = (mt >> (4 + 2 * sl)) & 3;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) Uo[k * P.nu + 3 * cid + a] = CMPC_R(r, L.u + 3 * sl + a);
-    }
+    double v = 0.0;   // inactive contacts carry exact zeros
+    for (int sl = 0; sl < ns; ++sl)
+      if (((mt >> (4 + 2 * sl)) & 3) == c) v = CMPC_R(r, L.u + 3 * sl + a);
+    Uo[e] = v;
   }
 }
 
@@ -2088,7 +2092,7 @@ CMPC_FN void write_stats(const Batch& bt, const Inst& I, const Sv& S, const Drv&
   double* inf = bt.info + (long)I.b * INFO;
   inf[0] = D.snorm; inf[1] = D.acc; inf[2] = S.pri; inf[3] = S.dua;
   inf[4] = S.rho; inf[5] = D.radius; inf[6] = D.weight; inf[7] = (double)D.polished;
-  inf[8] = (double)S.n_pmm; inf[9] = (double)S.n_polish; inf[10] = 0.0; inf[11] = 0.0;
+  inf[8] = (double)S.n_pmm; inf[9] = (double)S.n_polish; inf[10] = (double)D.certified; inf[11] = 0.0;
 }
 
 // bind the per-instance input pointers

@@ -265,36 +265,29 @@ def friction_backoffs(model, traj_tuple=None):
 
 
 def compute_trajectory_data(model, traj_tuple):
-    """dict(dynamics (9,N), gradients{f_x (N,9,9), f_u (N,9,nu)}, LQR_gains (N,nu,9),
-    Covs (N+1,9,9)) like the reference's compute_trajectory_data (centroidal_model.py:257-291);
-    the covariance-gradient tensors, identically zero in the reference,
-    are not produced."""
+    """dict(dynamics (9,N), gradients{f_x (N,9,9), f_u (N,9,nu), f_w (N,9,nw)}, LQR_gains (N,nu,9),
+    Covs (N+1,9,9), Covs_gradients{Cov_dx (N+1,9,9,9,N+1), Cov_du (N+1,9,9,nu,N+1)}) like the reference's
+    compute_trajectory_data (/root/reference/src/centroidal_model.py:257-291).
+    f_w = df/dp, the contact-position Jacobian the covariance propagation uses (:233-238): rows 6..8 of
+    the block of contact i are -dt [f_i]x for an active contact, zero otherwise.  The covariance-gradient
+    tensors are identically zero in the reference (nothing ever writes them after
+    the jnp.zeros of :266-267); they are returned as zeros of the reference's shapes unless
+    ``model._SKIP_COV_GRADIENTS`` is set (they take 8 N^2 (9+nu) 81 bytes)."""
     f, fx, fu = _lin_call(model, traj_tuple["state"], traj_tuple["control"], True)
     gains, covs = lqr_gains_covs(model, traj_tuple)
-    return dict(dynamics=f.T.copy(), gradients={"f_x": fx, "f_u": fu}, LQR_gains=gains, Covs=covs)
-
-
-def integrate_dynamics_trajectory(model, traj_tuple):
-    """(9, N+1) array of one-step predictions; the last column (never read by the reference,
-    scp_solver.py:82-86) repeats column N-1."""
-    f = _lin_call(model, traj_tuple["state"], traj_tuple["control"], False).T
-    return np.concatenate([f, f[:, -1:]], axis=1)
-
-
-def integrate_one_step(model, x, u, contacts_position_all, contacts_logic_all, contacts_orientation_all):
-    torch = _torch_cuda()
-    lib = L.load()
-    prob = model.problem_arrays()
-    nc = prob["contact_active"].shape[1]
-    dev = torch.device("cuda", torch.cuda.current_device())
-    X = np.zeros((1, 2, 9)); X[0, 0] = np.asarray(x, dtype=np.float64)
-    Xd = torch.from_numpy(X).to(dev)
-    Ud = torch.from_numpy(np.asarray(u, dtype=np.float64).reshape(1, 1, -1).copy()).to(dev)
-    cp = torch.from_numpy(np.asarray(contacts_position_all, dtype=np.float64).reshape(1, 1, nc, 3).copy()).to(dev)
-    ca = torch.from_numpy(np.asarray(contacts_logic_all).astype(np.int32).reshape(1, 1, nc).copy()).to(dev)
-    dims = L.cmpc_dims(1, 1, nc, 1)
-    mdl = L.make_model_struct(prob)
-    f = torch.empty((1, 1, 9), dtype=torch.float64, device=dev)
-    L.check(lib.cmpc_rollout(C.byref(dims), C.byref(mdl), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca), _ptr(f),
-                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), lib)
-    return f[0, 0].cpu().numpy()
+    N, nu = model._N, model._n_u
+    U = np.asarray(traj_tuple["control"], dtype=np.float64)
+    logic = model._contact_data["contacts_logic"]
+    nc = logic.shape[1]
+    npc = model._n_u_per_contact
+    f0 = 2 if model._robot == "TALOS" else 0
+    fw = np.zeros((N, 9, 3 * nc))
+    for k in range(N):
+        for c in range(nc):
+            if logic[k, c]:
+                fx_, fy_, fz_ = U[npc * c + f0:npc * c + f0 + 3, k]
+                fw[k, 6:9, 3 * c:3 * c + 3] = -model._dt * np.array([[0.0, -fz_, fy_], [fz_, 0.0, -fx_], [-fy_, fx_, 0.0]])
+    out = dict(dynamics=f.T.copy(), gradients={"f_x": fx, "f_u": fu, "f_w": fw}, LQR_gains=gains, Covs=covs)
+    if not getattr(model, "_SKIP_COV_GRADIENTS", False):
+        out["Covs_gradients"] = {"Cov_dx": np.zeros((N + 1, 9, 9, 9, N + 1)), "Cov_du": np.zeros((N + 1, 9, 9, nu, N + 1))}
+    return out

@@ -41,8 +41,11 @@ def gather_solutions(local, B, dist, device=None, dst=None):
         lead = t.shape[-1] if key == "ints" else t.shape[0]
         if key == "ints":
             t = t.transpose(0, 1).contiguous()           # [b, 3]
-        pad = torch.zeros((bmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:lead] = t
+        if lead == bmax:      # equal shards (the usual case): the shard itself is the send buffer
+            pad = t.contiguous()
+        else:
+            pad = torch.zeros((bmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[:lead] = t
         bufs = [torch.empty_like(pad) for _ in range(world)]
         if dst is None:
             dist.all_gather(bufs, pad)

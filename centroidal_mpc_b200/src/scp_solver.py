@@ -60,6 +60,38 @@ def solve_scp(model, scp_params):
     return all_solution
 
 
+def sum_up_all_costs(model):
+    """Cost(Q, p) of the QP in the reference's variable order (/root/reference/src/scp_solver.py:10-26): the
+    inspector view of what the device minimises (src/cost.py)."""
+    from scipy import sparse
+    from .cost import Cost, construct_state_tracking_cost, construct_state_trust_region_cost, construct_total_cost
+    total = [construct_total_cost(model), construct_state_trust_region_cost(model)]
+    if model._robot != "TALOS" and not model._DYNAMICS_FIRST:
+        total.append(construct_state_tracking_cost(model))
+    n = model._total_nb_optimizers
+    Q, p = sparse.csc_matrix((n, n)), np.zeros(n)
+    for c in total:
+        Q = Q + c.Q
+        p = p + c.p
+    return Cost(Q=sparse.csc_matrix(Q), p=p)
+
+
+def stack_up_all_constraints(model, traj_tuple, traj_data, trust_region_updates, friction_ub=None):
+    """Constraint(mat, lb, ub) of the QP in the reference's row order: initial, dynamics, final, (CoP,)
+    friction pyramid, state trust region (/root/reference/src/scp_solver.py:28-48).  ``traj_data`` is
+    ``model.compute_trajectory_data(traj_tuple)`` (the device's linearisation)."""
+    from scipy import sparse
+    from . import constraints as C
+    parts = [C.construct_initial_constraints(model), C.construct_dynamics_constraints(model, traj_tuple, traj_data),
+             C.construct_final_constraints(model)]
+    if model._robot == "TALOS":
+        parts.append(C.construct_cop_constraints(model))
+    parts += [C.construct_friction_pyramid_constraints(model, traj_tuple, traj_data, friction_ub=friction_ub),
+              C.construct_state_trust_region_constraints(model, traj_tuple, trust_region_updates)]
+    return C.Constraint(mat=sparse.vstack([c.mat for c in parts], "csc"), lb=np.hstack([c.lb for c in parts]),
+                        ub=np.hstack([c.ub for c in parts]))
+
+
 def get_QP_solution(model, z):
     """Column-major unpack of a reference-ordered decision vector (scp_solver.py:89-93)."""
     n_x, n_u, N = model._n_x, model._n_u, model._N

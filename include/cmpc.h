@@ -118,7 +118,9 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
 /* Per-instance statistics of the last solve (device pointers, each nullable):
  * qp_iters[B] total ADMM iterations, n_factor[B] Riccati factorisations, info[B][12] =
  * {sigma_max(X-Xbar), accuracy ratio, primal res, dual res, rho, radius, weight, polished,
- *  multiplier-method sweeps, polish attempts, 0, 0}.  Asynchronous copies on `stream` (pass the stream
+ *  multiplier-method sweeps, polish attempts, certified, 0}.  certified = 1: the last QP ended at a certified KKT
+ * point (active set consistent, primal residual <= active_set_tol (1 + norm), stationarity exact); 0: it ended by OSQP's
+ * termination test at eps_abs / eps_rel, i.e. with the accuracy of the reference's own solver setting.  Asynchronous copies on `stream` (pass the stream
  * of the solve, so that they are ordered after it). */
 int cmpc_get_stats(cmpc_handle h, int32_t* qp_iters, int32_t* n_factor, double* info, void* stream);
 

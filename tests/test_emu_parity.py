@@ -20,20 +20,25 @@ from test_oracle import _golden_files, load_golden
 TOL = 1e-6
 
 
+TIGHT = dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=40000, polish_refine_iter=30)
+
+
 @pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
 def test_emu_matches_oracle(cases, name):
+    """1e-6 against the tightly solved oracle (at OSQP's default tolerance, the reference's setting, the
+    oracle itself is up to 3.7e-6 away from that answer on bolt); SCP counts also against the default one."""
     conf, models = cases[name]
     out = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params)
     for b in range(2):
         ref = scp.solve_scp(models[b].problem_arrays(), conf.scp_params)
-        if ref is False:
-            continue        # OSQP's iteration cap, see test_golden
-        assert out["status"][b] == 0
-        assert out["scp_iters"][b] == ref["iterations"]
-        assert out["n_accepted"][b] == len(ref["state"])
-        tol = TOL if name != "bolt" else 5e-6      # see check_against_golden
-        assert relerr(out["X"][b].T, ref["state"][-1]) < tol
-        assert relerr(out["U"][b].T, ref["control"][-1]) < tol
+        tight = scp.solve_scp(models[b].problem_arrays(), conf.scp_params, osqp_settings=TIGHT)
+        assert tight is not False and out["status"][b] == 0
+        if ref is not False:       # OSQP's iteration cap on a feasible QP, see test_golden
+            assert out["scp_iters"][b] == ref["iterations"]
+        assert out["scp_iters"][b] == tight["iterations"]
+        assert out["n_accepted"][b] == len(tight["state"])
+        assert relerr(out["X"][b].T, tight["state"][-1]) < TOL
+        assert relerr(out["U"][b].T, tight["control"][-1]) < TOL
 
 
 @pytest.mark.parametrize("path", _golden_files(), ids=lambda p: os.path.basename(p)[:-4])
@@ -399,3 +404,25 @@ def test_team_of_8_lanes_trust_region_and_general_friction_paths(cases):
     # no early polish: ADMM runs to OSQP's termination test (CHECK sweeps, rho adaptation, rescale)
     qp = dict(active_set_start=0)
     _assert_same(E.solve_scp(batch, conf.scp_params, qp_overrides=qp, team_lanes=8), E.solve_scp(batch, conf.scp_params, qp_overrides=qp))
+
+
+# ---- branches of the trust-region loop the shipped configurations never take (tests/golden/scen_*.npz) ----
+from scenarios import check_scenario, load_scenario, scenario_files, scenario_qp   # noqa: E402
+
+
+@pytest.mark.parametrize("path", scenario_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_trust_region_scenarios_match_oracle(path):
+    """Binding L1 trust region on an ACCEPTED iterate (slack active / on the surface of the ball), rejection
+    followed by acceptance with a different QP solution (accuracy ratio; trust test), the NaN convergence
+    test of a zero warm start, an infeasible QP: trajectories at 1e-6 against the tightly solved oracle,
+    equal iteration / acceptance counts, equal verdict."""
+    g, conf, sp, model = load_scenario(path)
+    out = E.solve_scp(ProblemBatch([model]), sp, qp_overrides=scenario_qp(path))
+    check_scenario(out, 0, g, relerr)
+    if "binding" in path or "surface" in path:
+        # the rows bind: the accepted iterate leaves the L1 ball of the radius (slack) or sits on its surface
+        dk = np.abs(out["X"][0][:, 6:] - np.asarray(g["X_ref"]).T[:, 6:]).sum(axis=1).max()
+        assert dk >= float(g["radius"][-1]) * (1 - 1e-9)
+        assert abs(dk - float(g["max_dkappa_l1"])) < 1e-6
+    if "then_accept" in path:
+        assert int(g["iterations"]) == 2 and int(g["n_accepted"]) == 1

@@ -177,3 +177,20 @@ def test_product_path_has_no_cpu_fallback(cases):
             if f.endswith(".py"):
                 src += open(os.path.join(dp, f)).read()
     assert "import oracle" not in src and "from oracle" not in src and "emu_binding" not in src
+
+
+def test_batch_rejects_mixed_models():
+    """One model struct and one mode per batch: mixing weights or nominal / stochastic models raises
+    instead of silently solving everything with instance 0's settings."""
+    import copy
+    conf = synthetic.load_conf("solo12_trot", N=10)
+    a = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 0))
+    conf2 = copy.copy(conf)
+    conf2.state_cost_weights = conf.state_cost_weights * 2.0
+    b = Centroidal_model(conf2, centroidal_traj=synthetic.reference_trajectory(conf, 1))
+    with pytest.raises(ValueError, match="state_cost_weights"):
+        ProblemBatch([a, b])
+    c = Centroidal_model(conf, STOCHASTIC_OCP=True, centroidal_traj=synthetic.reference_trajectory(conf, 1))
+    with pytest.raises(ValueError, match="STOCHASTIC_OCP"):
+        ProblemBatch([a, c])
+    assert ProblemBatch([a, Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 2))]).B == 2
