@@ -94,9 +94,20 @@ CMPC_HD int sp_ldi(unsigned p, int e, int t, int which) {   // int32 pair field:
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(p - (unsigned)t * 8u + (unsigned)e * (TL * 8u) + (unsigned)(which * TL + t) * 4u));
   return v;
 }
+// pre-scaled offsets of a lane's own rows: formed once per run of knots and made opaque to the compiler, which
+// would otherwise rematerialise the index arithmetic (a third of the instructions of a knot) in every knot
+typedef unsigned SOff;
+CMPC_HD SOff s_off(int fields) { return (unsigned)fields * (TL * 8u); }
+CMPC_HD unsigned sp_at(unsigned p, SOff o) { return p + o; }
+#define CMPC_OPAQUE(x) asm volatile("" : "+r"(x))
 #else
 typedef const double* StagedPtr;
 typedef double* ScratchPtr;
+typedef long SOff;
+CMPC_HD SOff s_off(int fields) { return (long)fields * TL; }
+CMPC_HD const double* sp_at(const double* p, SOff o) { return p + o; }
+CMPC_HD double* sp_at(double* p, SOff o) { return p + o; }
+#define CMPC_OPAQUE(x)
 CMPC_HD double sp_ld(const double* p, int e) { return p[(long)e * TL]; }
 CMPC_HD void sp_st(double* p, int e, double v) { p[(long)e * TL] = v; }
 CMPC_HD int sp_ldi(const double* p, int e, int t, int which) {
@@ -833,27 +844,39 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
   constexpr Lay L = lay_of(NS, !FAST);
   constexpr int NA = 3 * NS, n = NA + 9, NAP = L.nap;
   constexpr int CT = (NA + NL - 1) / NL, RT = (n + NL - 1) / NL;
+  constexpr int CT1 = CT > 0 ? CT : 1;
   const int q = sub_of(I);
-  // the lane's control rows j = q + NL t  (hu_j)
-  int cj[CT > 0 ? CT : 1], cs[CT > 0 ? CT : 1], ca[CT > 0 ? CT : 1], ca1[CT > 0 ? CT : 1], ca2[CT > 0 ? CT : 1];
-  bool cok[CT > 0 ? CT : 1];
-  double cg[CT > 0 ? CT : 1][4];
+  // the lane's control rows j = q + NL t  (hu_j): pre-scaled offsets of everything the row touches
+  int cs4[CT1];
+  bool cok[CT1];
+  double cg[CT1][4];
+  SOff o_vf[CT1], o_p0[CT1], o_pA[CT1], o_pB[CT1], o_c0[CT1], o_cA[CT1], o_cB[CT1], o_dA[CT1], o_dB[CT1], o_g[CT1], o_gs[CT1], o_ux[CT1];
 #pragma unroll
   for (int t = 0; t < CT; ++t) {
     const int j = q + NL * t;
     cok[t] = j < NA;
-    cj[t] = cok[t] ? j : 0;
-    cs[t] = cj[t] / 3;
-    ca[t] = cj[t] - 3 * cs[t];
-    ca1[t] = ca[t] == 2 ? 0 : ca[t] + 1;
-    ca2[t] = ca[t] == 0 ? 2 : ca[t] - 1;
-    cg[t][0] = ca[t] == 0 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][1] = ca[t] == 0 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
-    cg[t][2] = ca[t] == 1 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][3] = ca[t] == 1 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
+    const int jc = cok[t] ? j : 0;
+    const int s = jc / 3, a = jc - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
+    cs4[t] = 4 * s;
+    cg[t][0] = a == 0 ? 1.0 : (a == 2 ? -P.kf : 0.0); cg[t][1] = a == 0 ? -1.0 : (a == 2 ? -P.kf : 0.0);
+    cg[t][2] = a == 1 ? 1.0 : (a == 2 ? -P.kf : 0.0); cg[t][3] = a == 1 ? -1.0 : (a == 2 ? -P.kf : 0.0);
+    o_vf[t] = s_off(so_of<SK, NS, !FAST>(MODE == MODE_ADMM ? L.vf : L.yf) + 4 * s);
+    o_p0[t] = s_off(3 + a); o_pA[t] = s_off(6 + a1); o_pB[t] = s_off(6 + a2);
+    o_c0[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + 3 + a); o_cA[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + 6 + a1);
+    o_cB[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + 6 + a2);
+    o_dA[t] = s_off(so_of<SK, NS, !FAST>(L.d) + 3 * s + a2); o_dB[t] = s_off(so_of<SK, NS, !FAST>(L.d) + 3 * s + a1);
+    o_g[t] = s_off(so_of<SK, NS, !FAST>(L.g) + s * GS + a);   // G[0][a] of the slot (rows 3 apart)
+    o_gs[t] = s_off(so_of<SK, NS, !FAST>(L.g) + s * GS);      // the slot's table: e2 at 12 + row, ub at 16 + row
+    o_ux[t] = s_off(X_UX + jc);
+    CMPC_OPAQUE(cs4[t]); CMPC_OPAQUE(o_vf[t]); CMPC_OPAQUE(o_p0[t]); CMPC_OPAQUE(o_pA[t]); CMPC_OPAQUE(o_pB[t]);
+    CMPC_OPAQUE(o_c0[t]); CMPC_OPAQUE(o_cA[t]); CMPC_OPAQUE(o_cB[t]); CMPC_OPAQUE(o_dA[t]); CMPC_OPAQUE(o_dB[t]);
+    CMPC_OPAQUE(o_g[t]); CMPC_OPAQUE(o_gs[t]); CMPC_OPAQUE(o_ux[t]);
   }
   // the lane's rows rr = q + NL t of [Hn; Kt] hu: control rows give d, state rows the new p
-  int rrow[RT], ri[RT], rA[RT], rB[RT], roA[RT], roB[RT];
+  int rrow[RT];
   bool rok[RT], rst[RT], rg0[RT], rkx[RT];
   double rmul[RT], rwx[RT];
+  SOff o_m[RT], o_pi[RT], o_qA[RT], o_qB[RT], o_ei[RT], o_eA[RT], o_eB[RT], o_sA[RT], o_sB[RT], o_xb[RT], o_kx[RT];
 #pragma unroll
   for (int t = 0; t < RT; ++t) {
     const int rr = q + NL * t;
@@ -862,15 +885,21 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     rst[t] = rrow[t] >= NA;
     const int i = rst[t] ? rrow[t] - NA : 0;
     const int g3 = i / 3, a = i - 3 * g3, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
-    ri[t] = i;
+    const int rA = g3 == 0 ? 6 + a1 : a, rB = g3 == 0 ? 6 + a2 : a;
     rg0[t] = g3 == 0;
     rkx[t] = i >= 6;
     rmul[t] = g3 == 0 ? P.dt : (g3 == 1 ? P.dt_m : 0.0);   // (A'g)_i = g_i + mul (g[rA] sA - g[rB] sB)
-    rA[t] = g3 == 0 ? 6 + a1 : a;
-    rB[t] = g3 == 0 ? 6 + a2 : a;
-    roA[t] = a2;
-    roB[t] = a1;
     rwx[t] = pick9(P.Wx, i);
+    o_m[t] = s_off(so_of<SK, NS, !FAST>(L.hn) + rrow[t] * NAP);
+    o_pi[t] = s_off(i); o_qA[t] = s_off(rA); o_qB[t] = s_off(rB);
+    o_ei[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + i); o_eA[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + rA);
+    o_eB[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + rB);
+    o_sA[t] = s_off(so_of<SK, NS, !FAST>(L.s) + a2); o_sB[t] = s_off(so_of<SK, NS, !FAST>(L.s) + a1);
+    o_xb[t] = s_off(so_of<SK, NS, !FAST>(L.xb) + i);
+    o_kx[t] = s_off(X_KX + (i >= 6 ? i - 6 : 0));
+    CMPC_OPAQUE(rrow[t]); CMPC_OPAQUE(o_m[t]); CMPC_OPAQUE(o_pi[t]); CMPC_OPAQUE(o_qA[t]); CMPC_OPAQUE(o_qB[t]);
+    CMPC_OPAQUE(o_ei[t]); CMPC_OPAQUE(o_eA[t]); CMPC_OPAQUE(o_eB[t]); CMPC_OPAQUE(o_sA[t]); CMPC_OPAQUE(o_sB[t]);
+    CMPC_OPAQUE(o_xb[t]); CMPC_OPAQUE(o_kx[t]);
   }
   int k = k_io, buf = buf_io;
 #if defined(CMPC_PROFILE) && defined(__CUDACC__)
@@ -887,9 +916,9 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     ks.peek();
     CMPC_CK(0);
     double* w = rec_of(T, I, k);
-    const int pin = X_PX + buf * 9, pout = X_PX + (buf ^ 1) * 9;
+    const ScratchPtr pin = sp_at(xs, s_off(X_PX + buf * 9)), pout = sp_at(xs, s_off(X_PX + (buf ^ 1) * 9));
     // ---- phase 1 loads
-    const int nsl = CMPC_SI(r, L.meta, 0) & 7;
+    const int nsl4 = 4 * (CMPC_SI(r, L.meta, 0) & 7);
     const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
     const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
     double kin[4] = {0.0, 0.0, 0.0, 0.0};   // ADMM: vk[3]; multiplier mode: yk[4]
@@ -900,29 +929,28 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
 #pragma unroll
       for (int a = 0; a < 4; ++a) kin[a] = CMPC_S(r, L.yk + a);
     }
-    double fv[CT > 0 ? CT : 1][4], fg[CT > 0 ? CT : 1][4], fe[CT > 0 ? CT : 1][4], fu[CT > 0 ? CT : 1][4];
-    double p0[CT > 0 ? CT : 1], pA[CT > 0 ? CT : 1], pB[CT > 0 ? CT : 1], c0[CT > 0 ? CT : 1], cA[CT > 0 ? CT : 1], cB[CT > 0 ? CT : 1];
-    double dA[CT > 0 ? CT : 1], dB[CT > 0 ? CT : 1];
+    double fv[CT1][4], fg[CT1][4], fe[CT1][4], fu[CT1][4];
+    double p0[CT1], pA[CT1], pB[CT1], c0[CT1], cA[CT1], cB[CT1], dA[CT1], dB[CT1];
 #pragma unroll
     for (int t = 0; t < CT; ++t) {
-      const int s = cs[t];
+      const StagedPtr rv = sp_at(r, o_vf[t]), rg = sp_at(r, o_g[t]);
 #pragma unroll
       for (int row = 0; row < 4; ++row) {
-        fv[t][row] = (MODE == MODE_ADMM) ? CMPC_SO(r, L.vf, 4 * s + row) : CMPC_SO(r, L.yf, 4 * s + row);
+        fv[t][row] = sp_ld(rv, row);
         fg[t][row] = cg[t][row];
         fe[t][row] = row < 2 ? P.e2[0] : P.e2[2];
         fu[t][row] = 0.0;
         if (!FAST) {
-          fg[t][row] = CMPC_SO(r, L.g, s * GS + row * 3 + ca[t]);
-          fe[t][row] = CMPC_SO(r, L.g, s * GS + 12 + row);
-          fu[t][row] = CMPC_SO(r, L.g, s * GS + 16 + row);
+          fg[t][row] = sp_ld(rg, row * 3);
+          fe[t][row] = sp_ld(sp_at(r, o_gs[t]), 12 + row);
+          fu[t][row] = sp_ld(sp_at(r, o_gs[t]), 16 + row);
         }
       }
-      p0[t] = sp_ld(xs, pin + 3 + ca[t]);  c0[t] = CMPC_SO(r, L.pc, 3 + ca[t]);
-      pA[t] = sp_ld(xs, pin + 6 + ca1[t]); cA[t] = CMPC_SO(r, L.pc, 6 + ca1[t]);
-      pB[t] = sp_ld(xs, pin + 6 + ca2[t]); cB[t] = CMPC_SO(r, L.pc, 6 + ca2[t]);
-      dA[t] = CMPC_SO(r, L.d, 3 * s + ca2[t]);
-      dB[t] = CMPC_SO(r, L.d, 3 * s + ca1[t]);
+      p0[t] = sp_ld(sp_at(pin, o_p0[t]), 0); c0[t] = sp_ld(sp_at(r, o_c0[t]), 0);
+      pA[t] = sp_ld(sp_at(pin, o_pA[t]), 0); cA[t] = sp_ld(sp_at(r, o_cA[t]), 0);
+      pB[t] = sp_ld(sp_at(pin, o_pB[t]), 0); cB[t] = sp_ld(sp_at(r, o_cB[t]), 0);
+      dA[t] = sp_ld(sp_at(r, o_dA[t]), 0);
+      dB[t] = sp_ld(sp_at(r, o_dB[t]), 0);
     }
     // ---- phase 1 arithmetic: linear term of the kappa rows (replicated), hu of the lane's control rows
     double kl[3] = {0.0, 0.0, 0.0};
@@ -937,11 +965,10 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
         pmm_kappa_terms(P, S, pm, kb, kin, kM, kl);
       }
     }
-    double huo[CT > 0 ? CT : 1];
+    double huo[CT1];
 #pragma unroll
     for (int t = 0; t < CT; ++t) {
-      const int s = cs[t];
-      const double dtr = s < nsl ? P.dt : 0.0;
+      const double dtr = cs4[t] < nsl4 ? P.dt : 0.0;
       double tt[4];
 #pragma unroll
       for (int row = 0; row < 4; ++row) {
@@ -949,7 +976,7 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
           tt[row] = S.rho * fe[t][row] * fabs(fv[t][row]);                      // -(rho e2 w - y) = rho e2 |v|
           if (!FAST) tt[row] = fma(-S.rho * fe[t][row], fu[t][row], tt[row]);   // unshifted w = min(v, 0) + ub
         } else {
-          tt[row] = ((pm >> (4 * s + row)) & 1) ? (FAST ? fv[t][row] : fma(-P.inv_delta, fu[t][row], fv[t][row])) : 0.0;
+          tt[row] = ((pm >> (cs4[t] + row)) & 1) ? (FAST ? fv[t][row] : fma(-P.inv_delta, fu[t][row], fv[t][row])) : 0.0;
         }
       }
       const double o = fma(fg[t][3], tt[3], fma(fg[t][2], tt[2], fma(fg[t][1], tt[1], fg[t][0] * tt[0])));
@@ -962,7 +989,7 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     for (int a = 0; a < 3; ++a) sp_st(xs, X_KX + a, kl[a]);
 #pragma unroll
     for (int t = 0; t < CT; ++t)
-      if (cok[t]) sp_st(xs, X_UX + cj[t], huo[t]);
+      if (cok[t]) sp_st(sp_at(xs, o_ux[t]), 0, huo[t]);
     team_sync(I);
     CMPC_CK(2);
     // ---- phase 2 loads: hu, the lane's rows of [Hn; Kt], the operands of the state rows
@@ -970,21 +997,22 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
 #pragma unroll
     for (int l = 0; l < NA; ++l) hu[l] = sp_ld(xs, X_UX + l);
 #pragma unroll
-    for (int t = 0; t < RT; ++t)
+    for (int t = 0; t < RT; ++t) {
+      const StagedPtr rm = sp_at(r, o_m[t]);
 #pragma unroll
-      for (int l = 0; l < NA; ++l) Mr[t][l] = CMPC_SO(r, L.hn, rrow[t] * NAP + l);
+      for (int l = 0; l < NA; ++l) Mr[t][l] = sp_ld(rm, l);
+    }
     double qi[RT], qA[RT], qB[RT], ei[RT], eA[RT], eB[RT], sA[RT], sB[RT], xbi[RT], kx[RT];
 #pragma unroll
     for (int t = 0; t < RT; ++t) {
       if (NL * t + NL - 1 >= NA) {   // this row can be a state row
-        const int i = ri[t];
-        qi[t] = sp_ld(xs, pin + i);     ei[t] = CMPC_SO(r, L.pc, i);
-        qA[t] = sp_ld(xs, pin + rA[t]); eA[t] = CMPC_SO(r, L.pc, rA[t]);
-        qB[t] = sp_ld(xs, pin + rB[t]); eB[t] = CMPC_SO(r, L.pc, rB[t]);
-        sA[t] = CMPC_SO(r, L.s, roA[t]);
-        sB[t] = CMPC_SO(r, L.s, roB[t]);
-        xbi[t] = CMPC_SO(r, L.xb, i);
-        kx[t] = sp_ld(xs, X_KX + (rkx[t] ? i - 6 : 0));
+        qi[t] = sp_ld(sp_at(pin, o_pi[t]), 0); ei[t] = sp_ld(sp_at(r, o_ei[t]), 0);
+        qA[t] = sp_ld(sp_at(pin, o_qA[t]), 0); eA[t] = sp_ld(sp_at(r, o_eA[t]), 0);
+        qB[t] = sp_ld(sp_at(pin, o_qB[t]), 0); eB[t] = sp_ld(sp_at(r, o_eB[t]), 0);
+        sA[t] = sp_ld(sp_at(r, o_sA[t]), 0);
+        sB[t] = sp_ld(sp_at(r, o_sB[t]), 0);
+        xbi[t] = sp_ld(sp_at(r, o_xb[t]), 0);
+        kx[t] = sp_ld(sp_at(xs, o_kx[t]), 0);
       }
     }
     // ---- phase 2 arithmetic (two partial sums per row: shorter dependent chains)
@@ -1014,7 +1042,7 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
         if (rok[t] && !rst[t] && on) CMPC_R(w, L.dv + rrow[t]) = acc[t];
       }
       if (NL * t + NL - 1 >= NA) {
-        if (rok[t] && rst[t]) sp_st(xs, pout + ri[t], pn[t]);
+        if (rok[t] && rst[t]) sp_st(sp_at(pout, o_pi[t]), 0, pn[t]);
       }
     }
     team_sync(I);

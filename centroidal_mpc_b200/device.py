@@ -291,3 +291,29 @@ def compute_trajectory_data(model, traj_tuple):
     if not getattr(model, "_SKIP_COV_GRADIENTS", False):
         out["Covs_gradients"] = {"Cov_dx": np.zeros((N + 1, 9, 9, 9, N + 1)), "Cov_du": np.zeros((N + 1, 9, 9, nu, N + 1))}
     return out
+
+
+def integrate_dynamics_trajectory(model, traj_tuple):
+    """(9, N+1) array of one-step predictions; the last column (never read by the reference,
+    scp_solver.py:82-86) repeats column N-1."""
+    f = _lin_call(model, traj_tuple["state"], traj_tuple["control"], False).T
+    return np.concatenate([f, f[:, -1:]], axis=1)
+
+
+def integrate_one_step(model, x, u, contacts_position_all, contacts_logic_all, contacts_orientation_all):
+    torch = _torch_cuda()
+    lib = L.load()
+    prob = model.problem_arrays()
+    nc = prob["contact_active"].shape[1]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    X = np.zeros((1, 2, 9)); X[0, 0] = np.asarray(x, dtype=np.float64)
+    Xd = torch.from_numpy(X).to(dev)
+    Ud = torch.from_numpy(np.asarray(u, dtype=np.float64).reshape(1, 1, -1).copy()).to(dev)
+    cp = torch.from_numpy(np.asarray(contacts_position_all, dtype=np.float64).reshape(1, 1, nc, 3).copy()).to(dev)
+    ca = torch.from_numpy(np.asarray(contacts_logic_all).astype(np.int32).reshape(1, 1, nc).copy()).to(dev)
+    dims = L.cmpc_dims(1, 1, nc, 1)
+    mdl = L.make_model_struct(prob)
+    f = torch.empty((1, 1, 9), dtype=torch.float64, device=dev)
+    L.check(lib.cmpc_rollout(C.byref(dims), C.byref(mdl), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca), _ptr(f),
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), lib)
+    return f[0, 0].cpu().numpy()

@@ -161,6 +161,11 @@ int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, doubl
                            const double* covs, const double* contact_R, const int32_t* contact_active,
                            double* friction_ub, void* stream);
 
+/* Diagnostics of a profiling build of the library (-DCMPC_PROFILE, scripts/variant.sh prof): cycle counters per
+ * operation kind summed over all tiles since the last call, out32[32] (layout: scripts/prof_cycles.py).
+ * Returns -1 in a normal build.  Not part of the reference's interface. */
+int cmpc_debug_profile(double* out32);
+
 /* DFMA micro-benchmark on the current device: achieved FP64 TFLOP/s and the SM clock (MHz) seen. */
 int cmpc_fp64_peak(double* tflops, double* ms);
 

@@ -29,3 +29,24 @@ def cases():
         out[name] = (conf, [Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, b))
                             for b in range(3)])
     return out
+
+
+def with_weights_of(model, other):
+    """Copy of ``model`` (its gait / contact plan / warm start) carrying the cost weights of ``other``: a batch
+    shares one set of weights (ProblemBatch refuses anything else)."""
+    import copy
+    m = copy.copy(model)
+    m._state_cost_weights = other._state_cost_weights
+    m._control_cost_weights = other._control_cost_weights
+    return m
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    """A CUDA device and the built library (the GPU tests skip without a device)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+    g.build()
+    return torch

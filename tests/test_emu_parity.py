@@ -29,12 +29,27 @@ def test_emu_matches_oracle(cases, name):
     oracle itself is up to 3.7e-6 away from that answer on bolt); SCP counts also against the default one."""
     conf, models = cases[name]
     out = E.solve_scp(ProblemBatch(models[:2]), conf.scp_params)
-    for b in range(2):
-        ref = scp.solve_scp(models[b].problem_arrays(), conf.scp_params)
-        tight = scp.solve_scp(models[b].problem_arrays(), conf.scp_params, osqp_settings=TIGHT)
-        assert tight is not False and out["status"][b] == 0
+    check_against_tight_oracle(name, conf, models[:2], out)
+
+
+def check_against_tight_oracle(name, conf, models, out):
+    for b, m in enumerate(models):
+        ref = scp.solve_scp(m.problem_arrays(), conf.scp_params)
+        tight = scp.solve_scp(m.problem_arrays(), conf.scp_params, osqp_settings=TIGHT)
+        assert out["status"][b] == 0
         if ref is not False:       # OSQP's iteration cap on a feasible QP, see test_golden
             assert out["scp_iters"][b] == ref["iterations"]
+        if tight is False:
+            # bolt, instance 1: the OSQP restatement needs 96 275 iterations at eps 1e-9 (DESIGN.md section 5);
+            # the independent answer is HiGHS's (tests/golden/bolt_b1_highs.npz).  The device's polish does
+            # not certify on this QP and it ends by OSQP's termination test (info[10] = 0): the accuracy class
+            # of the reference's own tolerance eps = 1e-7, here 6e-6.
+            assert name == "bolt" and b == 1
+            g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bolt_b1_highs.npz"))
+            assert out["info"][b, 10] == 0.0
+            assert relerr(out["X"][b].T, g["X"]) < 1e-5 and relerr(out["U"][b].T, g["U"]) < 1e-5
+            continue
+        assert out["info"][b, 10] == 1.0     # certified KKT point
         assert out["scp_iters"][b] == tight["iterations"]
         assert out["n_accepted"][b] == len(tight["state"])
         assert relerr(out["X"][b].T, tight["state"][-1]) < TOL
@@ -97,7 +112,8 @@ def test_ragged_and_unshared_plans(cases):
     """Instances with different contact plans in one batch (no shared plan)."""
     conf_t, mt = cases["solo12_trot"]
     conf_b, mb = cases["solo12_bound"]
-    batch = ProblemBatch([mt[0], mb[0]], shared_plan=False)
+    from conftest import with_weights_of
+    batch = ProblemBatch([mt[0], with_weights_of(mb[0], mt[0])], shared_plan=False)
     # same robot, same N, different gait and weights would differ -> use trot weights for both
     out = E.solve_scp(batch, conf_t.scp_params)
     single = E.solve_scp(ProblemBatch([mt[0]]), conf_t.scp_params)

@@ -14,16 +14,6 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-6
 
 
-@pytest.fixture(scope="module")
-def gpu():
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    import __graft_entry__ as g
-    g.build()
-    return torch
-
-
 def test_smoke(gpu):
     import __graft_entry__ as g
     g.smoke()
@@ -56,17 +46,10 @@ def test_oracle_parity(gpu, cases, name):
     the oracle at the reference's settings."""
     from centroidal_mpc_b200.src.scp_solver import solve_scp_batched
     from oracle import scp
+    from test_emu_parity import check_against_tight_oracle
     conf, models = cases[name]
-    out = solve_scp_batched(models, conf.scp_params)
-    for b, m in enumerate(models[:2]):
-        ref = scp.solve_scp(m.problem_arrays(), conf.scp_params)
-        tight = scp.solve_scp(m.problem_arrays(), conf.scp_params, osqp_settings=TIGHT)
-        assert tight is not False and out["status"][b] == 0
-        if ref is not False:
-            assert out["scp_iters"][b] == ref["iterations"]
-        assert out["scp_iters"][b] == tight["iterations"] and out["n_accepted"][b] == len(tight["state"])
-        assert relerr(out["X"][b].T, tight["state"][-1]) < TOL
-        assert relerr(out["U"][b].T, tight["control"][-1]) < TOL
+    out = solve_scp_batched(models, conf.scp_params, return_stats=True)
+    check_against_tight_oracle(name, conf, models[:2], out)
 
 
 @pytest.mark.parametrize("name,B", [("solo12_trot", 64), ("solo12_pace", 33), ("bolt", 7)])
@@ -238,7 +221,8 @@ def test_general_friction_path_and_ragged_plans_on_device(gpu, cases):
     # different gaits in one tile: trot and bound plans side by side
     conf_t, mt = cases["solo12_trot"]
     _, mb = cases["solo12_bound"]
-    mixed = ProblemBatch([mt[0], mb[0], mt[1], mb[1]], shared_plan=False)
+    from conftest import with_weights_of
+    mixed = ProblemBatch([mt[0], with_weights_of(mb[0], mt[0]), mt[1], with_weights_of(mb[1], mt[0])], shared_plan=False)
     out = solve_scp_batched(mixed, conf_t.scp_params, return_stats=True)
     emu = E.solve_scp(mixed, conf_t.scp_params)
     np.testing.assert_array_equal(out["qp_iters"], emu["qp_iters"])
