@@ -111,7 +111,7 @@ def make_qp_struct(overrides=None, lib=None):
         q.max_iter, q.check_termination, q.polish, q.polish_refine_iter, q.adaptive_rho = 4000, 25, 1, 3, 1
         q.adaptive_rho_start = 200
         q.polish_active_set_rounds = 9
-        q.active_set_start, q.active_set_step, q.active_set_tol = 20, 20, 1e-9
+        q.active_set_start, q.active_set_step, q.active_set_tol = 8, 8, 1e-9
     for k, v in (overrides or {}).items():
         if not hasattr(q, k):
             raise CmpcError("unknown QP setting %r" % k)

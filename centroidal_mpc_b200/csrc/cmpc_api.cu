@@ -367,6 +367,7 @@ static int launch_tiles(cmpc_handle h, const Batch& bt_in, const cmpc_model* mod
     default_qp_settings(&dq);   // multiplier sweeps and active-set rounds to certify
     dq.polish_refine_iter = 10;
     dq.polish_active_set_rounds = 19;
+    dq.active_set_start = dq.active_set_step = 20;   // the back-offs need a better first guess of the active set
     qp = &dq;
   }
   int rc = fill_params(&prm, &h->dims, model, scp, qp, bt_in.cR == nullptr);

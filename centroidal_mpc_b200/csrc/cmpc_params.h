@@ -21,8 +21,8 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
   s->adaptive_rho = 1;
   s->adaptive_rho_start = 200;  // early residuals are transient: adapting on them hurts
   s->polish_active_set_rounds = 9;
-  s->active_set_start = 20;     // first certified-polish attempt after 20 ADMM iterations
-  s->active_set_step = 20;     // doubled after every failed attempt
+  s->active_set_start = 8;      // first certified-polish attempt after 8 ADMM iterations (swept on B200: DESIGN.md section 6)
+  s->active_set_step = 8;      // doubled after every failed attempt
   s->active_set_tol = 1e-9;
 }
 

@@ -362,6 +362,7 @@ struct Sv {
   double nq, dynrow;               // constant parts of the residual norms
   int kap;                         // multiplier method: some knot has trust-region rows
   int fail;                        // a pivot was not positive
+  int kbad;                        // polish: the trust-region rows of some knot contradict the branch they were given
   int lost;                        // a bulk copy never landed (device)
   int nconv;                       // all-zero warm start: the reference's convergence() is NaN, never below the threshold
   int n_pmm, n_polish;             // statistics: multiplier-method sweeps, polish attempts
@@ -1107,7 +1108,7 @@ CMPC_OP void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S
 // COPY: read-only LQR roll-out of the ADMM iterate into the solution record.
 // Team work split: x~ is replicated; phase 1 the owners of the control rows publish u~; phase 2 every
 // lane forms x~+, the friction rows (4 per slot) are updated by their owners.
-struct Res { double pri, dua, npri, ndua; };
+struct Res { double pri, dua, npri, ndua; int kbad; };
 
 template <int NS, int KIND, bool FAST, int SK>
 CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, const Inst& I, int k, const double* x) {
@@ -1146,22 +1147,37 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
         }
       }
     } else if (PMMK) {
-      if (S.kap) {
-        const int pm = CMPC_SI(r, L.meta, 1);
-        const int br = (pm >> 16) & 3;
-        if (br != 0) {
-          const double inv = P.inv_delta;
-          double accv = -S.radius;
+      // The trust-region rows enter the polish by the branch the prox took in the ADMM iterate (inside the
+      // L1 ball / linear penalty / on the surface).  Unlike the friction rows they are not corrected inside
+      // a polish attempt, so the point must CONFIRM the branch: inside -> |dkappa|_1 <= r; linear ->
+      // |dkappa|_1 >= r with the assumed signs; surface -> multiplier in [0, omega].  Otherwise the attempt
+      // is void (R.kbad) and ADMM goes on to a better guess.
+      const int pm = S.kap ? CMPC_SI(r, L.meta, 1) : 0;
+      const int br = (pm >> 16) & 3;
+      const double inv = P.inv_delta;
+      const double ktol = 1e-9 * (1.0 + S.radius);
+      double accv = -S.radius, dk1 = 0.0;
+      bool flip = false;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int code = (pm >> (18 + 2 * i)) & 3;
-            const double sgn = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
-            const double dk = x[6 + i] - CMPC_S(r, L.xb + 6 + i);
-            if (code == 0) CMPC_R(w, L.yk + i) = CMPC_S(r, L.yk + i) + inv * dk;
-            accv += sgn * dk;
-          }
-          if (br == 2) CMPC_R(w, L.yk + 3) = CMPC_S(r, L.yk + 3) + inv * accv;
+      for (int i = 0; i < 3; ++i) {
+        const int code = (pm >> (18 + 2 * i)) & 3;
+        const double sgn = code == 1 ? 1.0 : (code == 2 ? -1.0 : 0.0);
+        const double dk = x[6 + i] - CMPC_S(r, L.xb + 6 + i);
+        dk1 += fabs(dk);
+        if (br != 0) {
+          if (code == 0) CMPC_R(w, L.yk + i) = CMPC_S(r, L.yk + i) + inv * dk;
+          else if (sgn * dk < -ktol) flip = true;
+          accv += sgn * dk;
         }
+      }
+      if (br == 0) {
+        if (dk1 > S.radius + ktol) R.kbad = 1;
+      } else if (br == 1) {
+        if (dk1 < S.radius - ktol || flip) R.kbad = 1;
+      } else {
+        const double ys = CMPC_S(r, L.yk + 3) + inv * accv;
+        CMPC_R(w, L.yk + 3) = ys;
+        if (flip || ys < -1e-9 * (1.0 + S.weight) || ys > S.weight * (1.0 + 1e-9)) R.kbad = 1;
       }
 #pragma unroll
       for (int a = 0; a < 3; ++a) R.npri = fmax(R.npri, fabs(x[6 + a]));
@@ -1205,10 +1221,12 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
   const int N = P.N;
   const double al = ADMM ? P.alpha : 1.0;
   const double inv = P.inv_delta;
-  // the lane's control rows j = q + NL t (u_j) and friction rows bit = q + NL t (4 per slot)
-  int cj[CT > 0 ? CT : 1], cs[CT > 0 ? CT : 1], ca[CT > 0 ? CT : 1];
-  bool cok[CT > 0 ? CT : 1];
-  double cg[CT > 0 ? CT : 1][4];
+  // the lane's control rows j = q + NL t (u_j) and friction rows bit = q + NL t (4 per slot): pre-scaled offsets
+  constexpr int CT1 = CT > 0 ? CT : 1, FT1 = FT > 0 ? FT : 1;
+  int cj[CT1], cs[CT1], ca[CT1];
+  bool cok[CT1];
+  double cg[CT1][4];
+  SOff o_dv[CT1], o_kt[CT1], o_ux[CT1], o_gc[CT1], o_dx[CT1];
 #pragma unroll
   for (int t = 0; t < CT; ++t) {
     const int j = q + NL * t;
@@ -1218,20 +1236,33 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
     ca[t] = cj[t] - 3 * cs[t];
     cg[t][0] = ca[t] == 0 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][1] = ca[t] == 0 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
     cg[t][2] = ca[t] == 1 ? 1.0 : (ca[t] == 2 ? -P.kf : 0.0); cg[t][3] = ca[t] == 1 ? -1.0 : (ca[t] == 2 ? -P.kf : 0.0);
+    o_dv[t] = s_off(so_of<SK, NS, !FAST>(L.dv) + cj[t]);
+    o_kt[t] = s_off(so_of<SK, NS, !FAST>(L.kt) + cj[t]);
+    o_ux[t] = s_off(X_UX + cj[t]);
+    o_gc[t] = s_off(so_of<SK, NS, !FAST>(L.g) + cs[t] * GS + ca[t]);
+    o_dx[t] = s_off(X_DX + 4 * cs[t]);
+    CMPC_OPAQUE(cj[t]); CMPC_OPAQUE(cs[t]); CMPC_OPAQUE(ca[t]);
+    CMPC_OPAQUE(o_dv[t]); CMPC_OPAQUE(o_kt[t]); CMPC_OPAQUE(o_ux[t]); CMPC_OPAQUE(o_gc[t]); CMPC_OPAQUE(o_dx[t]);
   }
-  int fb[FT > 0 ? FT : 1], fs[FT > 0 ? FT : 1], frow[FT > 0 ? FT : 1];
-  bool fok[FT > 0 ? FT : 1];
-  double fgx[FT > 0 ? FT : 1], fgy[FT > 0 ? FT : 1], fe2[FT > 0 ? FT : 1];
+  int fb[FT1];
+  bool fok[FT1];
+  double fgx[FT1], fgy[FT1], fe2[FT1];
+  SOff o_fv[FT1], o_fu[FT1], o_fg[FT1], o_fe[FT1], o_fd[FT1];
 #pragma unroll
   for (int t = 0; t < FT; ++t) {
     const int bit = q + NL * t;
     fok[t] = bit < 4 * NS;
     fb[t] = fok[t] ? bit : 0;
-    fs[t] = fb[t] >> 2;
-    frow[t] = fb[t] & 3;
-    fgx[t] = frow[t] == 0 ? 1.0 : (frow[t] == 1 ? -1.0 : 0.0);
-    fgy[t] = frow[t] == 2 ? 1.0 : (frow[t] == 3 ? -1.0 : 0.0);
-    fe2[t] = frow[t] < 2 ? P.e2[0] : P.e2[2];
+    const int s = fb[t] >> 2, row = fb[t] & 3;
+    fgx[t] = row == 0 ? 1.0 : (row == 1 ? -1.0 : 0.0);
+    fgy[t] = row == 2 ? 1.0 : (row == 3 ? -1.0 : 0.0);
+    fe2[t] = row < 2 ? P.e2[0] : P.e2[2];
+    o_fv[t] = s_off(so_of<SK, NS, !FAST>((KIND == FW_ADMM || KIND == FW_ADMM_CHECK) ? L.vf : L.yf) + fb[t]);
+    o_fu[t] = s_off(X_UX + 3 * s);
+    o_fg[t] = s_off(so_of<SK, NS, !FAST>(L.g) + s * GS + row * 3);
+    o_fe[t] = s_off(so_of<SK, NS, !FAST>(L.g) + s * GS + 12 + row);   // ub 4 further
+    o_fd[t] = s_off(X_DX + fb[t]);
+    CMPC_OPAQUE(fb[t]); CMPC_OPAQUE(o_fv[t]); CMPC_OPAQUE(o_fu[t]); CMPC_OPAQUE(o_fg[t]); CMPC_OPAQUE(o_fe[t]); CMPC_OPAQUE(o_fd[t]);
   }
   int k = k_io;
   do {
@@ -1243,9 +1274,10 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
     double dvj[CT > 0 ? CT : 1], ktc[CT > 0 ? CT : 1][9];
 #pragma unroll
     for (int t = 0; t < CT; ++t) {
-      dvj[t] = CMPC_SO(r, L.dv, cj[t]);
+      dvj[t] = sp_ld(sp_at(r, o_dv[t]), 0);
+      const StagedPtr rk = sp_at(r, o_kt[t]);
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ktc[t][i] = CMPC_SO(r, L.kt, i * NAP + cj[t]);
+      for (int i = 0; i < 9; ++i) ktc[t][i] = sp_ld(rk, i * NAP);
     }
     if (on) fwd_state<NS, KIND, FAST, SK>(P, S, R, r, w, I, k, x);
     const double tolc = P.as_tol * (1.0 + S.npri);   // row-violation threshold (npri of the previous sweep)
@@ -1264,7 +1296,7 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
 #pragma unroll
     for (int t = 0; t < CT; ++t) {
       if (cok[t]) {
-        sp_st(xs, X_UX + cj[t], uo[t]);
+        sp_st(sp_at(xs, o_ux[t]), 0, uo[t]);
         if ((PMMK || COPY) && on) CMPC_R(w, L.u + cj[t]) = uo[t];
       }
     }
@@ -1284,14 +1316,14 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
     if (!COPY) {
 #pragma unroll
       for (int t = 0; t < FT; ++t) {
-        const int s = fs[t];
-        fvv[t] = ADMM ? CMPC_SO(r, L.vf, fb[t]) : CMPC_SO(r, L.yf, fb[t]);
-        fu0[t] = sp_ld(xs, X_UX + 3 * s); fu1[t] = sp_ld(xs, X_UX + 3 * s + 1); fu2[t] = sp_ld(xs, X_UX + 3 * s + 2);
+        const ScratchPtr xu = sp_at(xs, o_fu[t]);
+        fvv[t] = sp_ld(sp_at(r, o_fv[t]), 0);
+        fu0[t] = sp_ld(xu, 0); fu1[t] = sp_ld(xu, 1); fu2[t] = sp_ld(xu, 2);
         tgx[t] = fgx[t]; tgy[t] = fgy[t]; tgz[t] = -P.kf; te2[t] = fe2[t]; tub[t] = 0.0;
         if (!FAST) {
-          tgx[t] = CMPC_SO(r, L.g, s * GS + frow[t] * 3); tgy[t] = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 1);
-          tgz[t] = CMPC_SO(r, L.g, s * GS + frow[t] * 3 + 2);
-          te2[t] = CMPC_SO(r, L.g, s * GS + 12 + frow[t]); tub[t] = CMPC_SO(r, L.g, s * GS + 16 + frow[t]);
+          const StagedPtr rg = sp_at(r, o_fg[t]), re = sp_at(r, o_fe[t]);
+          tgx[t] = sp_ld(rg, 0); tgy[t] = sp_ld(rg, 1); tgz[t] = sp_ld(rg, 2);
+          te2[t] = sp_ld(re, 0); tub[t] = sp_ld(re, 4);
         }
       }
     }
@@ -1333,7 +1365,7 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
             const double wn = fmin(vn, 0.0);
             R.pri = fmax(R.pri, fabs(cf - wn));
             R.npri = fmax(R.npri, FAST ? fmax(fabs(cf), fabs(wn)) : fmax(fabs(cf + ub), fabs(wn + ub)));
-            sp_st(xs, X_DX + bit, S.rho * e2 * (fmax(vn, 0.0) - y0 - cf + w0));
+            sp_st(sp_at(xs, o_fd[t]), 0, S.rho * e2 * (fmax(vn, 0.0) - y0 - cf + w0));
           }
         } else if (fok[t]) {
           const bool act = (pm >> bit) & 1;
@@ -1364,9 +1396,9 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
             const int s = cs[t], a = ca[t];
             double gc[4];
 #pragma unroll
-            for (int row = 0; row < 4; ++row) gc[row] = FAST ? cg[t][row] : CMPC_SO(r, L.g, s * GS + row * 3 + a);
-            const double rdu = fma(gc[3], sp_ld(xs, X_DX + 4 * s + 3), fma(gc[2], sp_ld(xs, X_DX + 4 * s + 2),
-                                   fma(gc[1], sp_ld(xs, X_DX + 4 * s + 1), gc[0] * sp_ld(xs, X_DX + 4 * s))));
+            for (int row = 0; row < 4; ++row) gc[row] = FAST ? cg[t][row] : sp_ld(sp_at(r, o_gc[t]), row * 3);
+            const ScratchPtr xd = sp_at(xs, o_dx[t]);
+            const double rdu = fma(gc[3], sp_ld(xd, 3), fma(gc[2], sp_ld(xd, 2), fma(gc[1], sp_ld(xd, 1), gc[0] * sp_ld(xd, 0))));
             const int cid = (s < (mt & 7)) ? ((mt >> (4 + 2 * s)) & 3) : 0;
             double wsel = pick3(P.Wu[0], P.Wu[1], P.Wu[2], a);
             if (!FAST) {
@@ -1404,6 +1436,7 @@ CMPC_OP void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
   ks.open(T, I, 0, N + 1, 1);
   Res R;
   R.pri = R.dua = R.npri = R.ndua = 0.0;
+  R.kbad = 0;
   int nchg = 0;
   double x[9];
 #pragma unroll
@@ -1430,9 +1463,13 @@ CMPC_OP void forward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S_
       R.dua = team_max(I, xs, R.dua);
       R.ndua = team_max(I, xs, R.ndua);
     }
-    if (PMMK) nchg = team_sum(I, xs, nchg);
+    if (PMMK) {
+      nchg = team_sum(I, xs, nchg);
+      R.kbad = team_or(I, xs, R.kbad);
+    }
   }
   if (on && commit && (CHK || PMMK)) {
+    if (PMMK) S.kbad |= R.kbad;
     S.pri = R.pri;
     S.npri = fmax(R.npri, S.dynrow);
     if (CHK) {
@@ -1776,6 +1813,7 @@ CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc, int nconv)
   for (int i = 0; i < 9; ++i) S.ye[i] = 0.0;
   S.kap = 0;
   S.fail = 0;
+  S.kbad = 0;
   S.lost = 0;
   S.n_pmm = S.n_polish = 0;
   S.pri = S.dua = S.npri = S.ndua = 0.0;
@@ -1916,6 +1954,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
       // refinement), correct the friction active set, repeat at most 1 + rounds times.
       case PC_AFTER_BUILD:
         ++S.n_polish;
+        S.kbad = 0;
         D.certified = 0;
         D.prev_chg = 1 << 30;
         D.round = 0;
@@ -1935,6 +1974,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
       case PC_AFTER_PMM0:
         ++S.n_pmm;
         D.sw = 0;
+        if (S.kbad) { D.pc = PC_POLISH_END; break; }   // the trust-region branches were guessed wrongly: back to ADMM
         if (D.chg) { D.pc = PC_ROUND_CHECK; break; }   // rows changed: refactor right away
         D.pc = PC_SW_TOP;
         break;
@@ -1948,6 +1988,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         D.pc = PC_ROUND_CHECK;
         break;
       case PC_AFTER_PMM1:
+        if (S.kbad) { D.pc = PC_POLISH_END; break; }
         if (D.chg || S.pri <= P.as_tol * (1.0 + S.npri)) { D.pc = PC_ROUND_CHECK; break; }
         ++D.sw;
         D.pc = PC_SW_TOP;
@@ -1970,7 +2011,7 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         // OSQP's rule for an uncertified polish after normal termination: keep it if it improves
         const double m0 = fmax(D.pri0 / (P.eps_abs + P.eps_rel * D.npri0), D.dua0 / (P.eps_abs + P.eps_rel * D.ndua0));
         const double m1 = S.pri / (P.eps_abs + P.eps_rel * S.npri);
-        if (D.certified || (D.term && !S.fail && m1 < m0)) {
+        if (!S.kbad && (D.certified || (D.term && !S.fail && m1 < m0))) {
           D.solved = 1;
           D.polished = 1;
           S.dua = 0.0;

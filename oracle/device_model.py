@@ -16,8 +16,8 @@ CHECK = 25           # termination test every CHECK iterations (OSQP default) (k
 PER_ROW_FRICTION = True
 RHO0 = 2.0
 ADAPT_START = 200    # early residuals are transient; adapting on them hurts
-AS_START = 20        # first certified-polish attempt after this many ADMM iterations
-AS_STEP = 20         # interval to the next attempt (doubled after every failure)
+AS_START = 8         # first certified-polish attempt after this many ADMM iterations
+AS_STEP = 8          # interval to the next attempt (doubled after every failure)
 AS_ROUNDS = 9        # active-set correction rounds per attempt
 AS_TOL = 1e-9        # certificate tolerance (primal residual / row violation)
 RHO_K_REL = 1.0       # kappa-copy penalty = rho * RHO_K_REL * min(W_kappa)

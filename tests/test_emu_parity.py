@@ -316,7 +316,7 @@ def oracle_backoffs(m):
     return qp_build.friction_backoffs(prob, g, c, m._beta_u)[0]
 
 
-@pytest.mark.parametrize("qp", [None, dict(polish_refine_iter=10, polish_active_set_rounds=19)],
+@pytest.mark.parametrize("qp", [None, dict(polish_refine_iter=10, polish_active_set_rounds=19, active_set_start=20, active_set_step=20)],
                          ids=["library-defaults", "host-stochastic-defaults"])
 @pytest.mark.parametrize("name", ["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
 def test_stochastic_mode_matches_oracle(cases, name, qp):
@@ -371,7 +371,8 @@ def test_emu_matches_stochastic_golden(path):
     batch = ProblemBatch([m])
     gains, covs = E.lqr_covs(batch, batch.X_ref, batch.U_init, m._Q, m._R, m._Cov_w, m._Cov_eta)
     ub = E.friction_backoffs(batch, float(g["xi"]), gains, covs)
-    out = E.solve_scp(batch, conf.scp_params, dict(polish_refine_iter=10, polish_active_set_rounds=19), friction_ub=ub)
+    from centroidal_mpc_b200.device import STOCHASTIC_QP_DEFAULTS
+    out = E.solve_scp(batch, conf.scp_params, STOCHASTIC_QP_DEFAULTS, friction_ub=ub)
     assert out["status"][0] == 0
     check_against_stochastic_golden(g, gains[0], covs[0], ub[0], out["X"][0].T, out["U"][0].T, int(out["scp_iters"][0]))
 
@@ -385,7 +386,8 @@ def test_stochastic_headline_horizon_certifies_at_the_first_attempt():
     sto = batch.proto["stochastic"]
     g, c = E.lqr_covs(batch, batch.X_ref, batch.U_init, sto["Q"], sto["R"], sto["cov_w"], sto["cov_eta"])
     ub = E.friction_backoffs(batch, chance_constraint_xi(sto["beta_u"]), g, c)
-    tuned = E.solve_scp(batch, conf.scp_params, dict(polish_refine_iter=10, polish_active_set_rounds=19), friction_ub=ub)
+    from centroidal_mpc_b200.device import STOCHASTIC_QP_DEFAULTS
+    tuned = E.solve_scp(batch, conf.scp_params, STOCHASTIC_QP_DEFAULTS, friction_ub=ub)
     plain = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
     assert (tuned["status"] == 0).all() and (tuned["qp_iters"] == 20).all() and (tuned["info"][:, 9] == 1).all()
     assert plain["qp_iters"].max() > 20

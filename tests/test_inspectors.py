@@ -19,6 +19,8 @@ def _model(name, N, b=0, stochastic=False, rotate=False):
     conf = synthetic.load_conf(name, N=N)
     m = Centroidal_model(conf, STOCHASTIC_OCP=stochastic, centroidal_traj=synthetic.reference_trajectory(conf, b))
     if rotate:
+        import copy
+        m._contact_trajectory = copy.deepcopy(m._contact_trajectory)   # the poses belong to the shared config module
         c, s = np.cos(0.2), np.sin(0.2)
         Rx = np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
         for contact in m._contact_trajectory:
