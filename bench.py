@@ -325,13 +325,12 @@ def run_gpu_arm(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     # DRAM bytes of one launch from the committed ncu --set full capture of this kernel; the file is stamped
-    # with the hash of the library it was captured with and is ignored for any other build or workload
+    # with the build id (hash of the sources) of the library it was captured with and is ignored for any other
+    # build or workload
     traffic = None
     try:
-        import hashlib
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-        sha = hashlib.sha256(open(L.LIB_PATH, "rb").read()).hexdigest()
-        if traffic.get("lib_sha256") != sha or traffic.get("workload") != "%s N=%d B=%d" % (workload, HORIZON, B):
+        if traffic.get("build_id") != L.load().cmpc_build_id().decode() or traffic.get("workload") != "%s N=%d B=%d" % (workload, HORIZON, B):
             traffic = {"dram_bytes_per_launch": None,
                        "source": "profiles/r2_traffic.json was captured with another build or workload (%s); not used" % traffic.get("workload")}
     except (OSError, ValueError):

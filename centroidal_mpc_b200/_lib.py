@@ -47,7 +47,7 @@ LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
 EXPORTS = ["cmpc_debug_profile", "cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
            "cmpc_set_problem", "cmpc_set_friction_ub", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
            "cmpc_linearize", "cmpc_rollout", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
-           "cmpc_last_error", "cmpc_version"]
+           "cmpc_last_error", "cmpc_version", "cmpc_build_id"]
 
 _lib = None
 
@@ -152,6 +152,7 @@ def load():
     lib.cmpc_launch_count.restype = C.c_int64
     lib.cmpc_last_error.restype = C.c_char_p
     lib.cmpc_version.restype = C.c_char_p
+    lib.cmpc_build_id.restype = C.c_char_p
     _lib = lib
     return lib
 

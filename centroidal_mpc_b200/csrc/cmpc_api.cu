@@ -265,7 +265,11 @@ static const int MAX_CHUNKS = 8;
 extern "C" {
 
 const char* cmpc_last_error(void) { return g_err.c_str(); }
-const char* cmpc_version(void) { return "cmpc_b200 0.1.0 (sm_100a)"; }
+const char* cmpc_version(void) { return "cmpc_b200 0.2.0 (sm_100a)"; }
+#ifndef CMPC_BUILD_ID
+#define CMPC_BUILD_ID "unstamped"
+#endif
+const char* cmpc_build_id(void) { return CMPC_BUILD_ID; }
 int64_t cmpc_launch_count(void) { return g_launches.load(); }
 void cmpc_default_qp_settings(cmpc_qp_settings* s) { default_qp_settings(s); }
 

@@ -52,8 +52,9 @@ constexpr int X_KX = 30;           // kappa terms          [12]  (kl 3 | kM 9)
 constexpr int X_DX = 42;           // friction residual terms of a CHECK sweep [16]
 constexpr int X_RX = 58;           // team reductions of the host lock-step build [NL]
 constexpr int X_COMMON = 58 + 8;
-constexpr int X_CX = X_COMMON;     // factorisation: pivot column, double-buffered [2][21]
-constexpr int X_PS = X_CX + 42;    // P (full square 9 x 9)
+constexpr int X_CXS = 2 * 12 + 9;  // one pivot column: control entries twice (rotated window), state entries
+constexpr int X_CX = X_COMMON;     // factorisation: pivot column, double-buffered [2][X_CXS]
+constexpr int X_PS = X_CX + 2 * X_CXS;   // P (full square 9 x 9)
 constexpr int X_Y = X_PS + 81;     // Y = P [B A]  (9 x (na + 9))
 constexpr int X_FAC_END = X_Y + 9 * 21;
 // shared memory of a tile (in field rows of TL doubles): common scratch, then a region that holds the
@@ -174,7 +175,7 @@ CMPC_HD int team_sum(const Inst& I, ScratchPtr xs, int v) {
   return m;
 }
 #endif
-CMPC_HD int sub_of(const Inst& I) { return NL == 1 ? 0 : I.sub; }
+CMPC_HD int sub_of(const Inst& I) { return NL == 1 ? 0 : (I.sub & (NL - 1)); }   // the mask tells the compiler the range: dead row branches go
 // true when the predicate holds for every instance of the tile (device: the whole warp; host build: the
 // instances of a tile run one after the other, each for itself)
 CMPC_HD bool tile_all(bool v) {
@@ -583,14 +584,14 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
   team_sync(I);
   CMPC_FK(0);
   // ---- phase 2: the lane's tableau rows in registers: control columns by slot, state columns
-  double Tc[RT][NS > 0 ? NS : 1][3], Ts[RT][9];
+  double Tf[RT][NA > 0 ? NA : 1], Ts[RT][9];
 #pragma unroll
   for (int t = 0; t < RT; ++t) {
     const int rr = q + NL * t;
 #pragma unroll
     for (int c = 0; c < 9; ++c) Ts[t][c] = 0.0;
 #pragma unroll
-    for (int e = 0; e < NA; ++e) Tc[t][e / 3][e % 3] = 0.0;
+    for (int e = 0; e < NA; ++e) Tf[t][e] = 0.0;
     if (rr < NA) {   // control row (s, a):  B' (P B)  + R block
       const int s = rr / 3, a = rr - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
       const double dtr = s < nsl ? P.dt : 0.0;
@@ -628,7 +629,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
       for (int e = 0; e < NA; ++e) {
         double v = dtr * fma(sp_ld(xs, X_Y + (6 + a1) * n + e), dA, fma(-sp_ld(xs, X_Y + (6 + a2) * n + e), dB, sp_ld(xs, X_Y + (3 + a) * n + e)));
         if (e / 3 == s) v += radd[e % 3];
-        Tc[t][e / 3][e % 3] = v;
+        Tf[t][e] = v;
       }
     } else if (rr < n) {   // state row i:  Hux' | Q + A'(P A)
       const int i = rr - NA;
@@ -638,7 +639,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
 #pragma unroll
         for (int b2 = 0; b2 < 3; ++b2) {   // Hux[(s,b2)][i]
           const int b1 = nxt3(b2), bp = prv3(b2);
-          Tc[t][s][b2] = dts[s] * fma(sp_ld(xs, X_Y + (6 + b1) * n + NA + i), ds[s][bp],
+          Tf[t][3 * s + b2] = dts[s] * fma(sp_ld(xs, X_Y + (6 + b1) * n + NA + i), ds[s][bp],
                                       fma(-sp_ld(xs, X_Y + (6 + bp) * n + NA + i), ds[s][b1], sp_ld(xs, X_Y + (3 + b2) * n + NA + i)));
         }
       }
@@ -661,64 +662,52 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
     }
   }
   CMPC_FK(1);
-  // ---- phase 3: sweep the control pivots, slot by slot.  The pivot columns of the current slot are always
-  // the first block of the row registers: after its three pivots the blocks are rotated by one (a loop
-  // over the slots with compile-time register indices; after NS rotations the order is the original one).
-  // Per pivot the owners publish their entry of the pivot column (double-buffered), everybody reads the
-  // column -- it is the pivot row as well -- and updates its rows.
+  // ---- phase 3: sweep the control pivots, one per trip of a rolled loop: the body is small enough to stay in
+  // the instruction cache.  The pivot column always sits in register column 0: every trip writes the updated
+  // row back rotated by one column (the values are fresh, so the rotation costs no moves); after na trips the
+  // order is the original one.  Per pivot the owners publish their entry of the pivot column (double-buffered;
+  // the control part twice, back to back, so that the rotated window pv .. pv + na - 1 is contiguous), everybody
+  // reads the column -- it is the pivot row as well -- and updates its rows.
 #pragma unroll 1
-  for (int sc = 0; sc < NS; ++sc) {
+  for (int pv = 0; pv < NA; ++pv) {
+    const int cb = X_CX + (pv & 1) * X_CXS;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int pv = 3 * sc + a;
-      const int cb = X_CX + (pv & 1) * 21;
+    for (int t = 0; t < RT; ++t) {
+      const int rr = q + NL * t;
+      if (rr < n) sp_st(xs, cb + NA + rr, Tf[t][0]);    // control rows: second copy; state rows: 2 na + i
+      if (rr < NA) sp_st(xs, cb + rr, Tf[t][0]);
+    }
+    team_sync(I);
+    const ScratchPtr xw = sp_at(xs, s_off(cb + pv));
+    double c[NA > 0 ? NA : 1], c9[9];
 #pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const int rr = q + NL * t;
-        if (rr < n) sp_st(xs, cb + rr, Tc[t][0][a]);
-      }
-      team_sync(I);
-      double c[NS > 0 ? NS : 1][3], c9[9];
+    for (int j = 0; j < NA; ++j) c[j] = sp_ld(xw, j);
 #pragma unroll
-      for (int sj = 0; sj < NS; ++sj) {
-        const int so = sj + sc >= NS ? sj + sc - NS : sj + sc;   // the slot that sits in block sj now
+    for (int cc = 0; cc < 9; ++cc) c9[cc] = sp_ld(xs, cb + 2 * NA + cc);
+    const double piv = c[0];
+    if (!(piv > 0.0) && on) S.fail = 1;
+    const double ip = 1.0 / piv;
 #pragma unroll
-        for (int aj = 0; aj < 3; ++aj) c[sj][aj] = sp_ld(xs, cb + 3 * so + aj);
-      }
+    for (int t = 0; t < RT; ++t) {
+      const int rr = q + NL * t;
+      const double bc = Tf[t][0] * ip;
+      double nw[NA > 0 ? NA : 1];
+      if (rr == pv) {   // the pivot row: scaled column, -1/pivot on the diagonal
+        nw[0] = -ip;
 #pragma unroll
-      for (int cc = 0; cc < 9; ++cc) c9[cc] = sp_ld(xs, cb + NA + cc);
-      const double piv = c[0][a];
-      if (!(piv > 0.0) && on) S.fail = 1;
-      const double ip = 1.0 / piv;
+        for (int j = 1; j < NA; ++j) nw[j] = c[j] * ip;
+      } else {
+        nw[0] = bc;
 #pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const int rr = q + NL * t;
-        const double bc = Tc[t][0][a] * ip;
-        if (rr == pv) {   // the pivot row: scaled column, -1/pivot on the diagonal
+        for (int j = 1; j < NA; ++j) nw[j] = fma(-bc, c[j], Tf[t][j]);
+        if (NL * t + NL - 1 >= NA) {   // state columns (state rows only)
 #pragma unroll
-          for (int sj = 0; sj < NS; ++sj)
-#pragma unroll
-            for (int aj = 0; aj < 3; ++aj) Tc[t][sj][aj] = (sj == 0 && aj == a) ? -ip : c[sj][aj] * ip;
-        } else {
-#pragma unroll
-          for (int sj = 0; sj < NS; ++sj)
-#pragma unroll
-            for (int aj = 0; aj < 3; ++aj) Tc[t][sj][aj] = (sj == 0 && aj == a) ? bc : fma(-bc, c[sj][aj], Tc[t][sj][aj]);
-          if (NL * t + NL - 1 >= NA) {   // state columns (state rows only)
-#pragma unroll
-            for (int cc = 0; cc < 9; ++cc) Ts[t][cc] = fma(-bc, c9[cc], Ts[t][cc]);
-          }
+          for (int cc = 0; cc < 9; ++cc) Ts[t][cc] = fma(-bc, c9[cc], Ts[t][cc]);
         }
       }
-    }
 #pragma unroll
-    for (int t = 0; t < RT; ++t) {   // rotate the slot blocks
-      const double t0 = Tc[t][0][0], t1 = Tc[t][0][1], t2 = Tc[t][0][2];
-#pragma unroll
-      for (int sj = 0; sj + 1 < NS; ++sj) {
-        Tc[t][sj][0] = Tc[t][sj + 1][0]; Tc[t][sj][1] = Tc[t][sj + 1][1]; Tc[t][sj][2] = Tc[t][sj + 1][2];
-      }
-      Tc[t][NS > 0 ? NS - 1 : 0][0] = t0; Tc[t][NS > 0 ? NS - 1 : 0][1] = t1; Tc[t][NS > 0 ? NS - 1 : 0][2] = t2;
+      for (int j = 0; j + 1 < NA; ++j) Tf[t][j] = nw[j + 1];
+      Tf[t][NA > 0 ? NA - 1 : 0] = nw[0];
     }
   }
   CMPC_FK(2);
@@ -729,7 +718,7 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
     if (rr < n) {
       if (on) {
 #pragma unroll
-        for (int l = 0; l < NA; ++l) CMPC_R(w, L.hn + rr * NAP + l) = Tc[t][l / 3][l % 3];
+        for (int l = 0; l < NA; ++l) CMPC_R(w, L.hn + rr * NAP + l) = Tf[t][l];
       }
       if (rr >= NA) {
         const int i = rr - NA;

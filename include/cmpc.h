@@ -174,6 +174,9 @@ int64_t cmpc_launch_count(void);
 
 const char* cmpc_last_error(void);
 const char* cmpc_version(void);
+/* SHA-256 (first 16 hex digits) of the sources this library was built from, stamped by __graft_entry__.build();
+ * "unstamped" for a hand build.  bench.py matches it against profiles/r2_traffic.json. */
+const char* cmpc_build_id(void);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ if __name__ == "__main__":
     run("solo12_pace", 100, 1024, mode="A")         # config 2: perturbed initial states
     run("solo12_bound", 100, 4096)                  # config 3
     run("bolt", 100, 1024)                          # config 4: 8192 over 8 GPUs = 1024 per GPU
+    run("bolt", 100, 8192)                          # ... and the whole batch on one GPU
     run("solo12_trot", 100, 4096, stochastic=True)  # stochastic mode: friction rows with chance-constraint back-offs
     run("solo12_bound", 100, 4096, stochastic=True)
     for B in (256, 1024, 4096, 16384, 65536):       # config 5's batch sweep, on the solo12 trot problem

@@ -11,7 +11,13 @@ from centroidal_mpc_b200.device import BatchSolver
 name = sys.argv[1] if len(sys.argv) > 1 else "solo12_trot"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 conf = synthetic.load_conf(name, N=100)
-solver = BatchSolver(synthetic.make_batch(conf, B))
+batch = synthetic.make_batch(conf, B)
+if os.environ.get("CMPC_SAME"):      # every instance a copy of instance CMPC_SAME: all tiles run the same op sequence
+    j = int(os.environ["CMPC_SAME"])
+    for nm in ("x_init", "x_final", "X_ref", "U_init"):
+        a = getattr(batch, nm)
+        a[:] = a[j:j + 1]
+solver = BatchSolver(batch)
 lib = L.load()
 out = (C.c_double * 32)()
 for _ in range(2):
