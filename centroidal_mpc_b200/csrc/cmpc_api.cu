@@ -126,6 +126,11 @@ cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batc
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  if (!queue) {   // wave launch: one tile per CTA, every warp of the chip starts the same code together
+    const int tile = tile0 + (int)blockIdx.x;
+    if (tile < tiles) run_tile<FAST>(prm, bt, tile, T, nst_s);
+    return;
+  }
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = tile0 + atomicAdd(queue, 1);
@@ -382,19 +387,39 @@ static int launch_tiles(cmpc_handle h, const Batch& bt_in, const cmpc_model* mod
   bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = (int*)scp_iters; bt.status = (int*)status;
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
-  CUDA_TRY(cudaMemsetAsync(h->queue + slot, 0, sizeof(int), st));
   const long smem = scp_smem_bytes(h->dims.N, !prm.fast);
   if (smem > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
   int per_sm = (int)(h->smem_sm / (smem + 1024));   // 1 KB per block is reserved by the driver
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;                        // registers: __launch_bounds__(32, 8)
-  int blocks = tile1 - tile0;
   const int cap = h->num_sms * per_sm;
-  if (blocks > cap) blocks = cap;
-  if (prm.fast) cmpc_scp_kernel<true><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
-  else cmpc_scp_kernel<false><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
-  g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
+  // Waves: the tiles go out in back-to-back launches of at most one resident set (cap CTAs, one tile each).
+  // The solver's code (0.77 MB, of which a knot loop touches 15-30 KB) is far larger than the 32 KB
+  // instruction cache of an SM; warps that start together run the same operations at about the same time
+  // and share the fetched lines.  A persistent grid pulling tiles from a queue lets the warps drift apart:
+  // measured on B200 at 16384 instances, 37 x more instruction-cache misses (ncu gcc__cache_requests_type_
+  // instruction_lookup_miss), 10 instead of 2 no_instruction stall cycles per issue and 62 ms instead of
+  // 4 x 9.3 ms (profiles/r2_icache.md).  CMPC_PERSISTENT=1 selects the queue (for that comparison).
+  static const bool persistent = [] { const char* e = getenv("CMPC_PERSISTENT"); return e && e[0] == '1'; }();
+  const int total = tile1 - tile0;
+  if (persistent) {
+    CUDA_TRY(cudaMemsetAsync(h->queue + slot, 0, sizeof(int), st));
+    const int blocks = total > cap ? cap : total;
+    if (prm.fast) cmpc_scp_kernel<true><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
+    else cmpc_scp_kernel<false><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  const int waves = (total + cap - 1) / cap;
+  const int per = (total + waves - 1) / waves;       // equal waves: no short last one
+  for (int w0 = tile0; w0 < tile1; w0 += per) {
+    const int w1 = w0 + per < tile1 ? w0 + per : tile1;
+    if (prm.fast) cmpc_scp_kernel<true><<<w1 - w0, THREADS, smem, st>>>(prm, bt, nullptr, w0, w1);
+    else cmpc_scp_kernel<false><<<w1 - w0, THREADS, smem, st>>>(prm, bt, nullptr, w0, w1);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+  }
   return 0;
 }
 
