@@ -8,7 +8,7 @@ A "step" is one batched solve_scp over a synthetic batch: solo12 trot, horizon N
 independent MPC instances per GPU (weak scaling; instances are independent, so ranks share
 nothing on the solve path and one gather collects the solutions; the gather of step i runs on a side
 stream under the solve of step i+1).  Other BASELINE.json configurations:
-  --workload {solo12_trot,solo12_pace,solo12_bound,bolt}  --mode {A,B}  --batch B  --scaling {weak,strong}
+  --workload {solo12_trot,solo12_pace,solo12_bound,bolt,talos}  --mode {A,B}  --batch B  --scaling {weak,strong}
 (strong: --batch is the GLOBAL batch, split contiguously over the ranks; e.g. the bolt configuration is
 --workload bolt --batch 8192 --scaling strong --gpus 8, the pace one --workload solo12_pace --mode A --batch 1024).
 
@@ -171,11 +171,15 @@ def algorithmic_work(batch, stats):
     because a neighbouring lane needs another polish round is not algorithmic and is not counted."""
     import numpy as np
     ns = batch.contact_active[0].sum(axis=1).astype(float)   # active contacts per knot (shared plan)
+    wrench = getattr(batch, "wrench", False)
+    if wrench:
+        ns = 2 * ns                                            # a foot is a force slot and a wrench slot
     na = 3 * ns
     N = batch.N
     # record ranges of csrc/cmpc_core.cuh (lay_of) / cmpc_tile.cuh (ranges_of): A Pc[9]; M Hn[na*na] + Kt[9 na];
     # C meta + xbar + S + ck + d; D vk + vf; E dv; F yk + yf
-    segA, segHn, segKt, segC, segD, segE, segF = 9 + 0 * na, na * na, 9 * na, 16 + na, 3 + 4 * ns, na, 4 + 4 * ns
+    gen = 20 * ns if (wrench or batch.contact_R is not None) else 0 * ns   # general friction table (frames / CoP box)
+    segA, segHn, segKt, segC, segD, segE, segF = 9 + 0 * na, na * na, 9 * na, 16 + (3 if wrench else 1) * na + gen, 3 + 4 * ns, na, 4 + 4 * ns
     term = 9 + 16 + 3                                         # terminal knot: Pc slot + stage data + kappa copy
     bwd_admm = (segA + segHn + segKt + segC + segD + na).sum() + term          # [A .. D] + writes d_k
     fwd_admm = (segKt + segC + segD + segE + 3 + 4 * ns).sum() + term + 3      # [Kt .. E] + writes vk, vf
@@ -226,7 +230,9 @@ def run_gpu_arm(args):
     else:                          # weak scaling: every rank owns --batch instances; instance ids are global
         B, first, Bglobal = args.batch, rank * args.batch, args.batch * world
     batch = synthetic.make_batch(conf, B, mode=args.mode, first=first)
-    for name in ("x_init", "x_final", "X_ref", "U_init", "contact_pos", "contact_active"):
+    for name in ("x_init", "x_final", "X_ref", "U_init", "contact_pos", "contact_active", "contact_R"):
+        if getattr(batch, name) is None:
+            continue
         t = torch.from_numpy(getattr(batch, name)).pin_memory()
         setattr(batch, name, t.numpy())
         batch.__dict__.setdefault("_pinned", []).append(t)
@@ -393,7 +399,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU (weak) or in total (strong)")
-    ap.add_argument("--workload", default=WORKLOAD, choices=["solo12_trot", "solo12_pace", "solo12_bound", "bolt"])
+    ap.add_argument("--workload", default=WORKLOAD, choices=["solo12_trot", "solo12_pace", "solo12_bound", "bolt", "talos"])
     ap.add_argument("--mode", default="B", choices=["A", "B"], help="B: independent references; A: perturbed initial states")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

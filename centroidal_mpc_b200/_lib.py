@@ -9,13 +9,21 @@ LIB_PATH = os.environ.get("CMPC_B200_LIB") or os.path.join(_HERE, "csrc", "libcm
 
 
 class cmpc_dims(C.Structure):
-    _fields_ = [("batch", C.c_int32), ("N", C.c_int32), ("nc", C.c_int32), ("shared_plan", C.c_int32)]
+    _fields_ = [("batch", C.c_int32), ("N", C.c_int32), ("nc", C.c_int32), ("shared_plan", C.c_int32),
+                ("contact_model", C.c_int32)]   # 0 point contacts, 1 CoP / wrench (TALOS)
+
+
+CONTACT_POINT, CONTACT_WRENCH = 0, 1
+
+
+def contact_model_of(robot):
+    return CONTACT_WRENCH if robot == "TALOS" else CONTACT_POINT
 
 
 class cmpc_model(C.Structure):
     _fields_ = [("robot_mass", C.c_double), ("gravity_constant", C.c_double), ("dt", C.c_double),
                 ("mu", C.c_double), ("state_cost_weights", C.c_double * 9),
-                ("control_cost_weights", C.c_double * 12)]
+                ("control_cost_weights", C.c_double * 12), ("foot_range", C.c_double * 4)]
 
 
 class cmpc_scp_params(C.Structure):
@@ -46,7 +54,7 @@ LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
 
 EXPORTS = ["cmpc_debug_profile", "cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
            "cmpc_set_problem", "cmpc_set_friction_ub", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
-           "cmpc_linearize", "cmpc_rollout", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
+           "cmpc_linearize", "cmpc_rollout", "cmpc_linearize_wrench", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
            "cmpc_last_error", "cmpc_version", "cmpc_build_id"]
 
 _lib = None
@@ -70,6 +78,10 @@ def make_model_struct(prob):
         m.state_cost_weights[i] = wx[i]
     for i in range(12):
         m.control_cost_weights[i] = wu[i] if i < len(wu) else 1.0
+    if prob["robot"] == "TALOS":   # conf.robot_foot_range: -x[1] <= cop_x <= x[0], -y[1] <= cop_y <= y[0]
+        fr = prob["foot_range"]
+        m.foot_range[0], m.foot_range[1] = float(fr["x"][0]), float(fr["x"][1])
+        m.foot_range[2], m.foot_range[3] = float(fr["y"][0]), float(fr["y"][1])
     return m
 
 
@@ -144,6 +156,7 @@ def load():
     lib.cmpc_get_stats.argtypes = [C.c_void_p, ip, ip, dp, vp]
     lib.cmpc_linearize.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, dp, dp, vp]
     lib.cmpc_rollout.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, ip, dp, vp]
+    lib.cmpc_linearize_wrench.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, dp, ip, dp, dp, dp, vp]
     lib.cmpc_lqr_covs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.POINTER(cmpc_lqr_weights),
                                   dp, dp, dp, ip, dp, dp, vp, vp]
     lib.cmpc_friction_backoffs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.c_double,

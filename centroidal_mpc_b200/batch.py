@@ -13,12 +13,16 @@ class ProblemBatch:
         if not probs:
             raise ValueError("empty batch")
         p0 = probs[0]
-        if p0["robot"] == "TALOS":
-            raise NotImplementedError("the TALOS CoP/wrench contact model is SURVEY.md section 8 row f4 (next)")
         self.B = len(probs)
         self.N = int(p0["N"])
         self.nc = int(p0["contact_active"].shape[1])
-        self.nu = 3 * self.nc
+        # TALOS: flat feet, six controls (cop_x, cop_y, fx, fy, fz, tau_z) per foot -- the wrench contact model
+        self.wrench = p0["robot"] == "TALOS"
+        if self.wrench and self.nc > 2:
+            raise ValueError("the wrench contact model takes at most two feet")
+        if self.wrench and p0.get("stochastic") is not None:
+            raise NotImplementedError("STOCHASTIC_OCP is not available for the wrench contact model")
+        self.nu = (6 if self.wrench else 3) * self.nc
         self.proto = p0
         for p in probs[1:]:
             if int(p["N"]) != self.N or p["contact_active"].shape[1] != self.nc:
@@ -51,7 +55,7 @@ class ProblemBatch:
         self.contact_active = np.ascontiguousarray(np.stack([p["contact_active"] for p in plan]), dtype=np.int32)
         R = np.stack([p["contact_R"] for p in plan]).astype(f64)
         eye = np.eye(3)[None, None, None] * self.contact_active[..., None, None]
-        self.identity_R = bool(np.array_equal(R, eye))
+        self.identity_R = bool(np.array_equal(R, eye)) and not self.wrench   # the wrench model always reads the frames
         self.contact_R = None if self.identity_R else np.ascontiguousarray(R)
 
     @classmethod

@@ -17,10 +17,12 @@ BOLT_MASS = 1.3
 BOLT_COM_HEIGHT = 0.35
 BOLT_FEET = {"FL_ANKLE": (0.0, 0.065, 0.0), "FR_ANKLE": (0.0, -0.065, 0.0)}
 
-# talos legs: two flat feet
+# talos legs: two flat feet.  The reference gives this robot NO tracking gradient (scp_solver.py:13-20), so
+# its state cost is 1/2 x' W x about the world origin: the synthetic config puts the origin at the nominal
+# CoM (soles 0.88 m below it), which makes that cost a regulariser about the nominal posture
 TALOS_MASS = 90.0
-TALOS_COM_HEIGHT = 0.88
-TALOS_FEET = {"left_sole_link": (0.0, 0.085, 0.0), "right_sole_link": (0.0, -0.085, 0.0)}
+TALOS_COM_HEIGHT = 0.0
+TALOS_FEET = {"left_sole_link": (0.0, 0.085, -0.88), "right_sole_link": (0.0, -0.085, -0.88)}
 
 
 def solo12():

@@ -7,11 +7,21 @@
 #include <atomic>
 #include <string>
 
-#include "cmpc_params.h"
-#include "cmpc_tile.cuh"
+#include "cmpc_launch.cuh"
 #include "cmpc_lqr.cuh"
 
 using namespace cmpc;
+
+// the second compilation of the solver (cmpc_wrench.cu): CoP / wrench contact model
+struct WrSizes { long tiles, ws, nst, info, smem; };
+int cmpc_wr_sizes(int B, int N, int feet, WrSizes* out);
+int cmpc_wr_set_smem_limit(int smem_optin);
+int cmpc_wr_launch_scp(const cmpc_dims* dims, const cmpc_model* model, const cmpc_scp_params* scp, const cmpc_qp_settings* qp,
+                       const void* batch, size_t batch_bytes, const void* cfg, int tile0, int tile1, cudaStream_t st,
+                       std::string* msg, long long* n_launches);
+int cmpc_wr_linearize(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U, const double* contact_pos,
+                      const double* contact_R, const int32_t* contact_active, double* f, double* fx, double* fu, cudaStream_t st,
+                      std::string* msg);
 
 namespace {
 
@@ -27,119 +37,6 @@ int fail(int code, const std::string& msg) {
     cudaError_t e_ = (expr);                                                                   \
     if (e_ != cudaSuccess) return fail(-100 - (int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
-
-// ------------------------------------------------------------------------------------------
-// The SCP kernel: one warp per tile of TL = 32 / NL instances, NL lanes per instance (cmpc_core.cuh),
-// persistent over a queue of tiles; a CTA is one warp, several CTAs share an SM.  Each instance runs
-// the driver state machine (cmpc_tile.cuh: advance(), replicated in the lanes of its team); the warp
-// executes one whole-horizon operation at a time for the instances that asked for it, lowest operation
-// code first, so that instances that are ahead wait at the later operations (evaluate, write) and the
-// tile does those together.  Warps never synchronise with each other.
-// ------------------------------------------------------------------------------------------
-constexpr int THREADS = 32;
-constexpr int BAR_BYTES = 128;  // 4 mbarriers ("full" per ring slot), then the byte-range table of the open stream (5 x 16 bytes)
-inline long scp_smem_bytes(int N, bool gen) { return (long)tile_smem_fields(gen) * TL * 8 + BAR_BYTES + ((N + 1 + 15) & ~15); }
-
-#if defined(CMPC_PROFILE)
-// profiling build: cycles per operation kind summed over all warps (lane 0 of each warp)
-// [0..9] per Op code (sweeps: whole op), [10] backward part of ADMM sweeps, [11] of PMM sweeps,
-// [12] setup, [13] whole tile, [14] cycles waiting for bulk copies, [15] number of waits
-__device__ unsigned long long g_prof[32];
-#endif
-
-template <bool FAST>
-__device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& T, unsigned char* nst_s) {
-  const int lane = (int)(threadIdx.x & 31u);
-  const int t = lane & (TL - 1), q = lane / TL;
-  bind_tile(T, prm, bt, tile);
-#if defined(CMPC_PROFILE)
-  long long prof[32];
-  for (int i = 0; i < 32; ++i) prof[i] = 0;
-  T.prof = prof;
-  const long long tile_t0 = clock64();
-#endif
-  const int b = tile * TL + t;
-  const bool live = b < bt.B;
-  Inst I;
-  Sv S;
-  Drv D;
-  D.check = D.upd = 0;
-  bind_instance(I, prm, bt, live ? b : bt.B - 1);   // lanes past the batch run along on a valid instance, without writing
-  I.lane = t;
-  I.sub = q;
-  for (int k0 = 0; k0 <= prm.N; k0 += NL) {   // slots per knot of the tile: the record layout of the knot
-    const int k = k0 + q;
-    int ns = (live && k < prm.N) ? active_slots(prm, I, k) : 0;
-#pragma unroll
-    for (int m = 1; m < TL; m <<= 1) ns = max(ns, __shfl_xor_sync(0xffffffffu, ns, m));
-    if (t == 0 && k <= prm.N) { T.nst[k] = ns; nst_s[k] = (unsigned char)ns; }
-  }
-  __syncwarp();
-  {
-    double mq = 0.0, mc = 0.0;
-    int nconv = 0;
-    setup_knots(prm, T, I, live, &mq, &mc, &nconv);
-    setup_finish(I, S, mq, mc, nconv);
-  }
-  __syncwarp();
-#if defined(CMPC_PROFILE)
-  prof[12] += clock64() - tile_t0;
-#endif
-  int op = OP_DONE;
-  if (live) {
-    drv_init(prm, S, D);
-    op = advance(prm, S, D);
-  }
-  for (;;) {
-    const int sel = __reduce_min_sync(0xffffffffu, op);
-    if (sel == OP_DONE) break;
-    const bool on = op == sel;
-    const bool anycheck = __any_sync(0xffffffffu, on && D.check);
-    execute<FAST>(sel, prm, T, I, bt, S, D, on, anycheck);
-    if (on) op = advance(prm, S, D);
-    __syncwarp();
-  }
-  if (live) write_stats(bt, I, S, D);
-#if defined(CMPC_PROFILE)
-  prof[13] += clock64() - tile_t0;
-  if (lane == 0)
-    for (int i = 0; i < 32; ++i) atomicAdd(&g_prof[i], (unsigned long long)prof[i]);
-#endif
-}
-
-template <bool FAST>
-__global__ void __launch_bounds__(THREADS, 8)
-cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tile0,
-                int tiles) {   // this launch solves the tiles [tile0, tiles), pulled from its own queue counter
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const unsigned lane = threadIdx.x & 31u;
-  constexpr long SCR_BYTES = (long)tile_smem_fields(!FAST) * TL * 8;
-  TileCtx T;
-  T.smem_sa = smem_addr(smem_raw);
-  T.bars_sa = T.smem_sa + (unsigned)SCR_BYTES;
-  T.phases = 0;
-  unsigned char* nst_s = smem_raw + SCR_BYTES + BAR_BYTES;
-  T.nst_sa = smem_addr(nst_s);
-  if (lane == 0) {
-    for (int d = 0; d < 4; ++d)   // "full" barriers of the ring slots (bulk-copy completion)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(T.bars_sa + 8u * d) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  if (!queue) {   // wave launch: one tile per CTA, every warp of the chip starts the same code together
-    const int tile = tile0 + (int)blockIdx.x;
-    if (tile < tiles) run_tile<FAST>(prm, bt, tile, T, nst_s);
-    return;
-  }
-  for (;;) {
-    int tile = 0;
-    if (lane == 0) tile = tile0 + atomicAdd(queue, 1);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= tiles) break;
-    run_tile<FAST>(prm, bt, tile, T, nst_s);
-    __syncwarp();
-  }
-}
 
 // compute_trajectory_data / integrate_dynamics_trajectory (one thread per instance and knot)
 __global__ void cmpc_linearize_kernel(const __grid_constant__ Params prm, int B, int shared_plan,
@@ -295,6 +192,9 @@ static int create_fail(cmpc_handle h, int code, const std::string& msg) {
 int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   if (!dims || !out) return fail(-1, "null argument");
   if (dims->N < 1 || dims->nc < 1 || dims->nc > MAXC || dims->batch < 1) return fail(-1, "bad dims");
+  const bool wrench = dims->contact_model == CMPC_CONTACT_WRENCH;
+  if (dims->contact_model != CMPC_CONTACT_POINT && !wrench) return fail(-1, "unknown contact model");
+  if (wrench && 2 * dims->nc > MAXC) return fail(-1, "the wrench contact model takes at most two feet");
   cmpc_handle h = (cmpc_handle)calloc(1, sizeof(cmpc_handle_s));
   if (!h) return fail(-1, "out of host memory");
   h->dims = *dims;
@@ -302,6 +202,13 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   CREATE_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   const int B = dims->batch, N = dims->N;
   WsSizes w = ws_sizes(B, N, dims->nc);
+  long smem_need = scp_smem_bytes(N, true);
+  if (wrench) {
+    WrSizes z;
+    cmpc_wr_sizes(B, N, dims->nc, &z);
+    w.tiles = z.tiles; w.ws = z.ws; w.nst = z.nst; w.info = z.info;
+    smem_need = z.smem;
+  }
   const long nd = w.ws + w.info;
   const long ni = w.nst + 3L * B + 64;
   h->ws_bytes = nd * 8 + ni * 4;
@@ -321,11 +228,11 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
   CREATE_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
   h->smem_max = smem_optin;
   h->smem_sm = smem_sm;
-  if (scp_smem_bytes(N, true) > h->smem_max) return create_fail(h, -3, "horizon too long for the shared-memory slot table");
+  if (smem_need > h->smem_max) return create_fail(h, -3, "horizon too long for the shared-memory slot table");
   // the attribute is per function and device: always the device maximum, so that handles with different
   // horizons can be alive at the same time
-  CREATE_TRY(cudaFuncSetAttribute(cmpc_scp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-  CREATE_TRY(cudaFuncSetAttribute(cmpc_scp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CREATE_TRY(set_scp_smem_limit(smem_optin));
+  if (wrench) CREATE_TRY((cudaError_t)cmpc_wr_set_smem_limit(smem_optin));
   h->bt.B = B;
   h->bt.plan_stride = dims->shared_plan ? 0 : 1;
   *out = h;
@@ -353,6 +260,7 @@ int cmpc_set_problem(cmpc_handle h, const cmpc_model* model, const double* x_ini
                      const double* contact_R, const int32_t* contact_active) {
   if (!h || !model || !x_init || !x_final || !X_ref || !U_init || !contact_pos || !contact_active)
     return fail(-1, "null argument");
+  if (h->dims.contact_model == CMPC_CONTACT_WRENCH && !contact_R) return fail(-1, "the wrench contact model needs contact_R");
   h->model = *model;
   h->bt.x_init = x_init; h->bt.x_final = x_final; h->bt.X_ref = X_ref; h->bt.U_init = U_init;
   h->bt.cpos = contact_pos; h->bt.cR = contact_R; h->bt.cact = (const int*)contact_active;
@@ -362,65 +270,28 @@ int cmpc_set_problem(cmpc_handle h, const cmpc_model* model, const double* x_ini
 
 int cmpc_set_friction_ub(cmpc_handle h, const double* friction_ub) {
   if (!h) return fail(-1, "null argument");
+  if (friction_ub && h->dims.contact_model == CMPC_CONTACT_WRENCH) return fail(-1, "friction back-offs are not available for the wrench contact model");
   h->bt.fub = friction_ub;
   return 0;
 }
 
-// launches the solver for the tiles [tile0, tile1) of the batch `bt_in` on `st`; `slot` picks the queue counter
+// launches the solver for the tiles [tile0, tile1) of the batch `bt_in` on `st` (cmpc_launch.cuh); the wrench
+// contact model runs the second compilation of the solver (cmpc_wrench.cu)
 static int launch_tiles(cmpc_handle h, const Batch& bt_in, const cmpc_model* model, const cmpc_scp_params* scp,
                         const cmpc_qp_settings* qp, double* X_out, double* U_out, int32_t* scp_iters, int32_t* status,
                         int32_t* n_accepted, int tile0, int tile1, int slot, cudaStream_t st) {
-  Params prm;
-  cmpc_qp_settings dq;
-  if (!qp && bt_in.fub) {   // upper bounds on the friction rows (stochastic mode): the polish needs more
-    default_qp_settings(&dq);   // multiplier sweeps and active-set rounds to certify
-    dq.polish_refine_iter = 10;
-    dq.polish_active_set_rounds = 19;
-    dq.active_set_start = dq.active_set_step = 20;   // the back-offs need a better first guess of the active set
-    qp = &dq;
-  }
-  int rc = fill_params(&prm, &h->dims, model, scp, qp, bt_in.cR == nullptr);
-  if (rc) return fail(rc, rc == -2 ? "cost weights must be positive" : "bad dims");
   Batch bt = bt_in;
-  if (bt.fub) prm.fast = 0;   // upper bounds live in the general friction table
-  bt.rfields = rec_fields(h->dims.nc, !prm.fast);
   bt.X_out = X_out; bt.U_out = U_out; bt.scp_iters = (int*)scp_iters; bt.status = (int*)status;
   bt.n_accepted = n_accepted ? (int*)n_accepted : h->d_nacc;
   bt.qp_iters = h->d_qpit; bt.n_factor = h->d_nfac;
-  const long smem = scp_smem_bytes(h->dims.N, !prm.fast);
-  if (smem > h->smem_max) return fail(-3, "horizon too long for the shared-memory slot table");
-  int per_sm = (int)(h->smem_sm / (smem + 1024));   // 1 KB per block is reserved by the driver
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;                        // registers: __launch_bounds__(32, 8)
-  const int cap = h->num_sms * per_sm;
-  // Waves: the tiles go out in back-to-back launches of at most one resident set (cap CTAs, one tile each).
-  // The solver's code (0.77 MB, of which a knot loop touches 15-30 KB) is far larger than the 32 KB
-  // instruction cache of an SM; warps that start together run the same operations at about the same time
-  // and share the fetched lines.  A persistent grid pulling tiles from a queue lets the warps drift apart:
-  // measured on B200 at 16384 instances, 37 x more instruction-cache misses (ncu gcc__cache_requests_type_
-  // instruction_lookup_miss), 10 instead of 2 no_instruction stall cycles per issue and 62 ms instead of
-  // 4 x 9.3 ms (profiles/r2_icache.md).  CMPC_PERSISTENT=1 selects the queue (for that comparison).
-  static const bool persistent = [] { const char* e = getenv("CMPC_PERSISTENT"); return e && e[0] == '1'; }();
-  const int total = tile1 - tile0;
-  if (persistent) {
-    CUDA_TRY(cudaMemsetAsync(h->queue + slot, 0, sizeof(int), st));
-    const int blocks = total > cap ? cap : total;
-    if (prm.fast) cmpc_scp_kernel<true><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
-    else cmpc_scp_kernel<false><<<blocks, THREADS, smem, st>>>(prm, bt, h->queue + slot, tile0, tile1);
-    g_launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-  }
-  const int waves = (total + cap - 1) / cap;
-  const int per = (total + waves - 1) / waves;       // equal waves: no short last one
-  for (int w0 = tile0; w0 < tile1; w0 += per) {
-    const int w1 = w0 + per < tile1 ? w0 + per : tile1;
-    if (prm.fast) cmpc_scp_kernel<true><<<w1 - w0, THREADS, smem, st>>>(prm, bt, nullptr, w0, w1);
-    else cmpc_scp_kernel<false><<<w1 - w0, THREADS, smem, st>>>(prm, bt, nullptr, w0, w1);
-    g_launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
-  }
-  return 0;
+  LaunchCfg cfg{h->num_sms, h->smem_sm, h->smem_max, h->queue + slot};
+  std::string msg;
+  long long nl = 0;
+  const int rc = h->dims.contact_model == CMPC_CONTACT_WRENCH
+                     ? cmpc_wr_launch_scp(&h->dims, model, scp, qp, &bt, sizeof(Batch), &cfg, tile0, tile1, st, &msg, &nl)
+                     : launch_scp(&h->dims, model, scp, qp, bt, cfg, tile0, tile1, st, &msg, &nl);
+  g_launches.fetch_add(nl);
+  return rc ? fail(rc, msg) : 0;
 }
 
 int cmpc_solve_scp(cmpc_handle h, const cmpc_scp_params* scp, const cmpc_qp_settings* qp, double* X_out,
@@ -450,7 +321,9 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   if (!h || !model || !scp) return fail(-1, "null argument");
   if (!x_init || !x_final || !X_ref || !U_init || !contact_pos || !contact_active || !X_out || !U_out || !scp_iters || !status)
     return fail(-1, "null argument");
-  const int B = h->dims.batch, N = h->dims.N, nc = h->dims.nc, nu = 3 * nc;
+  const bool wrench = h->dims.contact_model == CMPC_CONTACT_WRENCH;   // nc feet, six controls each
+  if (wrench && !contact_R) return fail(-1, "the wrench contact model needs contact_R");
+  const int B = h->dims.batch, N = h->dims.N, nc = h->dims.nc, nu = (wrench ? 6 : 3) * nc;
   const long Bp = h->dims.shared_plan ? 1 : B;
   const long n_xi = (long)B * 9, n_X = (long)B * (N + 1) * 9, n_U = (long)B * N * nu;
   const long n_cp = Bp * N * nc * 3, n_cR = contact_R ? Bp * N * nc * 9 : 0, n_ca = Bp * N * nc;
@@ -505,7 +378,9 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
     return true;
   };
   void *mX = nullptr, *mU = nullptr, *mi = nullptr, *ms = nullptr, *mn = nullptr;
-  const bool zero_copy = mapped(X_out, &mX) && mapped(U_out, &mU) && mapped(scp_iters, &mi) && mapped(status, &ms) &&
+  static const int env_zc = [] { const char* e = getenv("CMPC_HOST_ZEROCOPY"); return e ? atoi(e) : 1; }();
+  static const int env_chunks = [] { const char* e = getenv("CMPC_HOST_CHUNKS"); return e ? atoi(e) : 0; }();
+  const bool zero_copy = env_zc && mapped(X_out, &mX) && mapped(U_out, &mU) && mapped(scp_iters, &mi) && mapped(status, &ms) &&
                          (!n_accepted || mapped(n_accepted, &mn));
   if (zero_copy) {
     oX = (double*)mX; oU = (double*)mU; oit = (int*)mi; ost = (int*)ms; ona = n_accepted ? (int*)mn : oi + 2 * B;
@@ -514,6 +389,7 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   // results of chunk c-1 downloaded) while chunk c is being solved.
   const int tiles = h->tiles;
   int chunks = tiles >= 4 * MAX_CHUNKS ? MAX_CHUNKS : (tiles >= 8 ? 4 : 1);
+  if (env_chunks >= 1 && env_chunks <= MAX_CHUNKS && env_chunks <= tiles) chunks = env_chunks;
   const int per = (tiles + chunks - 1) / chunks;
   int rc = 0;
   for (int c = 0; c < chunks; ++c) {
@@ -542,6 +418,7 @@ static int lin_common(const cmpc_dims* dims, const cmpc_model* model, const doub
                       const double* contact_pos, const int32_t* contact_active, double* f, double* fx,
                       double* fu, void* stream) {
   if (!dims || !model || !X || !U || !contact_pos || !contact_active || !f) return fail(-1, "null argument");
+  if (dims->contact_model != CMPC_CONTACT_POINT) return fail(-1, "point-contact entry: use cmpc_linearize_wrench for the wrench model");
   Params prm;
   int rc = fill_params(&prm, dims, model, nullptr, nullptr, 1);
   if (rc) return fail(rc, "bad dims or weights");
@@ -565,6 +442,18 @@ int cmpc_linearize(const cmpc_dims* dims, const cmpc_model* model, const double*
 int cmpc_rollout(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,
                  const double* contact_pos, const int32_t* contact_active, double* f, void* stream) {
   return lin_common(dims, model, X, U, contact_pos, contact_active, f, nullptr, nullptr, stream);
+}
+
+int cmpc_linearize_wrench(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,
+                          const double* contact_pos, const double* contact_R, const int32_t* contact_active, double* f,
+                          double* fx, double* fu, void* stream) {
+  if (!dims || !model || !X || !U || !contact_pos || !contact_R || !contact_active || !f) return fail(-1, "null argument");
+  if (dims->contact_model != CMPC_CONTACT_WRENCH) return fail(-1, "cmpc_linearize_wrench needs dims.contact_model = CMPC_CONTACT_WRENCH");
+  if ((fx == nullptr) != (fu == nullptr)) return fail(-1, "fx and fu go together");
+  std::string msg;
+  const int rc = cmpc_wr_linearize(dims, model, X, U, contact_pos, contact_R, contact_active, f, fx, fu, (cudaStream_t)stream, &msg);
+  g_launches.fetch_add(1);
+  return rc ? fail(rc, msg) : 0;
 }
 
 int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X,

@@ -33,8 +33,19 @@
 
 namespace cmpc {
 
+// Contact model of this compilation of the solver.  0: point contacts, three controls (fx, fy, fz) per
+// contact (solo12, bolt).  1 (cmpc_wrench.cu, namespace cmpc_wr): flat feet with six controls
+// (cop_x, cop_y, fx, fy, fz, tau_z) per foot (TALOS, centroidal_model.py:204-208).  A foot is carried as TWO
+// slots of three controls: a force slot (fx, fy, fz) whose lever arm is p + R[:,0:2] cop_bar - c_bar, and a
+// wrench slot (cop_x, cop_y, tau_z) that acts on the angular momentum only; the CoP box (constraints.py:
+// 111-145) takes the place of the wrench slot's four "friction" rows.  "Contact" c of the solver is then
+// the pseudo-contact 2 foot + kind.
+#ifndef CMPC_WRENCH
+#define CMPC_WRENCH 0
+#endif
+constexpr bool WR = CMPC_WRENCH != 0;
 constexpr int NX = 9;
-constexpr int MAXC = 4;    // contacts
+constexpr int MAXC = 4;    // contacts (wrench model: two feet = four pseudo-contacts)
 constexpr int MAXU = 12;   // 3 * MAXC
 // Execution model: NL lanes of a warp cooperate on one MPC instance (each lane owns rows of the
 // knot's small dense systems; vectors that every lane needs are exchanged through shared memory
@@ -89,7 +100,7 @@ CMPC_CX Lay lay_of(int ns, bool gen) {
   L.s = L.xb + 9;             // S[3]: sum of active fbar, A_k = I + dt[[0,I/m,0],[0,0,0],[[S]x,0,0]]
   L.ck = L.s + 3;             // ck[3]: affine term rows 6..8, -dt S x cbar (row 5 is dt m g)
   L.d = L.ck + 3;             // d[slot][3] = p_contact - cbar: B_k[:,3s:3s+3] = dt [0; I; [d]x]
-  L.g = L.d + L.na;
+  L.g = L.d + (WR ? 3 : 1) * L.na;   // wrench model: M[slot][9], kappa rows of B_k[:, slot] = dt M (column a at 3a)
   L.vk = L.g + (gen ? 20 * ns : 0);   // vk[3]: kappa copy, w = prox(v), y = rho_k (v - w)
   L.vf = L.vk + 3;            // vf[4*slot+row]: friction rows, w = min(v,0), y = rho e2 max(v,0)
   L.dv = L.vf + 4 * ns;
@@ -112,6 +123,9 @@ struct Params {
   double m, g, dt, mu, kf, dt_m, dtmg;
   double Wx[NX], Wu[MAXU];
   double e2[4];                       // fast path: friction-row equilibration factors e^2 per pyramid row
+  int nf;                             // rows of the contact arrays per knot: nc, or the feet (nc / 2) of the wrench model
+  double qs;                          // 1: tracking gradient q = -Wx xbar (cost.py:21-29); 0: none (TALOS, scp_solver.py:13-20)
+  double foot_range[4];               // wrench model: cop_x <= [0], -cop_x <= [1], cop_y <= [2], -cop_y <= [3]
   // QP solver settings (OSQP's where they have the same meaning; scp_solver.py:61-63)
   double alpha, rho0, eps_abs, eps_rel, delta, inv_delta, adapt_tol, rho_e_rel, rho_k_rel, rho_e_pol_rel, as_tol;
   int max_iter, check_every, polish, refine, adaptive_rho, adapt_start;
@@ -160,22 +174,71 @@ CMPC_HD void cross3(const double* a, const double* b, double* o) {
 CMPC_CX int nxt3(int a) { return a == 2 ? 0 : a + 1; }
 CMPC_CX int prv3(int a) { return a == 0 ? 2 : a - 1; }
 
+// position of control a of (pseudo-)contact c in the caller's control vector
+CMPC_CX int uix(int c, int a) {
+  return !WR ? 3 * c + a : 6 * (c >> 1) + ((c & 1) ? (a < 2 ? a : 5) : 2 + a);
+}
+
 // K1: closed-form Jacobian data and affine term of one knot
 //     (centroidal_model.py:189-232), point-contact model:
 //     A_k = I + dt [[0, I/m, 0],[0,0,0],[[S]x,0,0]],  S = sum_i a_i fbar_i
 //     B_k[:,3s:3s+3] = dt [0; I; [d_s]x],              d_s = p_s - cbar
 //     c_k = fbar - A xbar - B ubar = [0; dt m g e_z; -dt S x cbar]
 struct KnotLin {
-  double S[3], ck[3], d[MAXU];
+  double S[3], ck[3], d[WR ? 3 * MAXU : MAXU];   // wrench model: M[slot][9] instead of d[slot][3]
   int meta;   // slots | contact id per slot << 4
 };
+//     Wrench model (WR; centroidal_model.py:204-208), foot i with frame R = [r1 r2 r3]:
+//     kappa_dot += (p - c + r1 cop_x + r2 cop_y) x f + r3 tau_z.  Force slot: lever arm e = p + R[:,0:2] cop_bar
+//     - c_bar; wrench slot: kappa rows dt [r1 x fbar, r2 x fbar, r3], no momentum rows.  Both are stored as
+//     the 3x3 block M (column a at 3a) with B_k[6:9, slot] = dt M;
+//     c_k = [0; dt m g e_z; -dt S x cbar - dt sum_i (R[:,0:2] cop_bar_i) x fbar_i].
 CMPC_HD void linearize_knot(const Params& P, const double* xbar, const double* ubar, const double* cpos,
-                            const int* cact, int terminal, KnotLin& o) {
+                            const int* cact, int terminal, KnotLin& o, const double* cR = nullptr) {
   for (int i = 0; i < 3; ++i) o.S[i] = o.ck[i] = 0.0;
-  for (int i = 0; i < MAXU; ++i) o.d[i] = 0.0;
+  for (int i = 0; i < (WR ? 3 * MAXU : MAXU); ++i) o.d[i] = 0.0;
   o.meta = 0;
   if (terminal) return;   // terminal knot: no dynamics, no controls
   int slot = 0, code = 0;
+  if (WR) {
+    double bil[3] = {0.0, 0.0, 0.0};
+    for (int ft = 0; ft < P.nf; ++ft) {
+      if (!cact[ft]) continue;
+      const double* R = cR + 9 * ft;
+      const double* uf = ubar + 6 * ft;
+      const double fb[3] = {uf[2], uf[3], uf[4]};
+      double rc[3], e[3], t[3];
+      for (int a = 0; a < 3; ++a) {
+        rc[a] = R[3 * a] * uf[0] + R[3 * a + 1] * uf[1];     // R[:,0:2] cop_bar
+        e[a] = cpos[3 * ft + a] - xbar[a] + rc[a];
+        o.S[a] += fb[a];
+      }
+      cross3(rc, fb, t);
+      for (int a = 0; a < 3; ++a) bil[a] += t[a];
+      double* Mf = o.d + 9 * slot;        // force slot: [e]x, column a = e x e_a
+      for (int a = 0; a < 3; ++a) {
+        Mf[3 * a + a] = 0.0;
+        Mf[3 * a + nxt3(a)] = e[prv3(a)];
+        Mf[3 * a + prv3(a)] = -e[nxt3(a)];
+      }
+      code |= (2 * ft) << (2 * slot);
+      ++slot;
+      double* Mw = o.d + 9 * slot;        // wrench slot: [r1 x fbar, r2 x fbar, r3]
+      for (int a = 0; a < 2; ++a) {
+        const double ra[3] = {R[a], R[3 + a], R[6 + a]};
+        cross3(ra, fb, t);
+        for (int j = 0; j < 3; ++j) Mw[3 * a + j] = t[j];
+      }
+      for (int j = 0; j < 3; ++j) Mw[6 + j] = R[3 * j + 2];
+      code |= (2 * ft + 1) << (2 * slot);
+      ++slot;
+    }
+    double Sxc[3];
+    cross3(o.S, xbar, Sxc);
+    for (int a = 0; a < 3; ++a) o.ck[a] = -P.dt * Sxc[a] - P.dt * bil[a];
+    o.meta = slot | (code << 4);
+    return;
+  }
   for (int c = 0; c < P.nc; ++c) {
     if (cact[c]) {
       for (int a = 0; a < 3; ++a) {
@@ -194,9 +257,19 @@ CMPC_HD void linearize_knot(const Params& P, const double* xbar, const double* u
 
 // x+ = f(x,u) (centroidal_model.py:189-212), full (per-contact) control layout
 CMPC_HD void step_knot(const Params& P, const double* x, const double* u, const double* cpos, const int* cact,
-                       double* xn) {
+                       double* xn, const double* cR = nullptr) {
   double F[3] = {0, 0, 0}, Tq[3] = {0, 0, 0};
-  for (int c = 0; c < P.nc; ++c) {
+  for (int c = 0; c < P.nf; ++c) {
+    if (WR) {   // six controls per foot: (cop_x, cop_y, fx, fy, fz, tau_z)
+      if (!cact[c]) continue;
+      const double* R = cR + 9 * c;
+      const double* uf = u + 6 * c;
+      double arm[3], t[3];
+      for (int a = 0; a < 3; ++a) arm[a] = cpos[3 * c + a] - x[a] + (R[3 * a] * uf[0] + R[3 * a + 1] * uf[1]);
+      cross3(arm, uf + 2, t);
+      for (int a = 0; a < 3; ++a) { F[a] += uf[2 + a]; Tq[a] += t[a] + R[3 * a + 2] * uf[5]; }
+      continue;
+    }
     if (cact[c]) {
       double d[3] = {cpos[3 * c] - x[0], cpos[3 * c + 1] - x[1], cpos[3 * c + 2] - x[2]};
       double t[3];

@@ -29,16 +29,22 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
 inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const cmpc_scp_params* scp,
                        const cmpc_qp_settings* qp, int identity_R) {
   if (d->N < 1 || d->nc < 1 || d->nc > MAXC || d->batch < 0) return -1;
+  if (WR && 2 * d->nc > MAXC) return -1;
   cmpc_qp_settings dq;
   if (!qp) { default_qp_settings(&dq); qp = &dq; }
   memset(p, 0, sizeof(Params));
-  p->N = d->N; p->nc = d->nc; p->nu = 3 * d->nc; p->identity_R = identity_R;
+  p->N = d->N; p->nc = WR ? 2 * d->nc : d->nc; p->nu = 3 * p->nc; p->identity_R = identity_R;
+  p->nf = d->nc;
+  p->qs = WR ? 0.0 : 1.0;
+  for (int i = 0; i < 4; ++i) p->foot_range[i] = WR ? m->foot_range[i] : 0.0;
   p->m = m->robot_mass; p->g = m->gravity_constant; p->dt = m->dt; p->mu = m->mu;
   p->kf = p->mu * 0.70710678118654752440;
   p->dt_m = p->dt / p->m;
   p->dtmg = p->dt * p->m * p->g;
   for (int i = 0; i < NX; ++i) p->Wx[i] = m->state_cost_weights[i];
-  for (int i = 0; i < MAXU; ++i) p->Wu[i] = i < p->nu ? m->control_cost_weights[i] : 1.0;
+  for (int i = 0; i < MAXU; ++i) p->Wu[i] = 1.0;
+  for (int c = 0; c < p->nc; ++c)   // the solver's control order: three per (pseudo-)contact
+    for (int a = 0; a < 3; ++a) p->Wu[3 * c + a] = m->control_cost_weights[uix(c, a)];
   for (int i = 0; i < NX; ++i) if (!(p->Wx[i] > 0.0)) return -2;
   for (int i = 0; i < p->nu; ++i) if (!(p->Wu[i] > 0.0)) return -2;
   // fast path: identity contact frames and the same control weights for every contact, so the
@@ -46,7 +52,8 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   int uniform = 1;
   for (int c = 1; c < p->nc; ++c)
     for (int a = 0; a < 3; ++a) if (p->Wu[3 * c + a] != p->Wu[a]) uniform = 0;
-  p->fast = identity_R && uniform;
+  p->fast = identity_R && uniform && !WR;
+  if (WR) for (int i = 0; i < 4; ++i) if (!(p->foot_range[i] >= 0.0)) return -1;
   for (int row = 0; row < 4; ++row) {
     const double gx = (row < 2) ? 1.0 / sqrt(p->Wu[0]) : 0.0, gy = (row >= 2) ? 1.0 / sqrt(p->Wu[1]) : 0.0;
     const double gz = p->kf / sqrt(p->Wu[2]);
@@ -56,7 +63,11 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   p->alpha = qp->alpha; p->rho0 = qp->rho; p->eps_abs = qp->eps_abs;
   p->eps_rel = qp->eps_rel; p->delta = qp->delta; p->inv_delta = 1.0 / qp->delta; p->adapt_tol = qp->adaptive_rho_tolerance;
   p->rho_e_rel = 100.0; p->rho_k_rel = 1.0;
-  p->rho_e_pol_rel = 1e4;   // terminal-equality penalty while polishing (x max W_x), DESIGN.md
+  // terminal-equality penalty while polishing (x max W_x).  Wrench model: active CoP / friction rows at the last
+  // knots and x_N = x_final nearly over-determine the last controls; the multiplier iteration then contracts by
+  // 1 / (1 + penalty x joint compliance) only when BOTH penalties are large (measured: 0.93 per sweep at
+  // 1e7 / delta 1e-6, 0.08 at 1e9 / delta 1e-9)
+  p->rho_e_pol_rel = WR ? 1e6 : 1e4;
   p->max_iter = qp->max_iter; p->check_every = qp->check_termination > 0 ? qp->check_termination : 5;
   p->polish = qp->polish; p->refine = qp->polish_refine_iter; p->adaptive_rho = qp->adaptive_rho;
   p->adapt_start = qp->adaptive_rho_start;
@@ -76,8 +87,9 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
 // allocated for the general layout of the problem's contact count (friction table included), so that a
 // handle can switch between the nominal and the stochastic / rotated-contact path without reallocating.
 struct WsSizes { long tiles, ws, nst, info; int rfields; };
-inline WsSizes ws_sizes(int B, int N, int nc) {
+inline WsSizes ws_sizes(int B, int N, int nc_in) {
   WsSizes w;
+  const int nc = WR ? 2 * nc_in : nc_in;
   w.tiles = (B + TL - 1) / TL;
   w.rfields = rec_fields(nc, true);
   w.ws = w.tiles * (N + 1) * (long)(w.rfields * TL);

@@ -529,12 +529,15 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
   const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
   const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
   const double ck[3] = {CMPC_S(r, L.ck), CMPC_S(r, L.ck + 1), CMPC_S(r, L.ck + 2)};
-  double ds[NS > 0 ? NS : 1][3], dts[NS > 0 ? NS : 1];
+  // wrench model: B_k[:, slot] = dt [0; sg I; M] with the slot's 3x3 block M (column a at 3a) and sg = 1 for a
+  // force slot, 0 for a wrench slot (odd pseudo-contact id); point contacts: M = [d]x, sg = 1, never formed
+  double ds[NS > 0 ? NS : 1][WR ? 9 : 3], dts[NS > 0 ? NS : 1], sg[NS > 0 ? NS : 1];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     dts[s] = s < nsl ? P.dt : 0.0;
+    sg[s] = (WR && ((mt >> (4 + 2 * s)) & 1)) ? 0.0 : 1.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) ds[s][a] = CMPC_S(r, L.d + 3 * s + a);
+    for (int a = 0; a < (WR ? 9 : 3); ++a) ds[s][a] = CMPC_S(r, L.d + (WR ? 9 : 3) * s + a);
   }
   const bool kap = MODE == MODE_PMM && S.kap && k >= 1;
   if (kap) {   // kappa penalty block of the multiplier method -> scratch (every lane writes the same values)
@@ -569,6 +572,8 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
 #pragma unroll
         for (int a = 0; a < 3; ++a) {   // (P B)[i][(s,a)] = dt_s (P[i][3+a] + P[i][6+a1] d[a2] - P[i][6+a2] d[a1])
           const int a1 = nxt3(a), a2 = prv3(a);
+          if (WR) sp_st(xs, X_Y + i * n + 3 * s + a, dts[s] * fma(Pr[8], ds[s][3 * a + 2], fma(Pr[7], ds[s][3 * a + 1], fma(Pr[6], ds[s][3 * a], sg[s] * Pr[3 + a]))));
+          else
           sp_st(xs, X_Y + i * n + 3 * s + a, dts[s] * fma(Pr[6 + a1], ds[s][a2], fma(-Pr[6 + a2], ds[s][a1], Pr[3 + a])));
         }
       }
@@ -595,7 +600,10 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
     if (rr < NA) {   // control row (s, a):  B' (P B)  + R block
       const int s = rr / 3, a = rr - 3 * s, a1 = a == 2 ? 0 : a + 1, a2 = a == 0 ? 2 : a - 1;
       const double dtr = s < nsl ? P.dt : 0.0;
-      const double dA = CMPC_SO(r, L.d, 3 * s + a2), dB = CMPC_SO(r, L.d, 3 * s + a1);
+      const double dA = WR ? 0.0 : CMPC_SO(r, L.d, 3 * s + a2), dB = WR ? 0.0 : CMPC_SO(r, L.d, 3 * s + a1);
+      const double m0 = WR ? CMPC_SO(r, L.d, 9 * s + 3 * a) : 0.0, m1 = WR ? CMPC_SO(r, L.d, 9 * s + 3 * a + 1) : 0.0;
+      const double m2 = WR ? CMPC_SO(r, L.d, 9 * s + 3 * a + 2) : 0.0;
+      const double sgr = (WR && s < nsl && ((mt >> (4 + 2 * s)) & 1)) ? 0.0 : 1.0;
       // R block of the slot: W_u + G' diag(rr) G, columns 3s .. 3s+2
       double gc[3][4], rw[4];
 #pragma unroll
@@ -627,7 +635,9 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
       }
 #pragma unroll
       for (int e = 0; e < NA; ++e) {
-        double v = dtr * fma(sp_ld(xs, X_Y + (6 + a1) * n + e), dA, fma(-sp_ld(xs, X_Y + (6 + a2) * n + e), dB, sp_ld(xs, X_Y + (3 + a) * n + e)));
+        double v;
+        if (WR) v = dtr * fma(sp_ld(xs, X_Y + 8 * n + e), m2, fma(sp_ld(xs, X_Y + 7 * n + e), m1, fma(sp_ld(xs, X_Y + 6 * n + e), m0, sgr * sp_ld(xs, X_Y + (3 + a) * n + e))));
+        else v = dtr * fma(sp_ld(xs, X_Y + (6 + a1) * n + e), dA, fma(-sp_ld(xs, X_Y + (6 + a2) * n + e), dB, sp_ld(xs, X_Y + (3 + a) * n + e)));
         if (e / 3 == s) v += radd[e % 3];
         Tf[t][e] = v;
       }
@@ -639,6 +649,9 @@ CMPC_HD void factor_knot(const Params& P, Sv& S, StagedPtr r, double* w, const I
 #pragma unroll
         for (int b2 = 0; b2 < 3; ++b2) {   // Hux[(s,b2)][i]
           const int b1 = nxt3(b2), bp = prv3(b2);
+          if (WR) Tf[t][3 * s + b2] = dts[s] * fma(sp_ld(xs, X_Y + 8 * n + NA + i), ds[s][3 * b2 + 2], fma(sp_ld(xs, X_Y + 7 * n + NA + i), ds[s][3 * b2 + 1],
+                                      fma(sp_ld(xs, X_Y + 6 * n + NA + i), ds[s][3 * b2], sg[s] * sp_ld(xs, X_Y + (3 + b2) * n + NA + i))));
+          else
           Tf[t][3 * s + b2] = dts[s] * fma(sp_ld(xs, X_Y + (6 + b1) * n + NA + i), ds[s][bp],
                                       fma(-sp_ld(xs, X_Y + (6 + bp) * n + NA + i), ds[s][b1], sp_ld(xs, X_Y + (3 + b2) * n + NA + i)));
         }
@@ -855,6 +868,7 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     o_c0[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + 3 + a); o_cA[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + 6 + a1);
     o_cB[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + 6 + a2);
     o_dA[t] = s_off(so_of<SK, NS, !FAST>(L.d) + 3 * s + a2); o_dB[t] = s_off(so_of<SK, NS, !FAST>(L.d) + 3 * s + a1);
+    if (WR) { o_dA[t] = s_off(so_of<SK, NS, !FAST>(L.d) + 9 * s + 3 * a); o_dB[t] = s_off(so_of<SK, NS, !FAST>(L.d) + 9 * s + 3 * a + 1); }   // column a of M
     o_g[t] = s_off(so_of<SK, NS, !FAST>(L.g) + s * GS + a);   // G[0][a] of the slot (rows 3 apart)
     o_gs[t] = s_off(so_of<SK, NS, !FAST>(L.g) + s * GS);      // the slot's table: e2 at 12 + row, ub at 16 + row
     o_ux[t] = s_off(X_UX + jc);
@@ -880,6 +894,7 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     rkx[t] = i >= 6;
     rmul[t] = g3 == 0 ? P.dt : (g3 == 1 ? P.dt_m : 0.0);   // (A'g)_i = g_i + mul (g[rA] sA - g[rB] sB)
     rwx[t] = pick9(P.Wx, i);
+    if (WR) rwx[t] *= P.qs;
     o_m[t] = s_off(so_of<SK, NS, !FAST>(L.hn) + rrow[t] * NAP);
     o_pi[t] = s_off(i); o_qA[t] = s_off(rA); o_qB[t] = s_off(rB);
     o_ei[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + i); o_eA[t] = s_off(so_of<SK, NS, !FAST>(L.pc) + rA);
@@ -908,9 +923,15 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
     double* w = rec_of(T, I, k);
     const ScratchPtr pin = sp_at(xs, s_off(X_PX + buf * 9)), pout = sp_at(xs, s_off(X_PX + (buf ^ 1) * 9));
     // ---- phase 1 loads
-    const int nsl4 = 4 * (CMPC_SI(r, L.meta, 0) & 7);
+    const int mt_b = CMPC_SI(r, L.meta, 0);
+    const int nsl4 = 4 * (mt_b & 7);
     const int pm = (MODE == MODE_PMM) ? CMPC_SI(r, L.meta, 1) : 0;
     const double kb[3] = {CMPC_S(r, L.xb + 6), CMPC_S(r, L.xb + 7), CMPC_S(r, L.xb + 8)};
+    double g6w[3] = {0.0, 0.0, 0.0};   // wrench model: g[6..8] = p + Pc, every control row needs all three
+    if (WR) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) g6w[j] = sp_ld(pin, 6 + j) + CMPC_S(r, L.pc + 6 + j);
+    }
     double kin[4] = {0.0, 0.0, 0.0, 0.0};   // ADMM: vk[3]; multiplier mode: yk[4]
     if (MODE == MODE_ADMM) {
 #pragma unroll
@@ -941,6 +962,7 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
       pB[t] = sp_ld(sp_at(pin, o_pB[t]), 0); cB[t] = sp_ld(sp_at(r, o_cB[t]), 0);
       dA[t] = sp_ld(sp_at(r, o_dA[t]), 0);
       dB[t] = sp_ld(sp_at(r, o_dB[t]), 0);
+      if (WR) pA[t] = sp_ld(sp_at(r, o_dB[t]), 1);   // third entry of the column of M
     }
     // ---- phase 1 arithmetic: linear term of the kappa rows (replicated), hu of the lane's control rows
     double kl[3] = {0.0, 0.0, 0.0};
@@ -971,6 +993,10 @@ CMPC_HD void bwd_run(const Params& P, const Sv& S, const TileCtx& T, const Inst&
       }
       const double o = fma(fg[t][3], tt[3], fma(fg[t][2], tt[2], fma(fg[t][1], tt[1], fg[t][0] * tt[0])));
       const double g0 = p0[t] + c0[t], gA = pA[t] + cA[t], gB = pB[t] + cB[t];
+      if (WR) {
+        const double sgm = ((mt_b >> (4 + (cs4[t] >> 1))) & 1) ? 0.0 : 1.0;
+        huo[t] = dtr * fma(g6w[2], pA[t], fma(g6w[1], dB[t], fma(g6w[0], dA[t], sgm * g0))) + o;
+      } else
       huo[t] = dtr * fma(gA, dA[t], fma(-gB, dB[t], g0)) + o;
     }
     CMPC_CK(1);
@@ -1068,7 +1094,7 @@ CMPC_OP void backward_op(const Params& P_in, TileCtx& T, const Inst& I_in, Sv& S
     kappa_linear_term<0, MODE, FAST, SK>(P, S, r, I, CMPC_SI(r, L.meta, 1), kl);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      double p = -(P.Wx[i] * CMPC_S(r, L.xb + i)) - (rho_e * I.xf[i] - S.ye[i]);
+      double p = -((WR ? P.qs * P.Wx[i] : P.Wx[i]) * CMPC_S(r, L.xb + i)) - (rho_e * I.xf[i] - S.ye[i]);
       if (i >= 6) p += kl[i - 6];
       sp_st(xs, X_PX + i, p);
     }
@@ -1191,7 +1217,7 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
     for (int i = 0; i < 9; ++i) {
       const double Px = P.Wx[i] * x[i];
       const double rd = i >= 6 ? rdx[i - 6] : 0.0;
-      const double aty = rd - Px + P.Wx[i] * CMPC_S(r, L.xb + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
+      const double aty = rd - Px + (WR ? P.qs * P.Wx[i] : P.Wx[i]) * CMPC_S(r, L.xb + i);   // (A'y)_x = r_d - P x - q,  q = -Wx xbar
       R.dua = fmax(R.dua, fabs(rd));
       R.ndua = fmax(R.ndua, fmax(fabs(Px), fabs(aty)));
     }
@@ -1291,13 +1317,14 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
     }
     team_sync(I);
     // ---- phase 2 loads: u~, stage data, the lane's friction rows
-    double u[NA > 0 ? NA : 1], dsl[NS > 0 ? NS : 1][3];
+    double u[NA > 0 ? NA : 1], dsl[NS > 0 ? NS : 1][WR ? 9 : 3];
 #pragma unroll
     for (int j = 0; j < NA; ++j) u[j] = sp_ld(xs, X_UX + j);
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int a = 0; a < 3; ++a) dsl[s][a] = CMPC_S(r, L.d + 3 * s + a);
+      for (int a = 0; a < (WR ? 9 : 3); ++a) dsl[s][a] = CMPC_S(r, L.d + (WR ? 9 : 3) * s + a);
+    const int mt_f = WR ? CMPC_SI(r, L.meta, 0) : 0;
     const double S3[3] = {CMPC_S(r, L.s), CMPC_S(r, L.s + 1), CMPC_S(r, L.s + 2)};
     const double ckv[3] = {CMPC_S(r, L.ck), CMPC_S(r, L.ck + 1), CMPC_S(r, L.ck + 2)};
     double fvv[FT > 0 ? FT : 1], fu0[FT > 0 ? FT : 1], fu1[FT > 0 ? FT : 1], fu2[FT > 0 ? FT : 1];
@@ -1323,6 +1350,11 @@ CMPC_HD void fwd_run(const Params& P, Sv& S, Res& R, const TileCtx& T, const Ins
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const int a1 = nxt3(a), a2 = prv3(a);
+        if (WR) {   // padded slots carry M = 0 and u = 0
+          if (!((mt_f >> (4 + 2 * s)) & 1)) sF[a] = sF[a] + u[3 * s + a];
+          sT[a] = sT[a] + fma(dsl[s][6 + a], u[3 * s + 2], fma(dsl[s][3 + a], u[3 * s + 1], dsl[s][a] * u[3 * s]));
+          continue;
+        }
         sF[a] = sF[a] + u[3 * s + a];
         sT[a] = sT[a] + fma(dsl[s][a1], u[3 * s + a2], -(dsl[s][a2] * u[3 * s + a1]));
       }
@@ -1578,8 +1610,16 @@ CMPC_OP void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, bool 
     double F[3] = {0, 0, 0}, Tq[3] = {0, 0, 0};
     for (int sl = 0; sl < ns; ++sl) {
       const int cid = (mt >> (4 + 2 * sl)) & 3;
-      const double ds[3] = {CMPC_R(r, L.d + 3 * sl), CMPC_R(r, L.d + 3 * sl + 1), CMPC_R(r, L.d + 3 * sl + 2)};
       const double us[3] = {CMPC_R(r, L.u + 3 * sl), CMPC_R(r, L.u + 3 * sl + 1), CMPC_R(r, L.u + 3 * sl + 2)};
+      if (WR) {
+        for (int a = 0; a < 3; ++a) {
+          u[uix(cid, a)] = us[a];
+          if (!(cid & 1)) F[a] += us[a];
+          Tq[a] += CMPC_R(r, L.d + 9 * sl + 6 + a) * us[2] + CMPC_R(r, L.d + 9 * sl + 3 + a) * us[1] + CMPC_R(r, L.d + 9 * sl + a) * us[0];
+        }
+        continue;
+      }
+      const double ds[3] = {CMPC_R(r, L.d + 3 * sl), CMPC_R(r, L.d + 3 * sl + 1), CMPC_R(r, L.d + 3 * sl + 2)};
       double t[3];
       cross3(ds, us, t);
 #pragma unroll
@@ -1600,7 +1640,7 @@ CMPC_OP void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, bool 
       lin[3 + a] = x[3 + a] + P.dt * F[a] + (a == 2 ? P.dtmg : 0.0);
       lin[6 + a] = x[6 + a] + P.dt * Sxc[a] + P.dt * Tq[a] + CMPC_R(r, L.ck + a);
     }
-    step_knot(P, x, u, I.cpos + (long)k * P.nc * 3, I.cact + (long)k * P.nc, nl);
+    step_knot(P, x, u, I.cpos + (long)k * P.nf * 3, I.cact + (long)k * P.nf, nl, I.cR ? I.cR + (long)k * P.nf * 9 : nullptr);
     double nk = 0.0, dk = 0.0;
 #pragma unroll
     for (int i = 6; i < 9; ++i) nk += (nl[i] - lin[i]) * (nl[i] - lin[i]);
@@ -1705,7 +1745,7 @@ CMPC_OP void evaluate_op(const Params& P, const TileCtx& T, const Inst& I, bool 
 CMPC_HD int active_slots(const Params& P, const Inst& I, int k) {
   if (k >= P.N) return 0;
   int ns = 0;
-  for (int c = 0; c < P.nc; ++c) ns += I.cact[(long)k * P.nc + c] ? 1 : 0;
+  for (int c = 0; c < P.nf; ++c) ns += I.cact[(long)k * P.nf + c] ? (WR ? 2 : 1) : 0;   // wrench model: force + wrench slot per foot
   return ns;
 }
 CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool live, double* mq_out, double* mc_out, int* nconv_out) {
@@ -1720,19 +1760,21 @@ CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool 
     const int kk = k < N ? k : N - 1;
     const double* xb = I.Xr + k * 9;
     KnotLin Lk;
-    linearize_knot(P, xb, I.Ui + kk * P.nu, I.cpos + (long)kk * P.nc * 3, I.cact + (long)kk * P.nc, k == N, Lk);
+    linearize_knot(P, xb, I.Ui + kk * P.nu, I.cpos + (long)kk * P.nf * 3, I.cact + (long)kk * P.nf, k == N, Lk,
+                   I.cR ? I.cR + (long)kk * P.nf * 9 : nullptr);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
       CMPC_R(r, L.xb + i) = xb[i];
       CMPC_R(r, L.x + i) = 0.0;
-      mq = fmax(mq, fabs(P.Wx[i] * xb[i]));
+      mq = fmax(mq, fabs((WR ? P.qs * P.Wx[i] : P.Wx[i]) * xb[i]));
       nzx |= xb[i] != 0.0;
     }
     if (k < N)
       for (int j = 0; j < P.nu; ++j) nzu |= I.Ui[k * P.nu + j] != 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { CMPC_R(r, L.s + a) = Lk.S[a]; CMPC_R(r, L.ck + a) = Lk.ck[a]; }
-    for (int j = 0; j < L.na; ++j) { CMPC_R(r, L.d + j) = Lk.d[j]; CMPC_R(r, L.dv + j) = 0.0; CMPC_R(r, L.u + j) = 0.0; }
+    for (int j = 0; j < L.na; ++j) { CMPC_R(r, L.dv + j) = 0.0; CMPC_R(r, L.u + j) = 0.0; }
+    for (int j = 0; j < (WR ? 3 : 1) * L.na; ++j) CMPC_R(r, L.d + j) = Lk.d[j];
     for (int j = 0; j < 4 * nst; ++j) { CMPC_R(r, L.vf + j) = 0.0; CMPC_R(r, L.yf + j) = 0.0; }
 #pragma unroll
     for (int j = 0; j < 4; ++j) CMPC_R(r, L.yk + j) = 0.0;
@@ -1755,8 +1797,10 @@ CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool 
 #pragma unroll
           for (int a = 0; a < 3; ++a) {
             double g = pyr4(P, row, a);
-            if (sl < ns && I.cR) {
-              const double* Rm = I.cR + ((long)k * P.nc + cid) * 9;
+            if (WR && (cid & 1)) {   // wrench slot (cop_x, cop_y, tau_z): the CoP box, constraints.py:111-145
+              g = (a == (row >> 1)) ? ((row & 1) ? -1.0 : 1.0) : 0.0;
+            } else if (sl < ns && I.cR) {
+              const double* Rm = I.cR + ((long)k * P.nf + (WR ? cid >> 1 : cid)) * 9;
               g = 0.0;
 #pragma unroll
               for (int b2 = 0; b2 < 3; ++b2) g += pyr4(P, row, b2) * Rm[a * 3 + b2];
@@ -1768,17 +1812,19 @@ CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool 
 #pragma unroll
             for (int a = 0; a < 3; ++a) CMPC_R(r, L.g + sl * GS + row * 3 + a) = G[row * 3 + a];
             CMPC_R(r, L.g + sl * GS + 12 + row) = mx > 0.0 ? 1.0 / (mx * mx) : 0.0;
-            CMPC_R(r, L.g + sl * GS + 16 + row) = (sl < ns && I.fub) ? I.fub[((long)k * P.nc + cid) * 4 + row] : 0.0;
+            CMPC_R(r, L.g + sl * GS + 16 + row) = (WR && (cid & 1)) ? P.foot_range[row] : ((sl < ns && I.fub) ? I.fub[((long)k * P.nc + cid) * 4 + row] : 0.0);
           }
         }
         if (sl < ns) {
-          const double* ub = I.Ui + k * P.nu + 3 * cid;
+          const double* Uk = I.Ui + k * P.nu;
+          const double ub[3] = {Uk[uix(cid, 0)], Uk[uix(cid, 1)], Uk[uix(cid, 2)]};
 #pragma unroll
           for (int row = 0; row < 4; ++row) {
             double cf = 0.0;
 #pragma unroll
             for (int a = 0; a < 3; ++a) cf += G[row * 3 + a] * ub[a];
-            if (I.fub) cf -= I.fub[((long)k * P.nc + cid) * 4 + row];
+            if (WR && (cid & 1)) cf -= P.foot_range[row];
+            else if (I.fub) cf -= I.fub[((long)k * P.nc + cid) * 4 + row];
             CMPC_R(r, L.vf + 4 * sl + row) = fmin(cf, 0.0);
           }
         }
@@ -1821,7 +1867,13 @@ CMPC_OP void write_solution_knots(const Params& P, const TileCtx& T, const Inst&
     Xo[e] = CMPC_R(rec_of(T, I, k), L.x + i);
   }
   for (int e = sub_of(I); e < N * nu; e += NL) {
-    const int k = e / nu, j = e - k * nu, c = j / 3, a = j - 3 * c;
+    const int k = e / nu, j = e - k * nu;
+    int c = j / 3, a = j - 3 * c;
+    if (WR) {   // (cop_x, cop_y, fx, fy, fz, tau_z) per foot -> pseudo-contact and axis
+      const int ft = j / 6, w = j - 6 * ft;
+      c = 2 * ft + ((w >= 2 && w <= 4) ? 0 : 1);
+      a = (w >= 2 && w <= 4) ? w - 2 : (w == 5 ? 2 : w);
+    }
     const Lay L = lay_of(T.ns(k), T.gen != 0);
     const double* r = rec_of(T, I, k);
     const int mt = meta_of(T, I, k, L.meta)[0];
@@ -1977,6 +2029,9 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         D.pc = PC_ROUND_CHECK;
         break;
       case PC_AFTER_PMM1:
+#if !defined(__CUDACC__) && defined(CMPC_EMU_TRACE)
+        fprintf(stderr, "  pmm sweep: round %d sw %d chg %d pri %.3e\n", D.round, D.sw, D.chg, S.pri);
+#endif
         if (S.kbad) { D.pc = PC_POLISH_END; break; }
         if (D.chg || S.pri <= P.as_tol * (1.0 + S.npri)) { D.pc = PC_ROUND_CHECK; break; }
         ++D.sw;
@@ -1994,6 +2049,10 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         D.pc = D.round > P.as_rounds ? PC_POLISH_END : PC_ROUND_TOP;
         break;
       case PC_POLISH_END: {
+#if !defined(__CUDACC__) && defined(CMPC_EMU_TRACE)
+        fprintf(stderr, "polish end: it %d round %d sw %d chg %d kbad %d fail %d pri %.3e npri %.3e certified %d\n", D.it, D.round, D.sw,
+                D.chg, S.kbad, S.fail, S.pri, S.npri, D.certified);
+#endif
         S.kap = 0;
 #pragma unroll
         for (int i = 0; i < 9; ++i) S.ye[i] = D.ye_keep[i];   // the ADMM multiplier comes back
@@ -2159,10 +2218,10 @@ CMPC_HD void bind_instance(Inst& I, const Params& P, const Batch& bt, int b) {
   const long plan = (long)b * bt.plan_stride;
   I.b = b;
   I.lane = b & (TL - 1);
-  I.cpos = bt.cpos + plan * N * P.nc * 3;
-  I.cR = bt.cR ? bt.cR + plan * N * P.nc * 9 : nullptr;
+  I.cpos = bt.cpos + plan * N * P.nf * 3;
+  I.cR = bt.cR ? bt.cR + plan * N * P.nf * 9 : nullptr;
   I.fub = bt.fub ? bt.fub + (long)b * N * P.nc * 4 : nullptr;
-  I.cact = bt.cact + plan * N * P.nc;
+  I.cact = bt.cact + plan * N * P.nf;
   I.Xr = bt.X_ref + (long)b * (N + 1) * 9;
   I.Ui = bt.U_init + (long)b * N * P.nu;
   I.xi = bt.x_init + (long)b * 9;

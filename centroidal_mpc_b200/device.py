@@ -27,6 +27,9 @@ def _ptr(t):
 # applies the same values by itself when it is called with qp = NULL and upper bounds are bound
 # (cmpc_api.cu: launch_tiles), so a C caller gets them without knowing this table.
 STOCHASTIC_QP_DEFAULTS = dict(polish_refine_iter=10, polish_active_set_rounds=19, active_set_start=20, active_set_step=20)
+# ... and for the wrench contact model (TALOS): multipliers of the order of the 900 N contact forces make the
+# default certificate tolerance 1e-9 leave 6e-6 in X; 1e-11 reaches the tightly solved oracle to 3e-7
+WRENCH_QP_DEFAULTS = dict(polish_refine_iter=30, polish_active_set_rounds=19, active_set_tol=1e-11, delta=1e-9)
 
 
 class BatchSolver:
@@ -38,7 +41,8 @@ class BatchSolver:
         self.lib = L.load()
         self.batch = batch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.dims = L.cmpc_dims(batch.B, batch.N, batch.nc, 1 if batch.shared_plan else 0)
+        self.dims = L.cmpc_dims(batch.B, batch.N, batch.nc, 1 if batch.shared_plan else 0,
+                                L.contact_model_of(batch.proto["robot"]))
         self.model = L.make_model_struct(batch.proto)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -96,6 +100,8 @@ class BatchSolver:
         return self
 
     def _qp(self, overrides):
+        if getattr(self.batch, "wrench", False):
+            return dict(WRENCH_QP_DEFAULTS, **(overrides or {}))
         if self.friction_ub is None:
             return overrides
         return dict(STOCHASTIC_QP_DEFAULTS, **(overrides or {}))
@@ -164,18 +170,26 @@ def _lin_call(model, X, U, want_jac):
     lib = L.load()
     prob = model.problem_arrays()
     N, nc = prob["N"], prob["contact_active"].shape[1]
-    nu = 3 * nc
-    if prob["robot"] == "TALOS":
-        raise NotImplementedError("TALOS contact model: SURVEY.md section 8 row f4 (next)")
+    wrench = prob["robot"] == "TALOS"
+    nu = (6 if wrench else 3) * nc
     dev = torch.device("cuda", torch.cuda.current_device())
     Xd = torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float64).T[None])).to(dev)
     Ud = torch.from_numpy(np.ascontiguousarray(np.asarray(U, dtype=np.float64).T[None])).to(dev)
     cp = torch.from_numpy(np.ascontiguousarray(prob["contact_pos"][None])).to(dev)
     ca = torch.from_numpy(np.ascontiguousarray(prob["contact_active"][None].astype(np.int32))).to(dev)
-    dims = L.cmpc_dims(1, N, nc, 1)
+    dims = L.cmpc_dims(1, N, nc, 1, L.contact_model_of(prob["robot"]))
     mdl = L.make_model_struct(prob)
     f = torch.empty((1, N, 9), dtype=torch.float64, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if wrench:   # CoP / wrench contact model: the frames enter the dynamics
+        cR = torch.from_numpy(np.ascontiguousarray(prob["contact_R"][None].astype(np.float64))).to(dev)
+        fx = torch.empty((1, N, 9, 9), dtype=torch.float64, device=dev) if want_jac else None
+        fu = torch.empty((1, N, 9, nu), dtype=torch.float64, device=dev) if want_jac else None
+        L.check(lib.cmpc_linearize_wrench(C.byref(dims), C.byref(mdl), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(cR), _ptr(ca),
+                                          _ptr(f), _ptr(fx), _ptr(fu), st), lib)
+        if want_jac:
+            return f[0].cpu().numpy(), fx[0].cpu().numpy(), fu[0].cpu().numpy()
+        return f[0].cpu().numpy()
     if want_jac:
         fx = torch.empty((1, N, 9, 9), dtype=torch.float64, device=dev)
         fu = torch.empty((1, N, 9, nu), dtype=torch.float64, device=dev)
@@ -195,7 +209,7 @@ def lqr_gains_covs_batched(batch, X, U, Q, R, cov_w, cov_eta, want_covs=True):
     dev = torch.device("cuda", torch.cuda.current_device())
     B, N, nc, nu = batch.B, batch.N, batch.nc, batch.nu
     if batch.proto["robot"] == "TALOS":
-        raise NotImplementedError("TALOS contact model: SURVEY.md section 8 row f4 (next)")
+        raise NotImplementedError("LQR gains / covariances (stochastic mode) are built for the point-contact model only")
 
     def dv(a, dt):
         t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))

@@ -38,16 +38,40 @@ def reference_trajectory(conf, b=0, mode="B", v=0.1):
     mode 'A' (perturbed initial state only): the shared nominal trajectory; the caller
     perturbs x_init (see ``perturbed_x_init``)."""
     N, m, dt = conf.N, conf.robot_mass, conf.dt
+    if getattr(conf, "robot_name", "") == "TALOS":
+        v = 0.0   # the feet step in place (stepLength 0): the CoM sways sideways, it does not travel
     k = np.arange(N + 1)
     X = np.zeros((N + 1, 9))
     X[:, 0] = v * dt * k
     X[:, 2] = _COM_HEIGHT.get(conf.name, 0.23)
     X[:, 3] = m * v
+    if getattr(conf, "robot_name", "") == "TALOS":
+        _lateral_sway(conf, X)
     if mode == "B":
         rng = np.random.default_rng(1000 + b)
         X[:, 0:3] += rng.normal(0.0, 0.01, size=3)[None, :]
         X[:, 6:9] += rng.normal(0.0, 1e-3, size=(N + 1, 3))
     return X
+
+
+def _lateral_sway(conf, X, gain=0.85, half_window=6):
+    """Flat-footed biped: the CoM reference sways over the stance foot (a biped cannot hold its CoM between the
+    feet through a single-support phase: with the CoP confined to the sole the angular-momentum and lateral
+    momentum rows of the terminal equality contradict each other).  y_ref = moving average of gain * mean y of
+    the active feet, lateral momentum = m * dy/dt by finite differences."""
+    from .src.contact_plan import create_contact_trajectory
+    traj = create_contact_trajectory(conf)
+    N = conf.N
+    target = np.zeros(N + 1)
+    for k in range(N + 1):
+        kk = min(k, N - 1)
+        ys = [traj[c][kk].pose.translation[1] for c in traj if traj[c][kk].ACTIVE]
+        target[k] = gain * float(np.mean(ys)) if ys else 0.0
+    pad = np.concatenate([np.full(half_window, target[0]), target, np.full(half_window, target[-1])])
+    kernel = np.ones(2 * half_window + 1) / (2 * half_window + 1)
+    y = np.convolve(np.convolve(pad, kernel, mode="same"), kernel, mode="same")[half_window:half_window + N + 1]
+    X[:, 1] = y
+    X[:, 4] = conf.robot_mass * np.gradient(y, conf.dt)
 
 
 def perturbed_x_init(conf, b):

@@ -36,13 +36,22 @@ typedef struct {
   int32_t N;            /* horizon (knots of control) */
   int32_t nc;           /* contacts: 4 (solo12) or 2 (bolt); point-contact model, n_u = 3*nc */
   int32_t shared_plan;  /* 1: contact arrays have leading dimension 1 */
+  int32_t contact_model; /* CMPC_CONTACT_POINT (0): n_u = 3*nc, controls (fx,fy,fz) per contact (solo12, bolt);
+                            CMPC_CONTACT_WRENCH (1): flat feet, nc <= 2, n_u = 6*nc, controls (cop_x,cop_y,fx,fy,fz,tau_z)
+                            per foot in the reference's order (TALOS: src/centroidal_model.py:204-208,
+                            src/optimizer.py:48-64); contact_R is then mandatory, the CoP box rows
+                            (src/constraints.py:111-145) come from cmpc_model.foot_range, and the cost has no tracking
+                            gradient (src/scp_solver.py:13-20) */
 } cmpc_dims;
+enum { CMPC_CONTACT_POINT = 0, CMPC_CONTACT_WRENCH = 1 };
 
 /* conf attributes copied by Centroidal_model.__init__ (src/centroidal_model.py:27-32) */
 typedef struct {
   double robot_mass, gravity_constant, dt, mu;
   double state_cost_weights[9];     /* diagonal of conf.state_cost_weights   */
   double control_cost_weights[12];  /* diagonal of conf.control_cost_weights */
+  double foot_range[4];             /* wrench model only: conf.robot_foot_range, -[1] <= cop_x <= [0], -[3] <= cop_y <= [2]
+                                       (src/constraints.py:127-137) */
 } cmpc_model;
 
 /* conf.scp_params, keys read at src/scp_solver.py:120-128 */
@@ -136,6 +145,13 @@ int cmpc_rollout(const cmpc_dims* dims, const cmpc_model* model, const double* X
 
 /* conf.Q, conf.R, conf.cov_w, conf.cov_white_noise (src/centroidal_model.py:34-35,41-42): dense,
  * row-major; R and cov_w are nu x nu with leading dimension nu (the first nu*nu entries are read). */
+/* Wrench contact model (dims.contact_model = CMPC_CONTACT_WRENCH): f(x_k,u_k) and, when fx and fu are not
+   null, the Jacobians A_k [B][N][9][9], B_k [B][N][9][6*nc] along (X, U) in the reference's control order
+   -- integrate_model_one_step / jacfwd for robot == 'TALOS', /root/reference/src/centroidal_model.py:
+   189-212,229-231,243-255.  contact_R [Bp][N][nc][3][3] row-major. */
+int cmpc_linearize_wrench(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U,
+                          const double* contact_pos, const double* contact_R, const int32_t* contact_active, double* f,
+                          double* fx, double* fu, void* stream);
 typedef struct {
   double Q[81], R[144], cov_w[144], cov_eta[81];
 } cmpc_lqr_weights;

@@ -37,5 +37,7 @@ if __name__ == "__main__":
     run("bolt", 100, 8192)                          # ... and the whole batch on one GPU
     run("solo12_trot", 100, 4096, stochastic=True)  # stochastic mode: friction rows with chance-constraint back-offs
     run("solo12_bound", 100, 4096, stochastic=True)
-    for B in (256, 1024, 4096, 16384, 65536):       # config 5's batch sweep, on the solo12 trot problem
+    for B in (256, 1024, 4096, 16384, 65536):       # the batch sweep on the headline problem
         run("solo12_trot", 100, B, reps=3)
+    for B in (256, 1024, 4096, 16384, 65536):       # config 5: talos (CoP / wrench contact model), batch sweep
+        run("talos", 100, B, reps=3)

@@ -126,7 +126,7 @@ extern "C" int cmpc_emu_solve_scp(const cmpc_dims* dims, const cmpc_model* model
   const int B = dims->batch, N = dims->N;
   WsSizes w1 = ws_sizes(TL, N, dims->nc);   // tiles run one after the other: one tile of workspace
   WsSizes wb = ws_sizes(B, N, dims->nc);
-  const int rfields = rec_fields(dims->nc, !prm.fast);
+  const int rfields = rec_fields(prm.nc, !prm.fast);   // prm.nc: contacts, or the pseudo-contacts of the wrench model
   const long tile_ws = (long)(N + 1) * rfields * TL;
   std::vector<double> ws(w1.ws), scratch((size_t)X_FAC_END * TL);
   std::vector<int> nst(w1.nst);

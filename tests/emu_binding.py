@@ -17,24 +17,28 @@ _DEPS = [os.path.join(_HERE, "..", "centroidal_mpc_b200", "csrc", f)
 _libs = {}
 
 
-def build(force=False, team_lanes=1):
+def build(force=False, team_lanes=1, wrench=False):
     """team_lanes = 1: one host thread of control per instance.  team_lanes = 8: the lock-step build, in
     which the 8 lanes of an instance's team run as coroutines that switch at every team_sync, i.e. the
     work split, the shared-memory exchanges and the synchronisation points of the CUDA kernel."""
     so = _SO if team_lanes == 1 else _SO.replace(".so", "_nl%d.so" % team_lanes)
+    if wrench:   # the CoP / wrench contact model: the same source compiled with CMPC_WRENCH=1 (csrc/cmpc_wrench.cu)
+        so = so.replace(".so", "_wr.so")
     newest = max(os.path.getmtime(f) for f in _DEPS)
     if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC",
-                               "-DCMPC_NL=%d" % team_lanes, "-x", "c++", "-o", so + ".tmp", _SRC])
+                               "-DCMPC_NL=%d" % team_lanes, "-DCMPC_WRENCH=%d" % (1 if wrench else 0), "-x", "c++", "-o",
+                               so + ".tmp", _SRC])
         os.replace(so + ".tmp", so)
     return so
 
 
-def load(team_lanes=1):
-    if team_lanes not in _libs:
-        _libs[team_lanes] = C.CDLL(build(team_lanes=team_lanes))
-        assert _libs[team_lanes].cmpc_emu_team_lanes() == team_lanes
-    return _libs[team_lanes]
+def load(team_lanes=1, wrench=False):
+    key = (team_lanes, bool(wrench))
+    if key not in _libs:
+        _libs[key] = C.CDLL(build(team_lanes=team_lanes, wrench=wrench))
+        assert _libs[key].cmpc_emu_team_lanes() == team_lanes
+    return _libs[key]
 
 
 def _p(a):
@@ -44,7 +48,7 @@ def _p(a):
 def solve_scp(batch, scp_params, qp_overrides=None, friction_ub=None, team_lanes=1):
     """Run the host build of the device solver on a ProblemBatch; returns a dict of arrays.
     ``friction_ub`` [B,N,nc,4]: stochastic mode (upper bounds of the friction rows)."""
-    lib = load(team_lanes)
+    lib = load(team_lanes, wrench=getattr(batch, "wrench", False))
     lib.cmpc_emu_set_friction_ub.argtypes = [C.c_void_p]
     lib.cmpc_emu_set_friction_ub.restype = None
     fub = None if friction_ub is None else np.ascontiguousarray(friction_ub, dtype=np.float64)
@@ -57,7 +61,7 @@ def solve_scp(batch, scp_params, qp_overrides=None, friction_ub=None, team_lanes
 
 def _solve_scp(lib, batch, scp_params, qp_overrides):
     B, N, nu = batch.B, batch.N, batch.nu
-    dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0)
+    dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0, L.contact_model_of(batch.proto["robot"]))
     model = L.make_model_struct(batch.proto)
     scp = L.make_scp_struct(scp_params)
     qp = L.make_qp_struct(qp_overrides)

@@ -101,11 +101,18 @@ def scenarios():
     save("scen5_infeasible_free_fall", "solo12_trot", 10, m, {}, free_fall=True)
 
 
-def n100():
-    for conf_name, mode, B, ids in (("solo12_pace", "A", 1024, [int(i) for i in np.linspace(0, 1023, 32)]),
-                                    ("solo12_bound", "B", 4096, [int(i) for i in np.linspace(0, 4095, 8)]),
-                                    ("bolt", "B", 8192, [int(i) for i in np.linspace(0, 8191, 8)])):
-        conf = synthetic.load_conf(conf_name, N=100)
+N100 = (("solo12_pace", "A", 1024, [int(i) for i in np.linspace(0, 1023, 32)], 100),
+        ("solo12_bound", "B", 4096, [int(i) for i in np.linspace(0, 4095, 8)], 100),
+        ("bolt", "B", 8192, [int(i) for i in np.linspace(0, 8191, 8)], 100))
+# BASELINE configuration 5 (talos, CoP / wrench contact model): the smallest batch of its sweep at the benchmark
+# horizon, and a short-horizon case for the CPU suite (host build of the wrench solver)
+TALOS = (("talos", "B", 256, [int(i) for i in np.linspace(0, 255, 8)], 100),
+         ("talos", "B", 8, [0, 3, 7], 30))
+
+
+def n100(table=N100):
+    for conf_name, mode, B, ids, N in table:
+        conf = synthetic.load_conf(conf_name, N=N)
         Xs, Us, its, ok = [], [], [], []
         for b in ids:
             if mode == "A":
@@ -117,10 +124,10 @@ def n100():
             good = sol is not False and len(sol["state"]) > 0
             ok.append(good)
             its.append(sol["iterations"] if sol is not False else -1)
-            Xs.append(sol["state"][-1] if good else np.zeros((9, 101)))
-            Us.append(sol["control"][-1] if good else np.zeros((conf.n_u, 100)))
+            Xs.append(sol["state"][-1] if good else np.zeros((9, N + 1)))
+            Us.append(sol["control"][-1] if good else np.zeros((conf.n_u, N)))
             print(conf_name, b, "ok", good, "iterations", its[-1], flush=True)
-        np.savez_compressed(os.path.join(HERE, "n100_%s_mode%s.npz" % (conf_name, mode)), name=conf_name, mode=mode, batch=B,
+        np.savez_compressed(os.path.join(HERE, "n%d_%s_mode%s.npz" % (N, conf_name, mode)), name=conf_name, mode=mode, batch=B,
                             ids=np.array(ids), ok=np.array(ok), iterations=np.array(its), X=np.array(Xs), U=np.array(Us))
 
 
@@ -129,3 +136,5 @@ if __name__ == "__main__":
         scenarios()
     if len(sys.argv) < 2 or sys.argv[1] == "n100":
         n100()
+    if len(sys.argv) < 2 or sys.argv[1] == "talos":
+        n100(TALOS)

@@ -54,12 +54,12 @@ def check_scenario(out, b, g, relerr, tol=1e-6):
             assert abs(out["info"][b, 1] - float(g["acc"][-1])) < 1e-4 * float(g["acc"][-1])
 
 
-def n100_samples(name, mode):
-    """-> (conf, batch of the sampled instances, fixture)."""
+def n100_samples(name, mode, N=100):
+    """-> (conf, full batch, batch of the sampled instances, fixture)."""
     from centroidal_mpc_b200 import synthetic
     from centroidal_mpc_b200.batch import ProblemBatch
-    g = np.load(os.path.join(GOLDEN, "n100_%s_mode%s.npz" % (name, mode)))
-    conf = synthetic.load_conf(name, N=100)
+    g = np.load(os.path.join(GOLDEN, "n%d_%s_mode%s.npz" % (N, name, mode)))
+    conf = synthetic.load_conf(name, N=N)
     full = synthetic.make_batch(conf, int(g["batch"]), mode=mode)
     ids = np.asarray(g["ids"])
     sub = ProblemBatch.from_arrays(full.proto, full.x_init[ids], full.x_final[ids], full.X_ref[ids], full.U_init[ids])
