@@ -41,7 +41,7 @@ class cmpc_qp_settings(C.Structure):
                 ("polish_refine_iter", C.c_int32), ("adaptive_rho", C.c_int32),
                 ("adaptive_rho_start", C.c_int32), ("polish_active_set_rounds", C.c_int32),
                 ("active_set_start", C.c_int32), ("active_set_step", C.c_int32),
-                ("active_set_tol", C.c_double)]
+                ("active_set_tol", C.c_double), ("warm_start_tol", C.c_double), ("warm_start", C.c_int32)]
 
 
 class cmpc_lqr_weights(C.Structure):
@@ -124,6 +124,7 @@ def make_qp_struct(overrides=None, lib=None):
         q.adaptive_rho_start = 200
         q.polish_active_set_rounds = 9
         q.active_set_start, q.active_set_step, q.active_set_tol = 8, 8, 1e-9
+        q.warm_start_tol, q.warm_start = 1e-7, 0
     for k, v in (overrides or {}).items():
         if not hasattr(q, k):
             raise CmpcError("unknown QP setting %r" % k)

@@ -147,7 +147,7 @@ struct cmpc_handle_s {
   int num_sms;
   Batch bt;          // device pointers
   int tiles;
-  long smem_max, smem_sm;
+  long smem_max, smem_sm, wr_smem;
   cudaStream_t last_stream;
   void* ws;          // one allocation
   long ws_bytes;
@@ -209,6 +209,7 @@ int cmpc_create(const cmpc_dims* dims, cmpc_handle* out) {
     w.tiles = z.tiles; w.ws = z.ws; w.nst = z.nst; w.info = z.info;
     smem_need = z.smem;
   }
+  h->wr_smem = smem_need;
   const long nd = w.ws + w.info;
   const long ni = w.nst + 3L * B + 64;
   h->ws_bytes = nd * 8 + ni * 4;
@@ -387,8 +388,22 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   }
   // Chunks of whole tiles: the trajectories of chunk c+1 are uploaded (and, without mapped buffers, the
   // results of chunk c-1 downloaded) while chunk c is being solved.
+  // One chunk per resident set of tiles (a "wave", cmpc_launch.cuh), at most MAX_CHUNKS: the warps of a wave must
+  // start together (they share instruction fetches), so a batch that fits one wave is ONE upload and ONE launch --
+  // measured on B200, 4096 instances: 11.2 ms with 1 chunk, 12.1 / 13.0 / 13.4 ms with 2 / 4 / 8 chunks
+  // (scripts/e2e_chunks.py).  CMPC_HOST_CHUNKS overrides (for that comparison).
   const int tiles = h->tiles;
-  int chunks = tiles >= 4 * MAX_CHUNKS ? MAX_CHUNKS : (tiles >= 8 ? 4 : 1);
+  long smem = h->wr_smem;            // shared memory per CTA of the path this batch takes -> CTAs per SM -> resident set
+  if (!wrench) {
+    Params prm;
+    if (fill_params(&prm, &h->dims, model, scp, qp, contact_R == nullptr)) return fail(-1, "bad dims or weights");
+    smem = scp_smem_bytes(N, !(prm.fast && !h->bt.fub));
+  }
+  int per_sm = (int)(h->smem_sm / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const int cap = h->num_sms * per_sm;
+  int chunks = (tiles + cap - 1) / cap;
+  if (chunks > MAX_CHUNKS) chunks = MAX_CHUNKS;
   if (env_chunks >= 1 && env_chunks <= MAX_CHUNKS && env_chunks <= tiles) chunks = env_chunks;
   const int per = (tiles + chunks - 1) / chunks;
   int rc = 0;

@@ -130,6 +130,9 @@ struct Params {
   double alpha, rho0, eps_abs, eps_rel, delta, inv_delta, adapt_tol, rho_e_rel, rho_k_rel, rho_e_pol_rel, as_tol;
   int max_iter, check_every, polish, refine, adaptive_rho, adapt_start;
   int as_start, as_step, as_rounds;   // early active-set polish: first attempt, retry interval, rounds
+  int warm;                           // first QP starts with a polish on the active set read off the warm start
+  double warm_tol;
+  double as_tol_loose;                // certificate tolerance at the rounding floor of the multiplier iteration (= as_tol: off)
   // SCP parameters (scp_solver.py:120-128)
   double radius0, omega0, omega_max, acc_rho0, acc_rho1, beta_succ, beta_fail, gamma_fail, conv_thresh;
   int max_scp;

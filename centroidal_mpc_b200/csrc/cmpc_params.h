@@ -24,6 +24,8 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
   s->active_set_start = 8;      // first certified-polish attempt after 8 ADMM iterations (swept on B200: DESIGN.md section 6)
   s->active_set_step = 8;      // doubled after every failed attempt
   s->active_set_tol = 1e-9;
+  s->warm_start_tol = 1e-7;
+  s->warm_start = 0;
 }
 
 inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const cmpc_scp_params* scp,
@@ -74,6 +76,9 @@ inline int fill_params(Params* p, const cmpc_dims* d, const cmpc_model* m, const
   p->as_rounds = qp->polish_active_set_rounds;
   p->as_start = qp->active_set_start; p->as_step = qp->active_set_step > 0 ? qp->active_set_step : 10;
   p->as_tol = qp->active_set_tol > 0.0 ? qp->active_set_tol : 1e-9;
+  p->as_tol_loose = WR ? 100.0 * p->as_tol : p->as_tol;
+  p->warm = qp->warm_start != 0 && qp->polish != 0;
+  p->warm_tol = qp->warm_start_tol > 0.0 ? qp->warm_start_tol : 1e-7;
   if (scp) {
     p->radius0 = scp->trust_region_radius0; p->omega0 = scp->omega0; p->omega_max = scp->omega_max;
     p->acc_rho0 = scp->rho0; p->acc_rho1 = scp->rho1; p->beta_succ = scp->beta_succ;

@@ -1820,12 +1820,14 @@ CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool 
           const double ub[3] = {Uk[uix(cid, 0)], Uk[uix(cid, 1)], Uk[uix(cid, 2)]};
 #pragma unroll
           for (int row = 0; row < 4; ++row) {
-            double cf = 0.0;
+            double cf = 0.0, scale = 1.0;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) cf += G[row * 3 + a] * ub[a];
+            for (int a = 0; a < 3; ++a) { cf += G[row * 3 + a] * ub[a]; scale += fabs(G[row * 3 + a] * ub[a]); }
+            const double cf0 = cf;
             if (WR && (cid & 1)) cf -= P.foot_range[row];
             else if (I.fub) cf -= I.fub[((long)k * P.nc + cid) * 4 + row];
-            CMPC_R(r, L.vf + 4 * sl + row) = fmin(cf, 0.0);
+            // (warm start: a row the warm start sits on starts in the active set -- "active <=> v > 0")
+            CMPC_R(r, L.vf + 4 * sl + row) = (P.warm && cf >= -P.warm_tol * (scale + fabs(cf0 - cf))) ? 1e-300 : fmin(cf, 0.0);
           }
         }
       }
@@ -1910,7 +1912,8 @@ struct Drv {
   int it, next_as, as_step, nfact, solved, check, term;
   double pri0, dua0, npri0, ndua0;
   // polish
-  int round, sw, prev_chg, chg, certified, upd;
+  int round, sw, prev_chg, chg, certified, upd, stag;
+  double prev_pri;
   double ye_keep[9];
   double rho_new, rhok_new;
 };
@@ -1927,7 +1930,8 @@ CMPC_HD void drv_init(const Params& P, Sv& S, Drv& D) {
   D.next_as = -1;
   D.as_step = P.as_step;
   D.pri0 = D.dua0 = D.npri0 = D.ndua0 = 0.0;
-  D.round = D.sw = D.chg = D.certified = D.upd = 0;
+  D.round = D.sw = D.chg = D.certified = D.upd = D.stag = 0;
+  D.prev_pri = 0.0;
   D.prev_chg = 1 << 30;
 #pragma unroll
   for (int i = 0; i < 9; ++i) D.ye_keep[i] = 0.0;
@@ -1958,6 +1962,16 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
         S.tau = S.weight / S.rhok;
         D.nfact = 0; D.solved = 0; D.polished = 0; D.it = 0;
         S.fail = 0;
+        if (P.warm && D.it_scp == 0) {   // warm start: polish on the active set of the warm start first, no ADMM iteration
+          D.term = 0;
+          D.pri0 = D.dua0 = D.npri0 = D.ndua0 = 0.0;
+          D.next_as = -1;
+          D.as_step = P.as_step;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) D.ye_keep[i] = S.ye[i];
+          D.pc = PC_AFTER_BUILD;
+          return OP_BUILD_AS;
+        }
         D.pc = PC_AFTER_FACTOR0;
         return OP_FACTOR_ADMM;
       case PC_AFTER_FACTOR0:
@@ -2015,6 +2029,8 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
       case PC_AFTER_PMM0:
         ++S.n_pmm;
         D.sw = 0;
+        D.stag = 0;
+        D.prev_pri = S.pri;
         if (S.kbad) { D.pc = PC_POLISH_END; break; }   // the trust-region branches were guessed wrongly: back to ADMM
         if (D.chg) { D.pc = PC_ROUND_CHECK; break; }   // rows changed: refactor right away
         D.pc = PC_SW_TOP;
@@ -2034,13 +2050,21 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
 #endif
         if (S.kbad) { D.pc = PC_POLISH_END; break; }
         if (D.chg || S.pri <= P.as_tol * (1.0 + S.npri)) { D.pc = PC_ROUND_CHECK; break; }
+        // stiff penalties (wrench model): the multiplier iteration contracts fast and then sits on its rounding
+        // floor; a residual that stopped halving below the loose tolerance is as good as it gets
+        if (P.as_tol_loose > P.as_tol && S.pri > 0.5 * D.prev_pri && S.pri <= P.as_tol_loose * (1.0 + S.npri)) {
+          D.stag = 1;
+          D.pc = PC_ROUND_CHECK;
+          break;
+        }
+        D.prev_pri = S.pri;
         ++D.sw;
         D.pc = PC_SW_TOP;
         break;
       case PC_ROUND_CHECK:
         if (!(S.pri == S.pri)) { D.pc = PC_POLISH_END; break; }   // NaN
         if (D.chg == 0) {
-          D.certified = S.pri <= P.as_tol * (1.0 + S.npri);   // absolute + relative, the form of OSQP's test
+          D.certified = S.pri <= (D.stag ? P.as_tol_loose : P.as_tol) * (1.0 + S.npri);   // absolute + relative, the form of OSQP's test
           D.pc = PC_POLISH_END;
           break;
         }

@@ -78,6 +78,12 @@ typedef struct {
   int32_t active_set_step;       /* ADMM iterations between early polishes */
   double active_set_tol;         /* certificate: primal residual / row violation <= tol * (1 + norm), the form of
                                     OSQP's test (default 1e-9: 100x tighter than the reference's eps = 1e-7) */
+  double warm_start_tol;         /* warm_start: a friction / CoP row of the warm start U_init with G u - ub >= -tol (1 + |ub|)
+                                    starts in the active set (default 1e-7) */
+  int32_t warm_start;            /* 1: receding-horizon use -- U_init is (the shift of) a previous solution: the first QP
+                                    of the solve starts with a certified polish on the active set read off U_init, before
+                                    any ADMM iteration; when the certificate fails, ADMM runs as in a cold solve.  The
+                                    answer is the same certified KKT point either way (default 0) */
 } cmpc_qp_settings;
 
 /* status[] values */
