@@ -59,7 +59,13 @@ constexpr int X_Y = X_PS + 81;     // Y = P [B A]  (9 x (na + 9))
 constexpr int X_FAC_END = X_Y + 9 * 21;
 // shared memory of a tile (in field rows of TL doubles): common scratch, then a region that holds the
 // ring of a sweep or the factorisation scratch plus its small ring
-CMPC_CX int ring_fields(bool gen) { return 2 * imax(slot_fields(SK_BWD_ADMM, gen), slot_fields(SK_BWD_PMM, gen)); }
+// (measured on B200 with 3 and 4 slots: at 4096 instances the larger ring costs a resident CTA per SM -- two waves,
+// 13.5 instead of 9.7 ms; at 1024 instances, where occupancy does not matter, 5.86 against 5.80 ms: the bulk copies
+// are not what the knot steps wait for)
+#ifndef CMPC_RING_SLOTS
+#define CMPC_RING_SLOTS 2
+#endif
+CMPC_CX int ring_fields(bool gen) { return CMPC_RING_SLOTS * imax(slot_fields(SK_BWD_ADMM, gen), slot_fields(SK_BWD_PMM, gen)); }
 CMPC_CX int ring_depth(int sk, bool gen) {
   const int avail = (sk == SK_FAC_ADMM || sk == SK_FAC_PMM) ? ring_fields(gen) - (X_FAC_END - X_COMMON) : ring_fields(gen);
   return imin(4, imax(2, avail / slot_fields(sk, gen)));
