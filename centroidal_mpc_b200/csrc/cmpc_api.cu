@@ -159,7 +159,7 @@ struct cmpc_handle_s {
   // host entry point: the batch is cut into up to MAX_CHUNKS tile-aligned chunks, each with its own
   // stream (H2D of chunk c+1 and D2H of chunk c-1 overlap the solve of chunk c)
   cudaStream_t cs[8];
-  cudaEvent_t ev_small;
+  cudaEvent_t ev_small, ev_up[8], ev_done[8];
   int have_streams;
 };
 static const int MAX_CHUNKS = 8;
@@ -249,7 +249,7 @@ int cmpc_destroy(cmpc_handle h) {
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->have_streams) {
-    for (int c = 0; c < MAX_CHUNKS; ++c) cudaStreamDestroy(h->cs[c]);
+    for (int c = 0; c < MAX_CHUNKS; ++c) { cudaStreamDestroy(h->cs[c]); cudaEventDestroy(h->ev_up[c]); cudaEventDestroy(h->ev_done[c]); }
     cudaEventDestroy(h->ev_small);
   }
   free(h);
@@ -349,6 +349,10 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   if (!h->have_streams) {
     for (int c = 0; c < MAX_CHUNKS; ++c) CUDA_TRY(cudaStreamCreate(&h->cs[c]));   // blocking: ordered after earlier work on the null stream
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_small, cudaEventDisableTiming));
+    for (int c = 0; c < MAX_CHUNKS; ++c) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_up[c], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[c], cudaEventDisableTiming));
+    }
     h->have_streams = 1;
   }
   // Small inputs and the contact plan first, on chunk 0's stream; the other chunks wait for them.
@@ -386,12 +390,15 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
   if (zero_copy) {
     oX = (double*)mX; oU = (double*)mU; oit = (int*)mi; ost = (int*)ms; ona = n_accepted ? (int*)mn : oi + 2 * B;
   }
-  // Chunks of whole tiles: the trajectories of chunk c+1 are uploaded (and, without mapped buffers, the
-  // results of chunk c-1 downloaded) while chunk c is being solved.
+  // Chunks of whole tiles.  ALL kernels go to one stream, one wave after the other; the trajectories of chunk
+  // c+1 are uploaded on a second stream while chunk c is being solved, and, without mapped buffers, the results
+  // of chunk c-1 go down on a third.  (Kernels of different chunks must not overlap: a chunk on its own stream
+  // starts in the tail of the previous one, its warps drift apart and the instruction caches thrash -- measured
+  // at 16 384 instances: 60 ms with one stream per chunk, 44 ms with a single upload and one stream.)
   // One chunk per resident set of tiles (a "wave", cmpc_launch.cuh), at most MAX_CHUNKS: the warps of a wave must
   // start together (they share instruction fetches), so a batch that fits one wave is ONE upload and ONE launch --
   // measured on B200, 4096 instances: 11.2 ms with 1 chunk, 12.1 / 13.0 / 13.4 ms with 2 / 4 / 8 chunks
-  // (scripts/e2e_chunks.py).  CMPC_HOST_CHUNKS overrides (for that comparison).
+  // (scripts/e2e_chunks.py).  CMPC_HOST_CHUNKS overrides the chunk count (for that comparison).
   const int tiles = h->tiles;
   long smem = h->wr_smem;            // shared memory per CTA of the path this batch takes -> CTAs per SM -> resident set
   if (!wrench) {
@@ -411,21 +418,27 @@ int cmpc_solve_scp_host(cmpc_handle h, const cmpc_model* model, const cmpc_scp_p
     const int t0 = c * per, t1 = (c + 1) * per < tiles ? (c + 1) * per : tiles;
     if (t0 >= t1) break;
     const long b0 = (long)t0 * TL, b1 = (long)t1 * TL < B ? (long)t1 * TL : B, nb = b1 - b0;
-    cudaStream_t st = h->cs[c];
-    if (c) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_small, 0));
+    cudaStream_t s_kern = h->cs[0], s_up = chunks > 1 ? h->cs[1] : h->cs[0], s_down = h->cs[2];
+    if (c == 0 && chunks > 1) CUDA_TRY(cudaStreamWaitEvent(s_up, h->ev_small, 0));   // (staging buffers: after the previous call's work)
     const long xo = b0 * (N + 1) * 9, uo = b0 * N * nu;
-    CUDA_TRY(cudaMemcpyAsync(dX + xo, X_ref + xo, nb * (N + 1) * 9 * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(dU + uo, U_init + uo, nb * N * nu * 8, cudaMemcpyHostToDevice, st));
-    rc = launch_tiles(h, bt, model, scp, qp, oX, oU, oit, ost, ona, t0, t1, c, st);
+    CUDA_TRY(cudaMemcpyAsync(dX + xo, X_ref + xo, nb * (N + 1) * 9 * 8, cudaMemcpyHostToDevice, s_up));
+    CUDA_TRY(cudaMemcpyAsync(dU + uo, U_init + uo, nb * N * nu * 8, cudaMemcpyHostToDevice, s_up));
+    if (chunks > 1) {
+      CUDA_TRY(cudaEventRecord(h->ev_up[c], s_up));
+      CUDA_TRY(cudaStreamWaitEvent(s_kern, h->ev_up[c], 0));
+    }
+    rc = launch_tiles(h, bt, model, scp, qp, oX, oU, oit, ost, ona, t0, t1, 0, s_kern);
     if (rc) break;
     if (zero_copy) continue;
-    CUDA_TRY(cudaMemcpyAsync(X_out + xo, oX + xo, nb * (N + 1) * 9 * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(U_out + uo, oU + uo, nb * N * nu * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(scp_iters + b0, oit + b0, nb * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(status + b0, ost + b0, nb * 4, cudaMemcpyDeviceToHost, st));
-    if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted + b0, ona + b0, nb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(h->ev_done[c], s_kern));
+    CUDA_TRY(cudaStreamWaitEvent(s_down, h->ev_done[c], 0));
+    CUDA_TRY(cudaMemcpyAsync(X_out + xo, oX + xo, nb * (N + 1) * 9 * 8, cudaMemcpyDeviceToHost, s_down));
+    CUDA_TRY(cudaMemcpyAsync(U_out + uo, oU + uo, nb * N * nu * 8, cudaMemcpyDeviceToHost, s_down));
+    CUDA_TRY(cudaMemcpyAsync(scp_iters + b0, oit + b0, nb * 4, cudaMemcpyDeviceToHost, s_down));
+    CUDA_TRY(cudaMemcpyAsync(status + b0, ost + b0, nb * 4, cudaMemcpyDeviceToHost, s_down));
+    if (n_accepted) CUDA_TRY(cudaMemcpyAsync(n_accepted + b0, ona + b0, nb * 4, cudaMemcpyDeviceToHost, s_down));
   }
-  for (int c = 0; c < chunks; ++c) CUDA_TRY(cudaStreamSynchronize(h->cs[c]));
+  for (int c = 0; c < 3; ++c) CUDA_TRY(cudaStreamSynchronize(h->cs[c]));
   return rc;
 }
 

@@ -9,7 +9,7 @@ import numpy as np, torch
 from centroidal_mpc_b200 import synthetic
 from centroidal_mpc_b200.device import BatchSolver
 conf = synthetic.load_conf("solo12_trot", N=100)
-B = 4096
+B = int(os.environ.get("AB_BATCH", "4096"))
 batch = synthetic.make_batch(conf, B)
 keep = []
 for name in ("x_init", "x_final", "X_ref", "U_init", "contact_pos", "contact_active"):

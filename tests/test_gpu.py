@@ -402,10 +402,11 @@ def test_stochastic_mode_on_device(gpu, name):
     assert relerr(sol_s["control"][-1], sol_n["control"][-1]) > 5e-4
 
 
-@pytest.mark.parametrize("B", [1, 33, 300, 1100])
+@pytest.mark.parametrize("B", [1, 33, 300, 1100, 9001])
 def test_host_entry_point_chunking(gpu, B):
-    """cmpc_solve_scp_host cuts the batch into tile-aligned chunks on their own streams (copies
-    overlap the solves): ragged last tile, one chunk / four / eight; unshared plans at B=33.
+    """cmpc_solve_scp_host cuts the batch into chunks of one resident set of tiles each (kernels on one stream,
+    uploads of the next chunk on a second): ragged last tile, one chunk, three chunks (B = 9001); unshared plans
+    at B=33; pageable result buffers (staged downloads) here, pinned ones in bench.py.
     Results must equal the device-pointer entry bit for bit, all outputs included."""
     from centroidal_mpc_b200 import synthetic
     from centroidal_mpc_b200.batch import ProblemBatch
