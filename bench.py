@@ -380,6 +380,10 @@ def run_gpu_arm(args):
                               "frac": flops / (kernel_ms * 1e-3) / 1e12 / max(tf.value, 1e-9)}},
         "solver_stats": {"admm_iters_mean": float(stats["qp_iters"].mean()), "admm_iters_max": int(stats["qp_iters"].max()),
                          "factorisations_mean": float(stats["n_factor"].mean()),
+                         # a warp works for the four instances of its tile until the last one is done, and a wave ends with
+                         # its slowest tile: the per-tile maximum and the batch maximum next to the mean
+                         "factorisations_tile_max_mean": float(np.pad(stats["n_factor"], (0, (-len(stats["n_factor"])) % 4)).reshape(-1, 4).max(1).mean()),
+                         "factorisations_max": int(stats["n_factor"].max()),
                          "multiplier_sweeps_mean": float(stats["info"][:, 8].mean()),
                          "polish_attempts_mean": float(stats["info"][:, 9].mean()),
                          "scp_iters_mean": float(res["scp_iters"].mean()), "failed": int((res["status"] != 0).sum()),

@@ -202,6 +202,8 @@ CMPC_HD void friction_backoff_knot(const Params& P, double xi, int k, const doub
         if (cR) G = sgn * cR[9 * c + 3 * u + ax] - P.kf * cR[9 * c + 3 * u + 2];   // (pyr R')_ju = sum_a pyr_ja R_ua
         else G = (u == ax ? sgn : 0.0) - (u == 2 ? P.kf : 0.0);
         if (G > 1e-6 && sq[u] > 1e-6) ub[4 * c + j] -= xi * (2.0 * G * sq[u]);
+        if (!(sq[u] == sq[u])) ub[4 * c + j] = sq[u];   // non-finite gains (R + B'PB not positive definite) must not pass as
+                                                        // "no back-off": the NaN bound makes this instance's solve end with status != 0
       }
     }
   }

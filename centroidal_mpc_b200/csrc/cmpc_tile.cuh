@@ -372,6 +372,7 @@ struct Sv {
   int kbad;                        // polish: the trust-region rows of some knot contradict the branch they were given
   int lost;                        // a bulk copy never landed (device)
   int nconv;                       // all-zero warm start: the reference's convergence() is NaN, never below the threshold
+  int badin;                       // a non-finite input (reference point, warm start, friction bound): no solve, status QP_NUMERIC
   int n_pmm, n_polish;             // statistics: multiplier-method sweeps, polish attempts
   double ye[9];                    // multiplier of x_N = x_final
 };
@@ -1843,11 +1844,24 @@ CMPC_OP void setup_knots(const Params& P, const TileCtx& T, const Inst& I, bool 
   *mq_out = team_max(I, xs, mq);
   *mc_out = team_max(I, xs, mc);
   const int nz = team_or(I, xs, nzx | (nzu << 1));
-  *nconv_out = nz != 3;
+  // non-finite inputs: the maxima above swallow NaN (fmax), so test the data itself
+  int bad = 0;
+  for (int k = sub_of(I); live && k <= N; k += NL) {
+    for (int i = 0; i < 9; ++i) bad |= !(fabs(I.Xr[k * 9 + i]) <= 1.79e308);
+    if (k < N) {
+      for (int j = 0; j < P.nu; ++j) bad |= !(fabs(I.Ui[k * P.nu + j]) <= 1.79e308);
+      if (I.fub)
+        for (int j = 0; j < 4 * P.nc; ++j) bad |= !(fabs(I.fub[(long)k * P.nc * 4 + j]) <= 1.79e308);
+    }
+  }
+  for (int i = 0; i < 9; ++i) bad |= !(fabs(I.xi[i]) <= 1.79e308) || !(fabs(I.xf[i]) <= 1.79e308);
+  bad = team_or(I, xs, bad);
+  *nconv_out = (nz != 3 ? 1 : 0) | (bad ? 2 : 0);
 }
 CMPC_FN void setup_finish(const Inst& I, Sv& S, double mq, double mc, int nconv) {
   S.nq = mq;
-  S.nconv = nconv;
+  S.nconv = nconv & 1;
+  S.badin = (nconv >> 1) & 1;
   double mi = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) mi = fmax(mi, fabs(I.xi[i]));
@@ -1956,6 +1970,11 @@ CMPC_FN int advance(const Params& P, Sv& S, Drv& D) {
     }
     switch (D.pc) {
       case PC_SCP_TOP:
+        if (S.badin) {   // NaN / Inf in the problem data: the arithmetic below would swallow it (fmin / fmax) and "solve"
+          D.status = ST_QP_NUMERIC;
+          D.pc = PC_END;
+          break;
+        }
         // convergence() compares the warm start with itself (scp_solver.py:90-93): 0 < threshold whenever
         // both norms are nonzero, 0/0 = NaN (never converged) when one of them vanishes (S.nconv)
         if (!(D.it_scp < P.max_scp && D.weight < P.omega_max && !(D.it_scp != 0 && D.success && !S.nconv && 0.0 < P.conv_thresh))) {

@@ -168,7 +168,8 @@ typedef struct {
  * back as all_solution['gains'] / ['covs'] (src/scp_solver.py:165-166).
  * gains [B][N][nu][9]; covs [B][N+1][9][9] with covs[b][0] = 0 (nullable: gains only).
  * `w` is a HOST pointer; `scratch` is CMPC_LQR_SCRATCH_BYTES of caller-owned DEVICE memory.
- * A knot whose R + B'PB is not positive definite gets NaN gains. */
+ * A knot whose R + B'PB is not positive definite gets NaN gains; cmpc_friction_backoffs turns those into NaN
+ * bounds, so that the instance's solve ends with status != 0 instead of running without back-offs. */
 int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X,
                   const double* U, const double* contact_pos, const int32_t* contact_active, double* gains,
                   double* covs, void* scratch, void* stream);

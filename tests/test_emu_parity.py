@@ -444,3 +444,24 @@ def test_trust_region_scenarios_match_oracle(path):
         assert abs(dk - float(g["max_dkappa_l1"])) < 1e-6
     if "then_accept" in path:
         assert int(g["iterations"]) == 2 and int(g["n_accepted"]) == 1
+
+
+def test_non_finite_inputs_fail_only_their_instance():
+    """NaN / Inf in an instance's data (or NaN friction bounds from non-finite LQR gains) must not be swallowed by
+    the fmin / fmax of the iteration: that instance ends with status QP_NUMERIC, its neighbours in the tile solve."""
+    from centroidal_mpc_b200.device import STOCHASTIC_QP_DEFAULTS, chance_constraint_xi
+    conf = synthetic.load_conf("solo12_trot", N=30)
+    good = E.solve_scp(synthetic.make_batch(conf, 3), conf.scp_params)
+    bad = synthetic.make_batch(conf, 3)
+    bad.X_ref[2, 7, 3] = np.inf
+    out = E.solve_scp(bad, conf.scp_params)
+    np.testing.assert_array_equal(out["status"], [0, 0, 2])
+    np.testing.assert_array_equal(out["X"][:2], good["X"][:2])
+    sb = synthetic.make_batch(conf, 3, stochastic=True)
+    sto = sb.proto["stochastic"]
+    gains, covs = E.lqr_covs(sb, sb.X_ref, sb.U_init, sto["Q"], sto["R"], sto["cov_w"], sto["cov_eta"])
+    gains[1, 5] = np.nan                       # what a failed Cholesky in the gain recursion leaves
+    ub = E.friction_backoffs(sb, chance_constraint_xi(sto["beta_u"]), gains, covs)
+    assert np.isnan(ub[1]).any() and not np.isnan(ub[0]).any()
+    out = E.solve_scp(sb, conf.scp_params, qp_overrides=STOCHASTIC_QP_DEFAULTS, friction_ub=ub)
+    np.testing.assert_array_equal(out["status"], [0, 2, 0])
