@@ -251,12 +251,30 @@ def run_gpu_arm(args):
 
     # The single end-of-batch collective runs on a side stream: the gather of step i overlaps the solve of
     # step i+1 (the solver writes into alternating result buffers, so the gather reads a finished one).
-    side = torch.cuda.Stream() if world > 1 else None
+    # Multi-GPU result path.  "peer" (default): every rank's kernel writes its shard straight into a buffer on rank 0's
+    # GPU over NVLink at write-back (parallel.PeerResults) -- no gather kernel competes with the next solve for the SMs.
+    # "nccl": the single end-of-batch gather on a side stream (falls back to it when the peer mapping is refused).
+    peer = None
+    if world > 1 and args.gather == "peer":
+        try:
+            peer = parallel.PeerResults(Bglobal, HORIZON, batch.nu, dist, dst=0, slots=2)
+        except Exception as e:   # noqa: BLE001  (reported in the JSON line)
+            peer, args.gather = None, "nccl (peer mapping failed: %s)" % str(e)[:80]
+        ok = torch.tensor([1 if peer is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0 and peer is not None:
+            peer.close()
+            peer, args.gather = None, "nccl (peer mapping failed on another rank)"
+    side = torch.cuda.Stream() if world > 1 and peer is None else None
     gathered = [None]
     res_bufs = [(solver.X, solver.U, solver.ints), (torch.zeros_like(solver.X), torch.zeros_like(solver.U), torch.zeros_like(solver.ints))]
     parity = [0]
 
     def step_device():
+        if peer is not None:
+            solver.solve(conf.scp_params, out=peer.pointers(parity[0], first))
+            parity[0] ^= 1
+            return
         if world > 1:
             solver.X, solver.U, solver.ints = res_bufs[parity[0]]
         solver.solve(conf.scp_params)
@@ -270,7 +288,7 @@ def run_gpu_arm(args):
             parity[0] ^= 1
 
     def drain():
-        if world > 1:
+        if world > 1 and peer is None:
             torch.cuda.current_stream().wait_stream(side)
 
     sampler = ClockSampler(local_rank)
@@ -298,7 +316,11 @@ def run_gpu_arm(args):
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     total_ms = t_all0.elapsed_time(t_all1)
     stats = solver.stats()
-    res = solver.results()
+    if peer is not None:      # the whole job's solutions sit in rank 0's buffer (every rank has synchronised: barrier above)
+        view = peer.tensors(parity[0] ^ 1)
+        res = None if view is None else {k: v.cpu().numpy() for k, v in view.items()}
+    else:
+        res = solver.results()
 
     # end-to-end through the host entry point of the C ABI
     for _ in range(2):
@@ -359,8 +381,10 @@ def run_gpu_arm(args):
         "config": {"workload": "%s N=%d" % (workload, HORIZON), "batch_per_gpu": B, "global_batch": Bglobal,
                    "mode": "B (independent reference trajectories, rng(1000+b))" if args.mode == "B"
                            else "A (one shared reference, perturbed initial states, rng(1000+b))",
-                   "parallelism": "instances sharded across %d GPU(s), no collective on the solve path, one gather "
-                                  "(side stream, under the next step's solve)" % world,
+                   "parallelism": "instances sharded across %d GPU(s), no collective on the solve path, %s" % (
+                       world, "single GPU" if world == 1 else
+                       ("results written by the kernels straight into rank 0's buffer over NVLink peer memory (no gather)"
+                        if peer is not None else "one NCCL gather (side stream, under the next step's solve): " + args.gather)),
                    "l2": "solver workspace %.2f GB per GPU (>> 126 MB L2) is streamed by every sweep; no flush needed"
                          % (lib.cmpc_workspace_bytes(solver.handle) / 1e9)},
         "latency_ms_p50": srt[len(srt) // 2],
@@ -406,6 +430,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, choices=["solo12_trot", "solo12_pace", "solo12_bound", "bolt", "talos"])
     ap.add_argument("--mode", default="B", choices=["A", "B"], help="B: independent references; A: perturbed initial states")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--gather", default="peer", help="multi-GPU result path: peer (kernels write into rank 0's buffer) or nccl")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -55,7 +55,8 @@ LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
 EXPORTS = ["cmpc_debug_profile", "cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
            "cmpc_set_problem", "cmpc_set_friction_ub", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
            "cmpc_linearize", "cmpc_rollout", "cmpc_linearize_wrench", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
-           "cmpc_last_error", "cmpc_version", "cmpc_build_id"]
+           "cmpc_last_error", "cmpc_version", "cmpc_build_id", "cmpc_peer_alloc", "cmpc_peer_open", "cmpc_peer_close",
+           "cmpc_peer_free"]
 
 _lib = None
 
@@ -162,6 +163,10 @@ def load():
                                   dp, dp, dp, ip, dp, dp, vp, vp]
     lib.cmpc_friction_backoffs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.c_double,
                                            dp, dp, dp, ip, dp, vp]
+    lib.cmpc_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.cmpc_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.cmpc_peer_close.argtypes = [C.c_void_p]
+    lib.cmpc_peer_free.argtypes = [C.c_void_p]
     lib.cmpc_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.cmpc_launch_count.restype = C.c_int64
     lib.cmpc_last_error.restype = C.c_char_p

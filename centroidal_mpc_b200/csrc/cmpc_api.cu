@@ -530,6 +530,38 @@ int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, doubl
 }
 
 // profiling build only (-DCMPC_PROFILE): reads and clears the cycle counters; returns -1 in a normal build
+// ---- result buffers in the memory of another GPU of the node (include/cmpc.h "multi-GPU")
+int cmpc_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (bytes <= 0 || !dev_ptr || !handle64) return fail(-1, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, (size_t)bytes));          // a plain allocation of its own: IPC handles name whole allocations
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(-100 - (int)e, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  memcpy(handle64, &hd, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int cmpc_peer_open(const unsigned char* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return fail(-1, "null argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int cmpc_peer_close(void* dev_ptr) {
+  if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+int cmpc_peer_free(void* dev_ptr) {
+  if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+  return 0;
+}
+
 int cmpc_debug_profile(double* out16) {
 #if defined(CMPC_PROFILE)
   unsigned long long h[32], z[32] = {0};

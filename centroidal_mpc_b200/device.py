@@ -87,16 +87,20 @@ class BatchSolver:
                 self.friction_ub = friction_backoffs_batched(batch, gains, covs, sto["beta_u"])
         L.check(self.lib.cmpc_set_friction_ub(self.handle, _ptr(self.friction_ub)), self.lib)
 
-    def solve(self, scp_params, qp_overrides=None, stream=None):
+    def solve(self, scp_params, qp_overrides=None, stream=None, out=None):
+        """``out``: raw device pointers dict(X, U, scp_iters, status, n_accepted) to write the results to instead of
+        this solver's own tensors -- e.g. this rank's slice of a buffer on another GPU (parallel.PeerResults)."""
         torch = _torch_cuda()
         scp = L.make_scp_struct(scp_params)
         qp = L.make_qp_struct(self._qp(qp_overrides), self.lib)
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         self._stream = None if stream is None else torch.cuda.ExternalStream(stream, device=self.device)
+        if out is None:
+            ptrs = (_ptr(self.X), _ptr(self.U), _ptr(self.ints[0]), _ptr(self.ints[1]), _ptr(self.ints[2]))
+        else:
+            ptrs = tuple(C.c_void_p(int(out[k])) for k in ("X", "U", "scp_iters", "status", "n_accepted"))
         with torch.cuda.device(self.device):
-            L.check(self.lib.cmpc_solve_scp(self.handle, C.byref(scp), C.byref(qp), _ptr(self.X), _ptr(self.U),
-                                            _ptr(self.ints[0]), _ptr(self.ints[1]), _ptr(self.ints[2]),
-                                            C.c_void_p(st)), self.lib)
+            L.check(self.lib.cmpc_solve_scp(self.handle, C.byref(scp), C.byref(qp), *ptrs, C.c_void_p(st)), self.lib)
         return self
 
     def _qp(self, overrides):

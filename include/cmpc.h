@@ -187,6 +187,19 @@ int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, doubl
 /* Diagnostics of a profiling build of the library (-DCMPC_PROFILE, scripts/variant.sh prof): cycle counters per
  * operation kind summed over all tiles since the last call, out32[32] (layout: scripts/prof_cycles.py).
  * Returns -1 in a normal build.  Not part of the reference's interface. */
+/* Multi-GPU (one process per GPU, instances sharded, no collective on the solve path): instead of gathering the
+   solutions afterwards, every rank can hand cmpc_solve_scp result pointers INTO A BUFFER OF THE DESTINATION RANK'S
+   GPU; the kernel's write-back then goes over NVLink as the tiles finish (posted stores, like the mapped host
+   buffers of cmpc_solve_scp_host) and no gather kernel competes with the next solve for the SMs.
+   cmpc_peer_alloc: the destination rank allocates the buffer and gets a 64-byte handle to send to the other
+   processes (any channel; bench.py uses torch.distributed.broadcast_object_list); cmpc_peer_open: the other
+   ranks map it (peer access is enabled by the driver) and get a device pointer valid in THEIR process; the caller
+   offsets it to its shard.  The destination reads the buffer after all ranks have synchronised their streams.
+   No counterpart in the reference (it solves one problem per call on the CPU). */
+int cmpc_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int cmpc_peer_open(const unsigned char* handle64, void** dev_ptr);
+int cmpc_peer_close(void* dev_ptr);
+int cmpc_peer_free(void* dev_ptr);
 int cmpc_debug_profile(double* out32);
 
 /* DFMA micro-benchmark on the current device: achieved FP64 TFLOP/s and the SM clock (MHz) seen. */

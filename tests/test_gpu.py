@@ -532,3 +532,30 @@ def test_baseline_configs_at_n100_match_tight_oracle(gpu, name, mode):
         assert out["scp_iters"][b] == int(g["iterations"][j])
         worst = max(worst, relerr(out["X"][b].T, g["X"][j]), relerr(out["U"][b].T, g["U"][j]))
     assert worst < TOL, worst
+
+
+def test_results_into_a_peer_buffer(gpu):
+    """parallel.PeerResults / BatchSolver.solve(out=...): the kernel writes the solutions into a buffer obtained from
+    cmpc_peer_alloc (on a multi-GPU box: rank 0's memory, mapped into the other ranks with cmpc_peer_open) at an
+    instance offset; the zero-copy views of that buffer equal the solver's own result tensors.  One process here
+    (the destination's half of the exchange); bench.py --gpus N runs the cross-process half."""
+    from centroidal_mpc_b200 import parallel, synthetic
+    from centroidal_mpc_b200.device import BatchSolver
+
+    class OneRank:
+        def get_rank(self): return 0
+        def get_world_size(self): return 1
+        def broadcast_object_list(self, box, src=0): return None
+    conf = synthetic.load_conf("solo12_trot", N=30)
+    batch = synthetic.make_batch(conf, 37)
+    solver = BatchSolver(batch)
+    own = solver.solve(conf.scp_params).results()
+    first, total = 5, 50                                  # this "rank" owns instances 5..41 of a job of 50
+    peer = parallel.PeerResults(total, conf.N, batch.nu, OneRank(), dst=0, slots=2)
+    solver.solve(conf.scp_params, out=peer.pointers(1, first))
+    gpu.cuda.synchronize()
+    view = peer.tensors(1)
+    for key in ("X", "U", "scp_iters", "status", "n_accepted"):
+        np.testing.assert_array_equal(view[key][first:first + 37].cpu().numpy(), own[key], err_msg=key)
+    peer.close()
+    solver.close()
