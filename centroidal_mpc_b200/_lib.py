@@ -54,7 +54,7 @@ LQR_SCRATCH_BYTES = 4096   # CMPC_LQR_SCRATCH_BYTES
 
 EXPORTS = ["cmpc_debug_profile", "cmpc_default_qp_settings", "cmpc_create", "cmpc_destroy", "cmpc_workspace_bytes",
            "cmpc_set_problem", "cmpc_set_friction_ub", "cmpc_solve_scp", "cmpc_solve_scp_host", "cmpc_get_stats",
-           "cmpc_linearize", "cmpc_rollout", "cmpc_linearize_wrench", "cmpc_lqr_covs", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
+           "cmpc_linearize", "cmpc_rollout", "cmpc_linearize_wrench", "cmpc_lqr_covs", "cmpc_lqr_covs_wrench", "cmpc_friction_backoffs", "cmpc_fp64_peak", "cmpc_launch_count",
            "cmpc_last_error", "cmpc_version", "cmpc_build_id", "cmpc_peer_alloc", "cmpc_peer_open", "cmpc_peer_close",
            "cmpc_peer_free"]
 
@@ -90,6 +90,12 @@ def make_lqr_struct(Q, R, cov_w, cov_eta, nu):
     """conf.Q, conf.R, conf.cov_w, conf.cov_white_noise -> cmpc_lqr_weights (dense, row-major)."""
     import numpy as np
     w = cmpc_lqr_weights()
+    cov_w = np.asarray(cov_w, dtype=np.float64)
+    if cov_w.shape[0] < nu and cov_w.shape == (cov_w.shape[0],) * 2:
+        # wrench model: three position-noise components per foot (n_w = 3 nc < n_u = 6 nc): leading block of n_u x n_u
+        full = np.zeros((nu, nu))
+        full[:cov_w.shape[0], :cov_w.shape[0]] = cov_w
+        cov_w = full
     for name, a, n in (("Q", Q, 9), ("R", R, nu), ("cov_w", cov_w, nu), ("cov_eta", cov_eta, 9)):
         a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
         if a.shape != (n, n):
@@ -161,6 +167,8 @@ def load():
     lib.cmpc_linearize_wrench.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), dp, dp, dp, dp, ip, dp, dp, dp, vp]
     lib.cmpc_lqr_covs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.POINTER(cmpc_lqr_weights),
                                   dp, dp, dp, ip, dp, dp, vp, vp]
+    lib.cmpc_lqr_covs_wrench.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.POINTER(cmpc_lqr_weights),
+                                         dp, dp, dp, dp, ip, dp, dp, vp, vp]
     lib.cmpc_friction_backoffs.argtypes = [C.POINTER(cmpc_dims), C.POINTER(cmpc_model), C.c_double,
                                            dp, dp, dp, ip, dp, vp]
     lib.cmpc_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]

@@ -19,6 +19,9 @@ int cmpc_wr_set_smem_limit(int smem_optin);
 int cmpc_wr_launch_scp(const cmpc_dims* dims, const cmpc_model* model, const cmpc_scp_params* scp, const cmpc_qp_settings* qp,
                        const void* batch, size_t batch_bytes, const void* cfg, int tile0, int tile1, cudaStream_t st,
                        std::string* msg, long long* n_launches);
+int cmpc_wr_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X, const double* U,
+                     const double* contact_pos, const double* contact_R, const int32_t* contact_active, double* gains,
+                     double* covs, void* scratch, cudaStream_t st, std::string* msg, long long* n_launches);
 int cmpc_wr_linearize(const cmpc_dims* dims, const cmpc_model* model, const double* X, const double* U, const double* contact_pos,
                       const double* contact_R, const int32_t* contact_active, double* f, double* fx, double* fu, cudaStream_t st,
                       std::string* msg);
@@ -71,42 +74,6 @@ __global__ void cmpc_linearize_kernel(const __grid_constant__ Params prm, int B,
       dense_Bcol(prm, &L.d[3 * sl], ax, col);
       for (int i = 0; i < 9; ++i) fu[(t * 9 + i) * nu + 3 * ct + ax] = col[i];
     }
-  }
-}
-
-// LQR gains along the nominal trajectory (one thread per instance and knot): K [B][N][nu][9]
-__global__ void cmpc_lqr_gains_kernel(const __grid_constant__ Params prm, const LqrWeights* __restrict__ W, int B,
-                                      int shared_plan, const double* __restrict__ X, const double* __restrict__ U,
-                                      const double* __restrict__ cpos, const int* __restrict__ cact,
-                                      double* __restrict__ Kout) {
-  const int N = prm.N, nu = prm.nu, nc = prm.nc;
-  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long)B * N) return;
-  int b = (int)(t / N), k = (int)(t % N);
-  const long plan = shared_plan ? 0 : b;
-  double A[81], Bm[9 * MAXU], Ct[3 * MAXU], K[MAXU * 9];
-  knot_ABC(prm, X + ((long)b * (N + 1) + k) * 9, U + ((long)b * N + k) * nu, cpos + (plan * N + k) * nc * 3,
-           cact + (plan * N + k) * nc, A, Bm, Ct);
-  lqr_gain_knot(A, Bm, nu, *W, K);
-  for (int i = 0; i < nu * 9; ++i) Kout[t * nu * 9 + i] = K[i];
-}
-
-// covariance propagation (sequential in k; one thread per instance): covs [B][N+1][9][9], covs[b][0] = 0
-__global__ void cmpc_covs_kernel(const __grid_constant__ Params prm, const LqrWeights* __restrict__ W, int B,
-                                 int shared_plan, const double* __restrict__ X, const double* __restrict__ U,
-                                 const double* __restrict__ cpos, const int* __restrict__ cact,
-                                 const double* __restrict__ Kin, double* __restrict__ covs) {
-  const int N = prm.N, nu = prm.nu, nc = prm.nc;
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const long plan = shared_plan ? 0 : b;
-  double Sg[81], Sn[81], A[81], Bm[9 * MAXU], Ct[3 * MAXU];
-  for (int i = 0; i < 81; ++i) { Sg[i] = 0.0; covs[(long)b * (N + 1) * 81 + i] = 0.0; }
-  for (int k = 0; k < N; ++k) {
-    knot_ABC(prm, X + ((long)b * (N + 1) + k) * 9, U + ((long)b * N + k) * nu, cpos + (plan * N + k) * nc * 3,
-             cact + (plan * N + k) * nc, A, Bm, Ct);
-    cov_step_knot(A, Bm, Ct, Kin + ((long)b * N + k) * nu * 9, nu, *W, Sg, Sn);
-    for (int i = 0; i < 81; ++i) { Sg[i] = Sn[i]; covs[((long)b * (N + 1) + k + 1) * 81 + i] = Sn[i]; }
   }
 }
 
@@ -489,6 +456,7 @@ int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr
                   double* covs, void* scratch, void* stream) {
   if (!dims || !model || !w || !X || !U || !contact_pos || !contact_active || !gains || !scratch)
     return fail(-1, "null argument");
+  if (dims->contact_model != CMPC_CONTACT_POINT) return fail(-1, "point-contact entry: use cmpc_lqr_covs_wrench for the wrench model");
   static_assert(sizeof(cmpc_lqr_weights) == sizeof(LqrWeights), "cmpc_lqr_weights layout");
   Params prm;
   int rc = fill_params(&prm, dims, model, nullptr, nullptr, 1);
@@ -496,22 +464,26 @@ int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr
   const int nu = prm.nu;
   for (int i = 0; i < nu; ++i)
     if (!(w->R[i * nu + i] > 0.0)) return fail(-2, "R must have a positive diagonal");
-  cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(scratch, w, sizeof(LqrWeights), cudaMemcpyHostToDevice, st));
-  const LqrWeights* dW = (const LqrWeights*)scratch;
-  long total = (long)dims->batch * dims->N;
-  cmpc_lqr_gains_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(prm, dW, dims->batch, dims->shared_plan, X, U,
-                                                                    contact_pos, (const int*)contact_active, gains);
-  g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
-  if (covs) {
-    cmpc_covs_kernel<<<(unsigned)((dims->batch + 31) / 32), 32, 0, st>>>(prm, dW, dims->batch, dims->shared_plan, X, U,
-                                                                       contact_pos, (const int*)contact_active, gains,
-                                                                       covs);
-    g_launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
-  }
+  long long nl = 0;
+  const cudaError_t e = launch_lqr_covs(prm, (const LqrWeights*)w, dims->batch, dims->shared_plan, X, U, contact_pos, nullptr,
+                                        (const int*)contact_active, gains, covs, scratch, (cudaStream_t)stream, &nl);
+  g_launches.fetch_add(nl);
+  CUDA_TRY(e);
   return 0;
+}
+
+int cmpc_lqr_covs_wrench(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X,
+                         const double* U, const double* contact_pos, const double* contact_R, const int32_t* contact_active,
+                         double* gains, double* covs, void* scratch, void* stream) {
+  if (!dims || !model || !w || !X || !U || !contact_pos || !contact_R || !contact_active || !gains || !scratch)
+    return fail(-1, "null argument");
+  if (dims->contact_model != CMPC_CONTACT_WRENCH) return fail(-1, "cmpc_lqr_covs_wrench needs dims.contact_model = CMPC_CONTACT_WRENCH");
+  std::string msg;
+  long long nl = 0;
+  const int rc = cmpc_wr_lqr_covs(dims, model, w, X, U, contact_pos, contact_R, contact_active, gains, covs, scratch,
+                                  (cudaStream_t)stream, &msg, &nl);
+  g_launches.fetch_add(nl);
+  return rc ? fail(rc, msg) : 0;
 }
 
 int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, double xi, const double* gains,

@@ -22,11 +22,36 @@ struct LqrWeights {
 
 // dense B (9 x nu, row-major, per-contact control layout) and the torque rows of C = df/dp
 // (C[6:9, 3c:3c+3] = -dt [f_c]x for active contacts, zero elsewhere; stored as Ct[3][nu])
+// Wrench model (WR): B in the reference's control order (six per foot) from the slot blocks of linearize_knot; the
+// contact-position noise has three components per FOOT, so only the first 3 nf columns of Ct (and the leading
+// 3 nf x 3 nf block of cov_w) are used.
 CMPC_HD void dense_B_C(const Params& P, const double* x, const double* u, const double* cpos, const int* cact,
-                       double* Bm, double* Ct) {
+                       double* Bm, double* Ct, const double* cR = nullptr) {
   const int nu = P.nu;
   for (int i = 0; i < 9 * nu; ++i) Bm[i] = 0.0;
   for (int i = 0; i < 3 * nu; ++i) Ct[i] = 0.0;
+  if (WR) {
+    KnotLin L;
+    linearize_knot(P, x, u, cpos, cact, 0, L, cR);
+    const int ns = L.meta & 7;
+    for (int sl = 0; sl < ns; ++sl) {
+      const int pc = (L.meta >> (4 + 2 * sl)) & 3;
+      for (int a = 0; a < 3; ++a) {
+        const int col = uix(pc, a);
+        if (!(pc & 1)) Bm[(3 + a) * nu + col] = P.dt;
+        for (int j = 0; j < 3; ++j) Bm[(6 + j) * nu + col] = P.dt * L.d[9 * sl + 3 * a + j];
+      }
+    }
+    for (int f = 0; f < P.nf; ++f) {
+      if (!cact[f]) continue;
+      const double* fb = u + 6 * f + 2;
+      for (int a = 0; a < 3; ++a) {
+        Ct[nxt3(a) * nu + 3 * f + a] = -P.dt * fb[prv3(a)];
+        Ct[prv3(a) * nu + 3 * f + a] = P.dt * fb[nxt3(a)];
+      }
+    }
+    return;
+  }
   for (int c = 0; c < P.nc; ++c) {
     if (!cact[c]) continue;
     const double d[3] = {cpos[3 * c] - x[0], cpos[3 * c + 1] - x[1], cpos[3 * c + 2] - x[2]};
@@ -43,11 +68,11 @@ CMPC_HD void dense_B_C(const Params& P, const double* x, const double* u, const 
 
 // A (9x9), B (9 x nu), torque rows of C at one knot of the nominal trajectory
 CMPC_HD void knot_ABC(const Params& P, const double* x, const double* u, const double* cpos, const int* cact,
-                      double* A, double* Bm, double* Ct) {
+                      double* A, double* Bm, double* Ct, const double* cR = nullptr) {
   KnotLin L;
-  linearize_knot(P, x, u, cpos, cact, 0, L);
+  linearize_knot(P, x, u, cpos, cact, 0, L, cR);
   dense_A(P, L.S, A);
-  dense_B_C(P, x, u, cpos, cact, Bm, Ct);
+  dense_B_C(P, x, u, cpos, cact, Bm, Ct, cR);
 }
 
 // in-place Cholesky H = L L' (lower triangle, leading dimension ld); returns 0, or -1 when not SPD
@@ -208,5 +233,62 @@ CMPC_HD void friction_backoff_knot(const Params& P, double xi, int k, const doub
     }
   }
 }
+
+#if defined(__CUDACC__)
+// LQR gains along the nominal trajectory (one thread per instance and knot): K [B][N][nu][9]
+__global__ void cmpc_lqr_gains_kernel(const __grid_constant__ Params prm, const LqrWeights* __restrict__ W, int B,
+                                      int shared_plan, const double* __restrict__ X, const double* __restrict__ U,
+                                      const double* __restrict__ cpos, const double* __restrict__ cR,
+                                      const int* __restrict__ cact, double* __restrict__ Kout) {
+  const int N = prm.N, nu = prm.nu, nf = prm.nf;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * N) return;
+  int b = (int)(t / N), k = (int)(t % N);
+  const long plan = shared_plan ? 0 : b;
+  double A[81], Bm[9 * MAXU], Ct[3 * MAXU], K[MAXU * 9];
+  knot_ABC(prm, X + ((long)b * (N + 1) + k) * 9, U + ((long)b * N + k) * nu, cpos + (plan * N + k) * nf * 3,
+           cact + (plan * N + k) * nf, A, Bm, Ct, cR ? cR + (plan * N + k) * nf * 9 : nullptr);
+  lqr_gain_knot(A, Bm, nu, *W, K);
+  for (int i = 0; i < nu * 9; ++i) Kout[t * nu * 9 + i] = K[i];
+}
+
+// covariance propagation (sequential in k; one thread per instance): covs [B][N+1][9][9], covs[b][0] = 0
+__global__ void cmpc_covs_kernel(const __grid_constant__ Params prm, const LqrWeights* __restrict__ W, int B,
+                                 int shared_plan, const double* __restrict__ X, const double* __restrict__ U,
+                                 const double* __restrict__ cpos, const double* __restrict__ cR,
+                                 const int* __restrict__ cact, const double* __restrict__ Kin, double* __restrict__ covs) {
+  const int N = prm.N, nu = prm.nu, nf = prm.nf;
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long plan = shared_plan ? 0 : b;
+  double Sg[81], Sn[81], A[81], Bm[9 * MAXU], Ct[3 * MAXU];
+  for (int i = 0; i < 81; ++i) { Sg[i] = 0.0; covs[(long)b * (N + 1) * 81 + i] = 0.0; }
+  for (int k = 0; k < N; ++k) {
+    knot_ABC(prm, X + ((long)b * (N + 1) + k) * 9, U + ((long)b * N + k) * nu, cpos + (plan * N + k) * nf * 3,
+             cact + (plan * N + k) * nf, A, Bm, Ct, cR ? cR + (plan * N + k) * nf * 9 : nullptr);
+    cov_step_knot(A, Bm, Ct, Kin + ((long)b * N + k) * nu * 9, nu, *W, Sg, Sn);
+    for (int i = 0; i < 81; ++i) { Sg[i] = Sn[i]; covs[((long)b * (N + 1) + k + 1) * 81 + i] = Sn[i]; }
+  }
+}
+
+// launches the two kernels; the weights travel through `scratch` (device memory, CMPC_LQR_SCRATCH_BYTES)
+inline cudaError_t launch_lqr_covs(const Params& prm, const LqrWeights* w_host, int B, int shared_plan, const double* X,
+                                   const double* U, const double* cpos, const double* cR, const int* cact, double* gains,
+                                   double* covs, void* scratch, cudaStream_t st, long long* n_launches) {
+  cudaError_t e = cudaMemcpyAsync(scratch, w_host, sizeof(LqrWeights), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  const LqrWeights* dW = (const LqrWeights*)scratch;
+  const long total = (long)B * prm.N;
+  cmpc_lqr_gains_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(prm, dW, B, shared_plan, X, U, cpos, cR, cact, gains);
+  ++*n_launches;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (covs) {
+    cmpc_covs_kernel<<<(unsigned)((B + 31) / 32), 32, 0, st>>>(prm, dW, B, shared_plan, X, U, cpos, cR, cact, gains, covs);
+    ++*n_launches;
+    e = cudaGetLastError();
+  }
+  return e;
+}
+#endif
 
 }  // namespace cmpc

@@ -6,6 +6,7 @@
 #define CMPC_WRENCH 1
 #define cmpc cmpc_wr
 #include "cmpc_launch.cuh"
+#include "cmpc_lqr.cuh"
 #undef cmpc
 
 struct WrSizes { long tiles, ws, nst, info, smem; };
@@ -76,6 +77,23 @@ int cmpc_wr_linearize(const cmpc_dims* dims, const cmpc_model* model, const doub
   cmpc_wr_linearize_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(prm, dims->batch, dims->shared_plan, X, U, contact_pos,
                                                                             contact_R, (const int*)contact_active, f, fx, fu);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *msg = cudaGetErrorString(e); return -100 - (int)e; }
+  return 0;
+}
+
+// LQR gains / covariances along (X, U) for the wrench model (compute_trajectory_data: LQR_gains, Covs;
+// /root/reference/src/centroidal_model.py:215-227,233-238,284-285 with the TALOS Jacobians)
+int cmpc_wr_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X, const double* U,
+                     const double* contact_pos, const double* contact_R, const int32_t* contact_active, double* gains,
+                     double* covs, void* scratch, cudaStream_t st, std::string* msg, long long* n_launches) {
+  static_assert(sizeof(cmpc_lqr_weights) == sizeof(cmpc_wr::LqrWeights), "cmpc_lqr_weights layout");
+  cmpc_wr::Params prm;
+  int rc = cmpc_wr::fill_params(&prm, dims, model, nullptr, nullptr, 0);
+  if (rc) { *msg = "bad dims or weights"; return rc; }
+  for (int i = 0; i < prm.nu; ++i)
+    if (!(w->R[i * prm.nu + i] > 0.0)) { *msg = "R must have a positive diagonal"; return -2; }
+  const cudaError_t e = cmpc_wr::launch_lqr_covs(prm, (const cmpc_wr::LqrWeights*)w, dims->batch, dims->shared_plan, X, U, contact_pos,
+                                                 contact_R, (const int*)contact_active, gains, covs, scratch, st, n_launches);
   if (e != cudaSuccess) { *msg = cudaGetErrorString(e); return -100 - (int)e; }
   return 0;
 }

@@ -212,8 +212,7 @@ def lqr_gains_covs_batched(batch, X, U, Q, R, cov_w, cov_eta, want_covs=True):
     lib = L.load()
     dev = torch.device("cuda", torch.cuda.current_device())
     B, N, nc, nu = batch.B, batch.N, batch.nc, batch.nu
-    if batch.proto["robot"] == "TALOS":
-        raise NotImplementedError("LQR gains / covariances (stochastic mode) are built for the point-contact model only")
+    wrench = batch.proto["robot"] == "TALOS"
 
     def dv(a, dt):
         t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
@@ -222,15 +221,20 @@ def lqr_gains_covs_batched(batch, X, U, Q, R, cov_w, cov_eta, want_covs=True):
     if tuple(Xd.shape) != (B, N + 1, 9) or tuple(Ud.shape) != (B, N, nu):
         raise L.CmpcError("X must be [B,N+1,9] and U [B,N,nu]")
     cp, ca = dv(batch.contact_pos, torch.float64), dv(batch.contact_active, torch.int32)
-    dims = L.cmpc_dims(B, N, nc, 1 if batch.shared_plan else 0)
+    dims = L.cmpc_dims(B, N, nc, 1 if batch.shared_plan else 0, L.contact_model_of(batch.proto["robot"]))
     mdl = L.make_model_struct(batch.proto)
     w = L.make_lqr_struct(Q, R, cov_w, cov_eta, nu)
     gains = torch.empty((B, N, nu, 9), dtype=torch.float64, device=dev)
     covs = torch.empty((B, N + 1, 9, 9), dtype=torch.float64, device=dev) if want_covs else None
     scratch = torch.empty(L.LQR_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream()
-    L.check(lib.cmpc_lqr_covs(C.byref(dims), C.byref(mdl), C.byref(w), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca),
-                              _ptr(gains), _ptr(covs), _ptr(scratch), C.c_void_p(st.cuda_stream)), lib)
+    if wrench:
+        cR = dv(batch.contact_R, torch.float64)
+        L.check(lib.cmpc_lqr_covs_wrench(C.byref(dims), C.byref(mdl), C.byref(w), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(cR), _ptr(ca),
+                                         _ptr(gains), _ptr(covs), _ptr(scratch), C.c_void_p(st.cuda_stream)), lib)
+    else:
+        L.check(lib.cmpc_lqr_covs(C.byref(dims), C.byref(mdl), C.byref(w), _ptr(Xd), _ptr(Ud), _ptr(cp), _ptr(ca),
+                                  _ptr(gains), _ptr(covs), _ptr(scratch), C.c_void_p(st.cuda_stream)), lib)
     st.synchronize()   # `w` (host) and `scratch` must outlive the asynchronous copy
     return gains, covs
 

@@ -45,7 +45,7 @@ def solve_scp(model, scp_params):
         return False
     all_solution = dict(state=[], control=[], gains=[], covs=[])
     gains = covs = None
-    if int(out["n_accepted"][0]) > 0 and model._robot != "TALOS":   # (wrench model: gains / covs are not built, None)
+    if int(out["n_accepted"][0]) > 0:
         # traj_data is computed once, at the warm start (scp_solver.py:129-130), so every accepted
         # iterate carries the same LQR_gains / Covs (scp_solver.py:165-166)
         from ..device import lqr_gains_covs

@@ -180,6 +180,12 @@ int cmpc_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr
  * - sum_u xi 2 G_ju sqrt((K_c Sigma_k K_c')_uu) over the entries with G_ju > 1e-6 and sqrt(.) > 1e-6, zero at
  * k = 0 and for inactive contacts.  xi = Phi^-1(1 - beta_u/5*3) is computed by the caller (:157);
  * gains / covs are the outputs of cmpc_lqr_covs; contact_R as in cmpc_set_problem (NULL = identity). */
+/* The same for the wrench contact model (dims.contact_model = CMPC_CONTACT_WRENCH): R, cov_w with leading dimension
+   n_u = 6*nc; the contact-position noise has three components per foot, so cov_w is conf.cov_w (3 nc x 3 nc) in the
+   leading block of the 12 x 12 array.  contact_R [Bp][N][nc][3][3]. */
+int cmpc_lqr_covs_wrench(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w, const double* X,
+                         const double* U, const double* contact_pos, const double* contact_R, const int32_t* contact_active,
+                         double* gains, double* covs, void* scratch, void* stream);
 int cmpc_friction_backoffs(const cmpc_dims* dims, const cmpc_model* model, double xi, const double* gains,
                            const double* covs, const double* contact_R, const int32_t* contact_active,
                            double* friction_ub, void* stream);

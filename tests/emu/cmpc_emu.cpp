@@ -156,13 +156,13 @@ extern "C" int cmpc_emu_record_doubles(void) { return REC_MAX; }
 // host run of csrc/cmpc_lqr.cuh with the loop structure of cmpc_lqr_gains_kernel / cmpc_covs_kernel
 extern "C" int cmpc_emu_lqr_covs(const cmpc_dims* dims, const cmpc_model* model, const cmpc_lqr_weights* w,
                                  const double* X, const double* U, const double* contact_pos,
-                                 const int32_t* contact_active, double* gains, double* covs) {
+                                 const int32_t* contact_active, double* gains, double* covs, const double* contact_R) {
   static_assert(sizeof(cmpc_lqr_weights) == sizeof(LqrWeights), "cmpc_lqr_weights layout");
   Params prm;
   int rc = fill_params(&prm, dims, model, nullptr, nullptr, 1);
   if (rc) return rc;
   const LqrWeights& W = *(const LqrWeights*)w;
-  const int B = dims->batch, N = prm.N, nu = prm.nu, nc = prm.nc;
+  const int B = dims->batch, N = prm.N, nu = prm.nu, nc = prm.nf;   // rows of the contact arrays per knot
   for (int b = 0; b < B; ++b) {
     const long plan = dims->shared_plan ? 0 : b;
     double Sg[81] = {0}, Sn[81], A[81], Bm[9 * MAXU], Ct[3 * MAXU];
@@ -170,7 +170,7 @@ extern "C" int cmpc_emu_lqr_covs(const cmpc_dims* dims, const cmpc_model* model,
     for (int k = 0; k < N; ++k) {
       double* K = gains + ((long)b * N + k) * nu * 9;
       knot_ABC(prm, X + ((long)b * (N + 1) + k) * 9, U + ((long)b * N + k) * nu, contact_pos + (plan * N + k) * nc * 3,
-               (const int*)contact_active + (plan * N + k) * nc, A, Bm, Ct);
+               (const int*)contact_active + (plan * N + k) * nc, A, Bm, Ct, contact_R ? contact_R + (plan * N + k) * nc * 9 : nullptr);
       lqr_gain_knot(A, Bm, nu, W, K);
       if (!covs) continue;
       cov_step_knot(A, Bm, Ct, K, nu, W, Sg, Sn);

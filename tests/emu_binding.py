@@ -80,16 +80,17 @@ def _solve_scp(lib, batch, scp_params, qp_overrides):
 
 def lqr_covs(batch, X, U, Q, R, cov_w, cov_eta):
     """Host build of csrc/cmpc_lqr.cuh: gains [B,N,nu,9], covs [B,N+1,9,9]."""
-    lib = load()
+    wrench = getattr(batch, "wrench", False)
+    lib = load(wrench=wrench)
     B, N, nu = batch.B, batch.N, batch.nu
-    dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0)
+    dims = L.cmpc_dims(B, N, batch.nc, 1 if batch.shared_plan else 0, L.contact_model_of(batch.proto["robot"]))
     model = L.make_model_struct(batch.proto)
     w = L.make_lqr_struct(Q, R, cov_w, cov_eta, nu)
     X = np.ascontiguousarray(X, dtype=np.float64)
     U = np.ascontiguousarray(U, dtype=np.float64)
     gains, covs = np.zeros((B, N, nu, 9)), np.zeros((B, N + 1, 9, 9))
     rc = lib.cmpc_emu_lqr_covs(C.byref(dims), C.byref(model), C.byref(w), _p(X), _p(U), _p(batch.contact_pos),
-                               _p(batch.contact_active), _p(gains), _p(covs))
+                               _p(batch.contact_active), _p(gains), _p(covs), _p(batch.contact_R) if wrench else None)
     if rc != 0:
         raise RuntimeError("cmpc_emu_lqr_covs returned %d" % rc)
     return gains, covs

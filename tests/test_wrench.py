@@ -128,3 +128,42 @@ def test_wrench_linearize_kernel(gpu):
     np.testing.assert_allclose(fu, ref["f_u"], rtol=0, atol=1e-12)
     roll = m.integrate_dynamics_trajectory(traj)
     np.testing.assert_allclose(roll[:, :conf.N], dynamics.rollout(traj["state"], traj["control"], prob), atol=1e-11)
+
+
+def _perturbed_talos(N=30):
+    conf = synthetic.load_conf("talos", N=N)
+    m = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 1))
+    p = m.problem_arrays()
+    rng = np.random.default_rng(3)
+    X = p["X_ref"] + 0.01 * rng.normal(size=p["X_ref"].shape)
+    U = p["U_init"] + np.array([0.01, 0.01, 5.0, 5.0, 20.0, 1.0] * 2)[:, None] * rng.normal(size=p["U_init"].shape)
+    return conf, m, p, X, U
+
+
+def test_wrench_lqr_gains_and_covs_host_build():
+    """LQR_gains / Covs of compute_trajectory_data for robot == 'TALOS' (/root/reference/src/centroidal_model.py:
+    215-238,284-285 with the six-control Jacobians; position noise: three components per foot)."""
+    conf, m, p, X, U = _perturbed_talos()
+    g, c = E.lqr_covs(ProblemBatch([m]), X.T[None], U.T[None], conf.Q, conf.R, conf.cov_w, conf.cov_white_noise)
+    go, co = dynamics.lqr_gains_covs(X, U, p, conf.Q, conf.R, conf.cov_w, conf.cov_white_noise)
+    assert np.abs(g[0] - go).max() <= 1e-10 * np.abs(go).max()
+    assert np.abs(c[0] - co).max() <= 1e-8 * np.abs(co).max()
+
+
+@pytest.mark.gpu
+def test_wrench_trajectory_data_and_drop_in_solve(gpu):
+    """compute_trajectory_data (all keys) and the drop-in solve_scp for a TALOS model through the C ABI."""
+    from centroidal_mpc_b200.src.scp_solver import solve_scp
+    conf, m, p, X, U = _perturbed_talos()
+    td = m.compute_trajectory_data(dict(state=X, control=U))
+    ref = dynamics.trajectory_data(X, U, p)
+    go, co = dynamics.lqr_gains_covs(X, U, p, conf.Q, conf.R, conf.cov_w, conf.cov_white_noise)
+    np.testing.assert_allclose(td["dynamics"], ref["dynamics"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(td["gradients"]["f_u"], ref["f_u"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(td["gradients"]["f_w"], ref["f_w"], rtol=0, atol=1e-12)
+    assert np.abs(td["LQR_gains"] - go).max() <= 1e-10 * np.abs(go).max()
+    assert np.abs(td["Covs"] - co).max() <= 1e-8 * np.abs(co).max()
+    sol = solve_scp(m, conf.scp_params)
+    assert sol is not False and len(sol["state"]) == 1
+    assert sol["state"][-1].shape == (9, conf.N + 1) and sol["control"][-1].shape == (12, conf.N)
+    assert sol["gains"][-1].shape == (conf.N, 12, 9) and sol["covs"][-1].shape == (conf.N + 1, 9, 9)
