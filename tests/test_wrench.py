@@ -167,3 +167,56 @@ def test_wrench_trajectory_data_and_drop_in_solve(gpu):
     assert sol is not False and len(sol["state"]) == 1
     assert sol["state"][-1].shape == (9, conf.N + 1) and sol["control"][-1].shape == (12, conf.N)
     assert sol["gains"][-1].shape == (conf.N, 12, 9) and sol["covs"][-1].shape == (conf.N + 1, 9, 9)
+
+
+@pytest.mark.gpu
+def test_wrench_full_size_properties(gpu):
+    """BASELINE configuration 5 at the size the benchmark runs it (4096 x N = 100): every instance accepted and
+    certified, CoP box and friction pyramid hold, swinging feet carry exact zeros, boundary states are met."""
+    from centroidal_mpc_b200.device import BatchSolver
+    conf = synthetic.load_conf("talos", N=100)
+    batch = synthetic.make_batch(conf, 4096)
+    solver = BatchSolver(batch)
+    out = solver.solve(conf.scp_params).results()
+    st = solver.stats()
+    solver.close()
+    assert (out["status"] == 0).all() and (out["n_accepted"] == 1).all() and (out["scp_iters"] == 1).all()
+    assert (st["info"][:, 10] == 1).all() and (st["qp_iters"] == 8).all()
+    U, X = out["U"], out["X"]
+    act = batch.contact_active[0]                     # shared plan [N, 2]
+    kf = conf.mu / np.sqrt(2.0)
+    for c in range(2):
+        on = act[:, c] == 1
+        u = U[:, :, 6 * c:6 * c + 6]
+        assert np.all(u[:, ~on] == 0.0)
+        assert np.all(np.abs(u[:, on, 0]) <= conf.lxp + 1e-7) and np.all(np.abs(u[:, on, 1]) <= conf.lyp + 1e-7)
+        fz = u[:, on, 4]                              # identity foot frames in this gait
+        assert np.all(np.abs(u[:, on, 2]) <= kf * fz + 1e-5) and np.all(np.abs(u[:, on, 3]) <= kf * fz + 1e-5)
+    np.testing.assert_allclose(X[:, 0], batch.x_init, atol=1e-12)
+    np.testing.assert_allclose(X[:, -1], batch.x_final, atol=1e-6)
+
+
+def test_wrench_rotated_foot_frames_match_tight_oracle():
+    """Yawed and pitched soles and a warm start with nonzero CoP / tau_z: every block of the wrench Jacobian
+    (r1 x f, r2 x f, r3, lever arm p + R cop - c) and the friction pyramid in the foot frame are exercised
+    (the synthetic gait has identity frames and a zero-CoP warm start)."""
+    from oracle import scp as oscp
+    conf = synthetic.load_conf("talos", N=24)
+    m = Centroidal_model(conf, centroidal_traj=synthetic.reference_trajectory(conf, 2))
+    p = dict(m.problem_arrays())
+
+    def Rz(a): return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    def Ry(a): return np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    R = p["contact_R"].copy()
+    for c, (yaw, pitch) in enumerate(((0.3, 0.05), (-0.2, -0.04))):
+        R[:, c] = (Rz(yaw) @ Ry(pitch))[None] * p["contact_active"][:, c, None, None]
+    p["contact_R"] = R
+    U, rng = p["U_init"].copy(), np.random.default_rng(0)
+    U[[0, 1, 6, 7]] += 0.01 * rng.normal(size=(4, conf.N)) * p["contact_active"].T[[0, 0, 1, 1]]
+    U[[5, 11]] += 0.5 * rng.normal(size=(2, conf.N)) * p["contact_active"].T
+    p["U_init"] = U
+    out = E.solve_scp(ProblemBatch([p]), conf.scp_params, qp_overrides=WRENCH_QP_DEFAULTS)
+    ref = oscp.solve_scp(p, conf.scp_params, osqp_settings=dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=100000, polish_refine_iter=30))
+    assert ref is not False and len(ref["state"]) == 1 and out["status"][0] == 0 and out["n_accepted"][0] == 1
+    assert out["scp_iters"][0] == ref["iterations"]
+    assert relerr(out["X"][0].T, ref["state"][-1]) < TOL and relerr(out["U"][0].T, ref["control"][-1]) < TOL
