@@ -61,12 +61,16 @@ def _check(model, traj_data, tr, friction_ub=None, atol=0.0):
     np.testing.assert_allclose(cons.ub, up, rtol=0, atol=atol)
     # block offsets of the reference order: initial, dynamics, final, friction, trust
     N, nc = model._N, prob["contact_active"].shape[1]
-    assert blocks["dynamics"] == 9 and blocks["final"] == 9 + 9 * N and blocks["friction"] == 18 + 9 * N
-    assert blocks["trust"] == 18 + 9 * N + 5 * N * nc and blocks["m"] == cons.mat.shape[0]
+    cop = 2 * N * nc if prob["robot"] == "TALOS" else 0      # CoP box: x rows then y rows per foot (constraints.py:111-145)
+    assert blocks["dynamics"] == 9 and blocks["final"] == 9 + 9 * N and blocks["friction"] == 18 + 9 * N + cop
+    if cop:
+        assert blocks["cop"] == 18 + 9 * N
+    assert blocks["trust"] == 18 + 9 * N + cop + 5 * N * nc and blocks["m"] == cons.mat.shape[0]
     return cons
 
 
-@pytest.mark.parametrize("name,N", [("solo12_trot", 3), ("solo12_trot", 40), ("solo12_bound", 40), ("bolt", 5), ("bolt", 40)])
+@pytest.mark.parametrize("name,N", [("solo12_trot", 3), ("solo12_trot", 40), ("solo12_bound", 40), ("bolt", 5), ("bolt", 40),
+                                    ("talos", 5), ("talos", 30)])
 def test_inspectors_match_the_oracle_assembly(name, N):
     conf, model = _model(name, N)
     tr = dict(radius=conf.scp_params["trust_region_radius0"], weight=conf.scp_params["omega0"])
@@ -95,7 +99,7 @@ def test_builders_keep_the_reference_shapes():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,N,stochastic", [("solo12_trot", 5, False), ("solo12_trot", 40, False), ("bolt", 40, False),
-                                               ("solo12_bound", 40, True)])
+                                               ("solo12_bound", 40, True), ("talos", 30, False)])
 def test_device_problem_expands_to_the_oracle_qp(gpu, name, N, stochastic):
     """traj_data from the device (cmpc_linearize [+ cmpc_lqr_covs, cmpc_friction_backoffs]): the QP the
     device solves, written out in the reference's matrices, is the oracle's."""
