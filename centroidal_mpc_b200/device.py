@@ -26,7 +26,7 @@ def _ptr(t):
 # and the active set needs up to 13 correction rounds at N = 100.  The library
 # applies the same values by itself when it is called with qp = NULL and upper bounds are bound
 # (cmpc_api.cu: launch_tiles), so a C caller gets them without knowing this table.
-STOCHASTIC_QP_DEFAULTS = dict(polish_refine_iter=10, polish_active_set_rounds=19, active_set_start=20, active_set_step=20)
+STOCHASTIC_QP_DEFAULTS = dict(polish_refine_iter=10, polish_active_set_rounds=19)
 # ... and for the wrench contact model (TALOS): multipliers of the order of the 900 N contact forces make the
 # default certificate tolerance 1e-9 leave 6e-6 in X; 1e-11 reaches the tightly solved oracle to 3e-7
 WRENCH_QP_DEFAULTS = dict(polish_refine_iter=30, polish_active_set_rounds=19, active_set_tol=1e-11, delta=1e-9)

@@ -378,8 +378,9 @@ def test_emu_matches_stochastic_golden(path):
 
 
 def test_stochastic_headline_horizon_certifies_at_the_first_attempt():
-    """N = 100 bound gait with back-offs: with the host side's stochastic QP settings every instance is
-    certified by the first polish attempt (20 ADMM iterations); the library defaults leave some to retry."""
+    """N = 100 bound gait with back-offs: with the host side's stochastic QP settings (more multiplier sweeps and
+    active-set rounds per attempt) every instance is certified by the first polish attempt (8 ADMM iterations);
+    the plain defaults leave some to retry."""
     from centroidal_mpc_b200.device import chance_constraint_xi
     conf = synthetic.load_conf("solo12_bound", N=100)
     batch = synthetic.make_batch(conf, 8, stochastic=True)
@@ -389,8 +390,8 @@ def test_stochastic_headline_horizon_certifies_at_the_first_attempt():
     from centroidal_mpc_b200.device import STOCHASTIC_QP_DEFAULTS
     tuned = E.solve_scp(batch, conf.scp_params, STOCHASTIC_QP_DEFAULTS, friction_ub=ub)
     plain = E.solve_scp(batch, conf.scp_params, friction_ub=ub)
-    assert (tuned["status"] == 0).all() and (tuned["qp_iters"] == 20).all() and (tuned["info"][:, 9] == 1).all()
-    assert plain["qp_iters"].max() > 20
+    assert (tuned["status"] == 0).all() and (tuned["qp_iters"] == 8).all() and (tuned["info"][:, 9] == 1).all()
+    assert plain["qp_iters"].max() > 8
     assert relerr(tuned["X"], plain["X"]) < TOL and relerr(tuned["U"], plain["U"]) < TOL
 
 
