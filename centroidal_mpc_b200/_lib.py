@@ -126,7 +126,7 @@ def make_qp_struct(overrides=None, lib=None):
         lib.cmpc_default_qp_settings(C.byref(q))
     else:   # same numbers as csrc/cmpc_params.h default_qp_settings (checked by the tests)
         q.eps_abs = q.eps_rel = 1e-7
-        q.sigma, q.alpha, q.rho, q.delta, q.adaptive_rho_tolerance = 1e-6, 1.6, 2.0, 1e-6, 5.0
+        q.sigma, q.alpha, q.rho, q.delta, q.adaptive_rho_tolerance = 1e-6, 1.8, 2.0, 1e-6, 5.0
         q.max_iter, q.check_termination, q.polish, q.polish_refine_iter, q.adaptive_rho = 4000, 25, 1, 3, 1
         q.adaptive_rho_start = 200
         q.polish_active_set_rounds = 9

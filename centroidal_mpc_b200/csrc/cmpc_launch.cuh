@@ -139,7 +139,7 @@ inline int launch_scp(const cmpc_dims* dims, const cmpc_model* model, const cmpc
     default_qp_settings(&dq);       // more multiplier sweeps and active-set rounds to certify
     dq.polish_refine_iter = 10;
     dq.polish_active_set_rounds = 19;
-    if (WR) { dq.active_set_tol = 1e-11; dq.polish_refine_iter = 30; dq.delta = 1e-9; }   // multipliers of the order of the 900 N forces: 1e-9 leaves 6e-6 in X;
+    if (WR) { dq.active_set_tol = 1e-11; dq.polish_refine_iter = 30; dq.delta = 1e-9; dq.alpha = 1.6; }   // multipliers of the order of the 900 N forces: 1e-9 leaves 6e-6 in X;
                                                                           // the multiplier sweeps stop as soon as the certificate holds
     // (the first polish attempt stays at 8 ADMM iterations also with back-offs: measured on B200, 4096 x N=100,
     //  first attempt after 20 / 16 / 12 / 8 iterations: trot 21.4 / 19.1 / 17.5 / 16.6 ms, bound 20.3 / 19.0 / 18.3 / 17.4 ms)

@@ -10,7 +10,10 @@ inline void default_qp_settings(cmpc_qp_settings* s) {
   s->eps_abs = 1e-7;            // scp_solver.py:63
   s->eps_rel = 1e-7;
   s->sigma = 1e-6;              // OSQP default (unused, see cmpc.h)
-  s->alpha = 1.6;               // OSQP default
+  s->alpha = 1.8;               // over-relaxation (OSQP's default is 1.6).  Swept on B200, 1.6 / 1.7 / 1.8 / 1.9: trot 4096 9.7 / 9.2 / 8.9-9.0 /
+                                // 9.1 ms, bound 9.5 / 9.4 / 9.0 / 9.1, bolt 8192 12.1 / 12.4 / 11.9-12.2 / 11.5, talos 11.3 / 11.1 / 11.0 / 10.9;
+                                // fewer polish rounds and a shorter straggler tail (at most 7 instead of 9 factorisations); the
+                                // exception is pace mode A (no active rows at the solution): 3.2 ms up to 1.7, 4.1 ms from 1.75 on
   s->rho = 2.0;                 // initial penalty in equilibrated units
   s->delta = 1e-6;              // OSQP polish regularisation
   s->adaptive_rho_tolerance = 5.0;

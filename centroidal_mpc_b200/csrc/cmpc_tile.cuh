@@ -1200,8 +1200,10 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
         const double dk = x[6 + i] - CMPC_S(r, L.xb + 6 + i);
         dk1 += fabs(dk);
         if (br != 0) {
-          if (code == 0) CMPC_R(w, L.yk + i) = CMPC_S(r, L.yk + i) + inv * dk;
-          else if (sgn * dk < -ktol) flip = true;
+          if (code == 0) {   // pinned component: an equality row of the polish, part of its primal residual
+            CMPC_R(w, L.yk + i) = CMPC_S(r, L.yk + i) + inv * dk;
+            R.pri = fmax(R.pri, fabs(dk));
+          } else if (sgn * dk < -ktol) flip = true;
           accv += sgn * dk;
         }
       }
@@ -1212,6 +1214,7 @@ CMPC_HD void fwd_state(const Params& P, Sv& S, Res& R, StagedPtr r, double* w, c
       } else {
         const double ys = CMPC_S(r, L.yk + 3) + inv * accv;
         CMPC_R(w, L.yk + 3) = ys;
+        R.pri = fmax(R.pri, fabs(accv));   // the surface row |dkappa|_1 = r is an equality row of the polish too
         if (flip || ys < -1e-9 * (1.0 + S.weight) || ys > S.weight * (1.0 + 1e-9)) R.kbad = 1;
       }
 #pragma unroll

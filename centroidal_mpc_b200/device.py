@@ -29,7 +29,9 @@ def _ptr(t):
 STOCHASTIC_QP_DEFAULTS = dict(polish_refine_iter=10, polish_active_set_rounds=19)
 # ... and for the wrench contact model (TALOS): multipliers of the order of the 900 N contact forces make the
 # default certificate tolerance 1e-9 leave 6e-6 in X; 1e-11 reaches the tightly solved oracle to 3e-7
-WRENCH_QP_DEFAULTS = dict(polish_refine_iter=30, polish_active_set_rounds=19, active_set_tol=1e-11, delta=1e-9)
+# (relaxation 1.6 instead of the 1.8 of the point-contact default: with 1.8 a receding-horizon tick of the talos loop
+# fails to certify and runs into the ADMM iteration cap, tests/test_mpc.py)
+WRENCH_QP_DEFAULTS = dict(polish_refine_iter=30, polish_active_set_rounds=19, active_set_tol=1e-11, delta=1e-9, alpha=1.6)
 
 
 class BatchSolver:

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import dynamics
 
-ALPHA = 1.6
+ALPHA = 1.8     # csrc/cmpc_params.h default_qp_settings
 CHECK = 25           # termination test every CHECK iterations (OSQP default) (knot-local residuals, see iterate())
 PER_ROW_FRICTION = True
 RHO0 = 2.0
