@@ -6,12 +6,13 @@ import numpy as np, torch
 from centroidal_mpc_b200 import synthetic
 from centroidal_mpc_b200.device import BatchSolver
 
-for name, B in (("solo12_trot", 4096), ("solo12_bound", 4096), ("bolt", 8192), ("talos", 4096)):
+for name, B in (("solo12_trot", 4096), ("solo12_bound", 4096), ("bolt", 8192), ("solo12_pace", 4096)):
     conf = synthetic.load_conf(name, N=100)
     solver = BatchSolver(synthetic.make_batch(conf, B))
     ref = None
-    grid = [dict()] + [dict(active_set_start=s, active_set_step=s) for s in (4, 6, 10, 12)] + \
-           [dict(rho=r) for r in (0.5, 1.0, 4.0, 8.0)] + [dict(alpha=a) for a in (1.0, 1.8)] + [dict(polish_refine_iter=r) for r in (1, 6)]
+    grid = [dict()] + [dict(active_set_start=s, active_set_step=s) for s in (6, 7, 9, 10)] + \
+           [dict(rho=r) for r in (1.0, 1.5, 3.0, 4.0)] + [dict(alpha=a) for a in (1.85,)] + \
+           [dict(rho=3.0, active_set_start=6, active_set_step=6), dict(rho=1.5, active_set_start=10, active_set_step=10)]
     for ov in grid:
         for _ in range(2): solver.solve(conf.scp_params, ov or None)
         torch.cuda.synchronize(); ts = []
