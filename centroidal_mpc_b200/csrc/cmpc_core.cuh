@@ -1,7 +1,7 @@
 // cmpc_core.cuh — data layout, parameters and the closed-form centroidal model.
-// Execution model: one THREAD per MPC instance, 32 instances ("a tile") per warp, every
-// per-instance quantity stored lane-interleaved so that each load / store of a warp is one
-// coalesced 256-byte access.  cmpc_tile.cuh is the solver written against this layout.
+// Execution model: a TEAM of NL = 8 lanes per MPC instance, TL = 4 instances ("a tile") per warp; every
+// per-instance quantity of the knot records is stored instance-interleaved ([field][TL]), so that a range
+// of fields is one contiguous block for a bulk copy.  cmpc_tile.cuh is the solver written against this layout.
 //
 // What this replaces in the reference (paths relative to /root/reference):
 //   src/centroidal_model.py:189-232,257-291   dynamics + Jacobians  -> linearize_knot()

@@ -14,7 +14,8 @@ namespace cmpc {
 
 // ------------------------------------------------------------------------------------------
 // The SCP kernel: one warp per tile of TL = 32 / NL instances, NL lanes per instance (cmpc_core.cuh),
-// persistent over a queue of tiles; a CTA is one warp, several CTAs share an SM.  Each instance runs
+// one tile per CTA in a wave launch (launch_scp below; with a queue counter the CTAs are persistent and pull
+// tiles, kept for comparison); a CTA is one warp, seven CTAs share an SM.  Each instance runs
 // the driver state machine (cmpc_tile.cuh: advance(), replicated in the lanes of its team); the warp
 // executes one whole-horizon operation at a time for the instances that asked for it, lowest operation
 // code first, so that instances that are ahead wait at the later operations (evaluate, write) and the
@@ -94,7 +95,7 @@ __device__ void run_tile(const Params& prm, const Batch& bt, int tile, TileCtx& 
 template <bool FAST>
 __global__ void __launch_bounds__(THREADS, 8)
 cmpc_scp_kernel(const __grid_constant__ Params prm, const __grid_constant__ Batch bt, int* __restrict__ queue, int tile0,
-                int tiles) {   // this launch solves the tiles [tile0, tiles), pulled from its own queue counter
+                int tiles) {   // this launch solves the tiles [tile0, tiles): tile0 + blockIdx.x, or pulled from the queue counter
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31u;
   constexpr long SCR_BYTES = (long)tile_smem_fields(!FAST) * TL * 8;

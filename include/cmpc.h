@@ -69,7 +69,7 @@ typedef struct {
   double eps_abs, eps_rel;
   double sigma;                  /* accepted for OSQP compatibility, unused: W_x, W_u > 0 make the
                                     x-update strictly convex without a proximal term */
-  double alpha, rho, delta, adaptive_rho_tolerance;
+  double alpha /* relaxation; default 1.8 (OSQP: 1.6), 1.6 for the wrench model */, rho, delta, adaptive_rho_tolerance;
   int32_t max_iter, check_termination /* default 25 as in OSQP; every polish attempt checks too */, polish,
       polish_refine_iter, adaptive_rho;
   int32_t adaptive_rho_start;    /* first ADMM iteration at which rho may be adapted */
